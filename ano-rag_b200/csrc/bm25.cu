@@ -1,0 +1,462 @@
+// BM25 scoring over a block-partitioned inverted index (sm_100a).
+//
+// Replaces corpus.get_scores() at reference utils/bm25_search.py:309 (rank_bm25
+// BM25Okapi) / :43-63 (SimpleBM25) and the max-normalisation :329-333.
+//
+// Bit-exactness: the reference adds, per query token in order,
+//     idf[t] * ( tf*(k1+1) / (tf + k1*(1 - b + b*dl/avgdl)) )          (fp64)
+// to every doc.  The parenthesised factor depends only on (tf, dl); the host
+// tabulates it once per distinct pair with the reference's own numpy expression
+// (`gtab`), a posting stores the table index, and the kernel performs exactly the
+// two remaining roundings: one fp64 multiply and one fp64 add, token by token in
+// query order (a block barrier separates tokens, so no two tokens race on a doc).
+//
+// Layout in HBM: postings are term-major, doc-sorted, and cut at doc-block
+// boundaries (DOC_BLOCK = 16384 docs = one 128 KB fp64 accumulator tile in shared
+// memory).  post[i] = (doc % DOC_BLOCK) << 18 | gcode  (4 B per posting);
+// blk_off[t*NB + b] is where block b of term t starts.
+#include "common.cuh"
+
+#include <algorithm>
+#include <mutex>
+#include <vector>
+
+namespace arb {
+
+constexpr int DOC_BLOCK_LOG2 = 14;
+constexpr int DOC_BLOCK = 1 << DOC_BLOCK_LOG2;       // docs per accumulator tile
+constexpr int GCODE_BITS = 18;
+constexpr uint32_t GCODE_MASK = (1u << GCODE_BITS) - 1u;
+constexpr int BM25_THREADS = 1024;
+constexpr int CAND_CAP = 2048;                        // candidate buffer (power of two)
+constexpr int GTAB_SMEM = 4096;                       // g-table entries cached in smem
+constexpr int BM25_SMEM = DOC_BLOCK * 8 + CAND_CAP * 12 + GTAB_SMEM * 8 + 2 * ARB_MAX_QUERY_TERMS * 4 + 64;
+
+struct Bm25Dev {
+  int64_t n_docs, n_terms, n_post;
+  int nb;                       // doc blocks
+  int n_g;
+  const uint32_t* blk_off;      // [n_terms*nb + 1]
+  const uint32_t* post;         // [n_post]
+  const double* idf;            // [n_terms]
+  const double* gtab;           // [n_g]
+};
+
+// ---------------------------------------------------------------- build kernels
+__global__ void bm25_pack_kernel(const int32_t* __restrict__ doc, const int32_t* __restrict__ gcode, int64_t n,
+                                 uint32_t* __restrict__ post) {
+  int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  if (i < n) post[i] = (static_cast<uint32_t>(doc[i]) & (DOC_BLOCK - 1)) << GCODE_BITS | (static_cast<uint32_t>(gcode[i]) & GCODE_MASK);
+}
+
+// one thread per (term, block): first posting of term t whose doc >= b*DOC_BLOCK
+__global__ void bm25_blkoff_kernel(const int64_t* __restrict__ term_ptr, const int32_t* __restrict__ doc,
+                                   int64_t n_terms, int nb, int64_t n_post, uint32_t* __restrict__ blk_off) {
+  int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  if (i == n_terms * nb) { blk_off[i] = static_cast<uint32_t>(n_post); return; }
+  if (i > n_terms * nb) return;
+  const int64_t t = i / nb;
+  const int32_t lo_doc = static_cast<int32_t>(i % nb) << DOC_BLOCK_LOG2;
+  int64_t lo = term_ptr[t], hi = term_ptr[t + 1];
+  while (lo < hi) {
+    int64_t mid = (lo + hi) >> 1;
+    if (doc[mid] < lo_doc) lo = mid + 1; else hi = mid;
+  }
+  blk_off[i] = static_cast<uint32_t>(lo);
+}
+
+// ---------------------------------------------------------------- scoring core
+struct Bm25Smem {
+  double* acc;                  // [DOC_BLOCK]
+  unsigned long long* ckey;     // [CAND_CAP]
+  uint32_t* cdoc;               // [CAND_CAP]
+  double* gtab;                 // [GTAB_SMEM]
+  uint32_t* range;              // [2*MAX_QUERY_TERMS]
+  int* misc;                    // [0] candidate count
+};
+
+__device__ __forceinline__ Bm25Smem carve(uint8_t* base) {
+  Bm25Smem s;
+  s.acc = reinterpret_cast<double*>(base);
+  s.ckey = reinterpret_cast<unsigned long long*>(base + DOC_BLOCK * 8);
+  s.gtab = reinterpret_cast<double*>(base + DOC_BLOCK * 8 + CAND_CAP * 8);
+  s.cdoc = reinterpret_cast<uint32_t*>(base + DOC_BLOCK * 8 + CAND_CAP * 8 + GTAB_SMEM * 8);
+  s.range = s.cdoc + CAND_CAP;
+  s.misc = reinterpret_cast<int*>(s.range + 2 * ARB_MAX_QUERY_TERMS);
+  return s;
+}
+
+// Accumulate the scores of one doc block for one query into s.acc (fp64, query
+// token order).  All threads of the CTA call this; ends with a barrier.
+__device__ __forceinline__ void bm25_accumulate_block(const Bm25Dev& ix, const Bm25Smem& s, const int32_t* q_terms,
+                                                      int max_qt, int b, bool g_in_smem) {
+  const int tid = threadIdx.x;
+  for (int i = tid; i < DOC_BLOCK / 2; i += BM25_THREADS) reinterpret_cast<double2*>(s.acc)[i] = make_double2(0.0, 0.0);
+  if (tid < max_qt) {
+    const int t = q_terms[tid];
+    uint32_t lo = 0, hi = 0;
+    if (t >= 0 && t < ix.n_terms) {
+      lo = __ldg(ix.blk_off + static_cast<int64_t>(t) * ix.nb + b);
+      hi = __ldg(ix.blk_off + static_cast<int64_t>(t) * ix.nb + b + 1);
+    }
+    s.range[2 * tid] = lo;
+    s.range[2 * tid + 1] = hi;
+  }
+  __syncthreads();
+  for (int j = 0; j < max_qt; ++j) {
+    const uint32_t lo = s.range[2 * j], hi = s.range[2 * j + 1];
+    if (lo == hi) continue;                                   // uniform across the CTA
+    const double idf = __ldg(ix.idf + q_terms[j]);
+    if (idf != 0.0) {                                          // (idf.get(q) or 0): adds +0.0, a no-op
+      for (uint32_t i = lo + tid; i < hi; i += BM25_THREADS) {
+        const uint32_t u = __ldg(ix.post + i);
+        const uint32_t code = u & GCODE_MASK;
+        const double g = g_in_smem ? s.gtab[code] : __ldg(ix.gtab + code);
+        const uint32_t d = u >> GCODE_BITS;
+        s.acc[d] = __dadd_rn(s.acc[d], __dmul_rn(idf, g));
+      }
+    }
+    __syncthreads();
+  }
+}
+
+// block-wide bitonic sort of (ckey desc, cdoc asc) over CAND_CAP slots
+__device__ __forceinline__ void bitonic_sort_cands(const Bm25Smem& s) {
+  const int tid = threadIdx.x;
+  for (int size = 2; size <= CAND_CAP; size <<= 1) {
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+      __syncthreads();
+      for (int i = tid; i < CAND_CAP / 2; i += BM25_THREADS) {
+        const int lo = 2 * i - (i & (stride - 1));
+        const int hi = lo + stride;
+        const bool desc_block = ((lo & size) == 0);            // first-half blocks sort "best first"
+        const unsigned long long ka = s.ckey[lo], kb = s.ckey[hi];
+        const uint32_t da = s.cdoc[lo], db = s.cdoc[hi];
+        const bool a_before_b = (ka > kb) || (ka == kb && da < db);
+        if (a_before_b != desc_block) {
+          s.ckey[lo] = kb; s.ckey[hi] = ka;
+          s.cdoc[lo] = db; s.cdoc[hi] = da;
+        }
+      }
+    }
+  }
+  __syncthreads();
+}
+
+// Top-k kernel: grid (nq, n_split).  Each CTA walks its doc blocks in ascending
+// order keeping a running candidate set; a candidate must beat the current k-th
+// score strictly, which is exact because later docs have larger ids.
+__global__ void __launch_bounds__(BM25_THREADS, 1)
+bm25_topk_kernel(const Bm25Dev ix, const int32_t* __restrict__ q_terms_all, int max_qt, int k, int64_t id_base,
+                 int blocks_per_split, int64_t nq, double* __restrict__ part_scores, int64_t* __restrict__ part_ids) {
+  extern __shared__ __align__(16) uint8_t bsm[];
+  const Bm25Smem s = carve(bsm);
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int64_t q = blockIdx.x;
+  const int split = blockIdx.y;
+  const int32_t* q_terms = q_terms_all + q * max_qt;
+  const bool g_in_smem = ix.n_g <= GTAB_SMEM;
+  if (g_in_smem) for (int i = tid; i < ix.n_g; i += BM25_THREADS) s.gtab[i] = ix.gtab[i];
+  for (int i = tid; i < CAND_CAP; i += BM25_THREADS) { s.ckey[i] = 0ull; s.cdoc[i] = 0xFFFFFFFFu; }
+  if (tid == 0) s.misc[0] = 0;
+  __syncthreads();
+
+  double thr = 0.0;                               // docs with score <= 0 are never candidates
+  const int b0 = split * blocks_per_split;
+  const int b1 = min(b0 + blocks_per_split, ix.nb);
+  for (int b = b0; b < b1; ++b) {
+    bm25_accumulate_block(ix, s, q_terms, max_qt, b, g_in_smem);
+    const int64_t doc0 = static_cast<int64_t>(b) << DOC_BLOCK_LOG2;
+    const int n_here = static_cast<int>(min(static_cast<long long>(DOC_BLOCK), static_cast<long long>(ix.n_docs - doc0)));
+    for (int base = 0; base < n_here; base += BM25_THREADS) {
+      const int d = base + tid;
+      const double v = d < n_here ? s.acc[d] : 0.0;
+      const bool pass = v > thr;
+      const uint32_t m = __ballot_sync(0xffffffffu, pass);
+      int pos = 0;
+      if (lane == 0 && m) pos = atomicAdd(&s.misc[0], __popc(m));
+      pos = __shfl_sync(0xffffffffu, pos, 0);
+      if (pass) {
+        const int slot = pos + __popc(m & ((1u << lane) - 1u));
+        s.ckey[slot] = f64_key(v);
+        s.cdoc[slot] = static_cast<uint32_t>(doc0 + d);
+      }
+      __syncthreads();
+      const int cnt = s.misc[0];
+      if (cnt > CAND_CAP - BM25_THREADS) {        // next sweep could overflow: keep the k best
+        bitonic_sort_cands(s);
+        const int keep = min(cnt, k);
+        if (cnt >= k) thr = key_f64(s.ckey[k - 1]);
+        __syncthreads();
+        for (int i = keep + tid; i < CAND_CAP; i += BM25_THREADS) { s.ckey[i] = 0ull; s.cdoc[i] = 0xFFFFFFFFu; }
+        if (tid == 0) s.misc[0] = keep;
+        __syncthreads();
+      }
+    }
+    __syncthreads();
+  }
+  bitonic_sort_cands(s);
+  const int cnt = min(s.misc[0], k);
+  double* os = part_scores + (static_cast<int64_t>(split) * nq + q) * k;
+  int64_t* oi = part_ids + (static_cast<int64_t>(split) * nq + q) * k;
+  for (int i = tid; i < k; i += BM25_THREADS) {
+    if (i < cnt) { os[i] = key_f64(s.ckey[i]); oi[i] = id_base + static_cast<int64_t>(s.cdoc[i]); }
+    else         { os[i] = 0.0; oi[i] = -1; }
+  }
+}
+
+// Full score vectors: grid (nq, nb); out[q, doc] for doc < n_out.
+__global__ void __launch_bounds__(BM25_THREADS, 1)
+bm25_scores_kernel(const Bm25Dev ix, const int32_t* __restrict__ q_terms_all, int max_qt, int64_t n_out,
+                   double* __restrict__ out) {
+  extern __shared__ __align__(16) uint8_t bsm[];
+  const Bm25Smem s = carve(bsm);
+  const int tid = threadIdx.x;
+  const int64_t q = blockIdx.x;
+  const int b = blockIdx.y;
+  const bool g_in_smem = ix.n_g <= GTAB_SMEM;
+  if (g_in_smem) for (int i = tid; i < ix.n_g; i += BM25_THREADS) s.gtab[i] = ix.gtab[i];
+  __syncthreads();
+  bm25_accumulate_block(ix, s, q_terms_all + q * max_qt, max_qt, b, g_in_smem);
+  const int64_t doc0 = static_cast<int64_t>(b) << DOC_BLOCK_LOG2;
+  const long long lim = min(min(static_cast<long long>(ix.n_docs), static_cast<long long>(n_out)) - static_cast<long long>(doc0), static_cast<long long>(DOC_BLOCK));
+  for (int64_t d = tid; d < lim; d += BM25_THREADS) out[q * n_out + doc0 + d] = s.acc[d];
+}
+
+// utils/bm25_search.py:329-333: divide by the max when it is > 0.  One CTA per query.
+__global__ void __launch_bounds__(1024)
+bm25_normalise_kernel(double* __restrict__ out, int64_t n_out) {
+  __shared__ double red[32];
+  double* row = out + blockIdx.x * n_out;
+  double m = -INFINITY;
+  for (int64_t i = threadIdx.x; i < n_out; i += blockDim.x) m = fmax(m, row[i]);
+  for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    m = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : -INFINITY;
+    for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if (threadIdx.x == 0) red[0] = m;
+  }
+  __syncthreads();
+  m = red[0];
+  if (m > 0.0)
+    for (int64_t i = threadIdx.x; i < n_out; i += blockDim.x) row[i] = __ddiv_rn(row[i], m);
+}
+
+__global__ void fill_f64_kernel(double* p, double v, int64_t n) {
+  int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  if (i < n) p[i] = v;
+}
+
+int merge_topk_device(int score_dtype, const void* scores, const int64_t* ids, int parts, int64_t nq, int k,
+                      void* out_scores, int64_t* out_ids, cudaStream_t st);   // fuse.cu
+
+}  // namespace arb
+
+using namespace arb;
+
+struct arb_bm25 {
+  Bm25Dev dev;
+  uint32_t* blk_off = nullptr;
+  uint32_t* post = nullptr;
+  double* idf = nullptr;
+  double* gtab = nullptr;
+  std::vector<int64_t> df;      // host copy of per-term df (roofline accounting)
+};
+
+static int bm25_set_smem_attrs() {
+  static std::once_flag once;
+  static cudaError_t err = cudaSuccess;
+  std::call_once(once, [] {
+    err = cudaFuncSetAttribute(bm25_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, BM25_SMEM);
+    if (err == cudaSuccess)
+      err = cudaFuncSetAttribute(bm25_scores_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, BM25_SMEM);
+  });
+  ARB_CUDA(err);
+  return ARB_OK;
+}
+
+extern "C" int arb_bm25_create(arb_bm25** out, int64_t n_docs, int64_t n_terms, const int64_t* term_ptr,
+                               const int32_t* post_doc, const int32_t* post_gcode, const double* idf,
+                               const double* gtab, int64_t n_g, void* stream) {
+  ARB_CHECK(out != nullptr, ARB_EINVAL, "arb_bm25_create: out is NULL");
+  ARB_CHECK(n_docs >= 0 && n_docs < (int64_t(1) << 31), ARB_ELIMIT, "arb_bm25_create: n_docs must be < 2^31");
+  ARB_CHECK(n_terms >= 0 && term_ptr != nullptr, ARB_EINVAL, "arb_bm25_create: bad term table");
+  ARB_CHECK(n_g >= 0 && n_g <= (int64_t(1) << GCODE_BITS), ARB_ELIMIT, "arb_bm25_create: more than 2^18 distinct (tf, doc_len) pairs");
+  const int64_t n_post = term_ptr[n_terms];
+  ARB_CHECK(n_post >= 0 && n_post < 0xFFFFFFF0ll, ARB_ELIMIT, "arb_bm25_create: more than 2^32 postings per shard");
+  ARB_CHECK(n_post == 0 || (post_doc && post_gcode && idf && gtab), ARB_EINVAL, "arb_bm25_create: NULL posting arrays");
+  const int nb = static_cast<int>(std::max<int64_t>(1, (n_docs + DOC_BLOCK - 1) / DOC_BLOCK));
+  ARB_CHECK(n_terms * nb < 0x7FFFFFF0ll, ARB_ELIMIT, "arb_bm25_create: n_terms * doc_blocks too large");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+
+  arb_bm25* bm = new arb_bm25();
+  auto fail = [&](int rc) { arb_bm25_destroy(bm); return rc; };
+  const size_t n_off = static_cast<size_t>(n_terms) * nb + 1;
+  if (cudaMalloc(&bm->blk_off, n_off * 4) != cudaSuccess || cudaMalloc(&bm->post, std::max<size_t>(n_post, 1) * 4) != cudaSuccess ||
+      cudaMalloc(&bm->idf, std::max<size_t>(n_terms, 1) * 8) != cudaSuccess || cudaMalloc(&bm->gtab, std::max<size_t>(n_g, 1) * 8) != cudaSuccess) {
+    cudaGetLastError();
+    set_error("arb_bm25_create: out of device memory");
+    return fail(ARB_ENOMEM);
+  }
+  {
+    AsyncBuf d_ptr, d_doc, d_code;
+    if (d_ptr.alloc((n_terms + 1) * 8, st) != cudaSuccess || d_doc.alloc(std::max<size_t>(n_post, 1) * 4, st) != cudaSuccess ||
+        d_code.alloc(std::max<size_t>(n_post, 1) * 4, st) != cudaSuccess) {
+      cudaGetLastError();
+      set_error("arb_bm25_create: out of device memory (staging)");
+      return fail(ARB_ENOMEM);
+    }
+    cudaError_t e = cudaMemcpyAsync(d_ptr.p, term_ptr, (n_terms + 1) * 8, cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess && n_post) e = cudaMemcpyAsync(d_doc.p, post_doc, n_post * 4, cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess && n_post) e = cudaMemcpyAsync(d_code.p, post_gcode, n_post * 4, cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess && n_terms) e = cudaMemcpyAsync(bm->idf, idf, n_terms * 8, cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess && n_g) e = cudaMemcpyAsync(bm->gtab, gtab, n_g * 8, cudaMemcpyHostToDevice, st);
+    if (e != cudaSuccess) return fail(cuda_fail(e, "bm25 H2D", __FILE__, __LINE__));
+    if (n_post) {
+      bm25_pack_kernel<<<static_cast<unsigned>((n_post + 255) / 256), 256, 0, st>>>(d_doc.as<int32_t>(), d_code.as<int32_t>(), n_post, bm->post);
+      count_launch();
+    }
+    bm25_blkoff_kernel<<<static_cast<unsigned>((n_off + 255) / 256), 256, 0, st>>>(d_ptr.as<int64_t>(), d_doc.as<int32_t>(), n_terms, nb, n_post, bm->blk_off);
+    count_launch();
+    e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) return fail(cuda_fail(e, "bm25 build kernels", __FILE__, __LINE__));
+  }
+  bm->df.resize(n_terms);
+  for (int64_t t = 0; t < n_terms; ++t) bm->df[t] = term_ptr[t + 1] - term_ptr[t];
+  bm->dev.n_docs = n_docs; bm->dev.n_terms = n_terms; bm->dev.n_post = n_post;
+  bm->dev.nb = nb; bm->dev.n_g = static_cast<int>(n_g);
+  bm->dev.blk_off = bm->blk_off; bm->dev.post = bm->post; bm->dev.idf = bm->idf; bm->dev.gtab = bm->gtab;
+  *out = bm;
+  return ARB_OK;
+}
+
+extern "C" int arb_bm25_destroy(arb_bm25* bm) {
+  if (!bm) return ARB_OK;
+  if (bm->blk_off) cudaFree(bm->blk_off);
+  if (bm->post) cudaFree(bm->post);
+  if (bm->idf) cudaFree(bm->idf);
+  if (bm->gtab) cudaFree(bm->gtab);
+  delete bm;
+  return ARB_OK;
+}
+
+extern "C" int64_t arb_bm25_ndocs(const arb_bm25* bm) { return bm ? bm->dev.n_docs : 0; }
+extern "C" int64_t arb_bm25_npostings(const arb_bm25* bm) { return bm ? bm->dev.n_post : 0; }
+
+extern "C" int64_t arb_bm25_query_postings(const arb_bm25* bm, const int32_t* q_terms, int64_t nq, int max_qt) {
+  if (!bm || !q_terms) return 0;
+  int64_t total = 0;
+  for (int64_t i = 0; i < nq * max_qt; ++i) {
+    const int32_t t = q_terms[i];
+    if (t >= 0 && t < bm->dev.n_terms) total += bm->df[t];
+  }
+  return total;
+}
+
+static int stage_terms(const int32_t* q_terms, int64_t nq, int max_qt, int q_is_device, AsyncBuf& buf,
+                       const int32_t** dev_terms, cudaStream_t st) {
+  if (q_is_device) { *dev_terms = q_terms; return ARB_OK; }
+  ARB_CUDA(buf.alloc(static_cast<size_t>(nq) * max_qt * 4, st));
+  ARB_CUDA(cudaMemcpyAsync(buf.p, q_terms, static_cast<size_t>(nq) * max_qt * 4, cudaMemcpyHostToDevice, st));
+  *dev_terms = buf.as<int32_t>();
+  return ARB_OK;
+}
+
+extern "C" int arb_bm25_search(const arb_bm25* bm, const int32_t* q_terms, int64_t nq, int max_qt, int q_is_device,
+                               int k, int64_t id_base, double* out_scores, int64_t* out_ids, int out_is_device,
+                               void* stream) {
+  ARB_CHECK(bm != nullptr, ARB_EINVAL, "arb_bm25_search: NULL index");
+  ARB_CHECK(nq >= 0 && (q_terms != nullptr || nq == 0), ARB_EINVAL, "arb_bm25_search: bad q_terms/nq");
+  ARB_CHECK(max_qt >= 1 && max_qt <= ARB_MAX_QUERY_TERMS, ARB_ELIMIT, "arb_bm25_search: max_qt must be in [1, 64]");
+  ARB_CHECK(k >= 1 && k <= ARB_MAX_TOPK, ARB_ELIMIT, "arb_bm25_search: k must be in [1, 256]");
+  ARB_CHECK(out_scores != nullptr && out_ids != nullptr, ARB_EINVAL, "arb_bm25_search: NULL output");
+  ARB_CHECK(nq <= 2147483647ll, ARB_ELIMIT, "arb_bm25_search: too many queries");
+  if (nq == 0) return ARB_OK;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  int rc = bm25_set_smem_attrs();
+  if (rc) return rc;
+  AsyncBuf tbuf, pscores, pids, oscores, oids;
+  const int32_t* d_terms = nullptr;
+  rc = stage_terms(q_terms, nq, max_qt, q_is_device, tbuf, &d_terms, st);
+  if (rc) return rc;
+
+  // few queries: cut the doc blocks over several CTAs per query and merge
+  const int sms = num_sms();
+  int n_split = 1;
+  if (nq < sms) n_split = static_cast<int>(std::min<int64_t>(bm->dev.nb, (sms + nq - 1) / nq));
+  n_split = std::max(1, std::min(n_split, 8192 / k));
+  const int bps = (bm->dev.nb + n_split - 1) / n_split;
+  n_split = (bm->dev.nb + bps - 1) / bps;
+
+  double* d_scores = out_scores;
+  int64_t* d_ids = out_ids;
+  if (!out_is_device) {
+    ARB_CUDA(oscores.alloc(static_cast<size_t>(nq) * k * 8, st));
+    ARB_CUDA(oids.alloc(static_cast<size_t>(nq) * k * 8, st));
+    d_scores = oscores.as<double>();
+    d_ids = oids.as<int64_t>();
+  }
+  double* ps = d_scores;
+  int64_t* pi = d_ids;
+  if (n_split > 1) {
+    ARB_CUDA(pscores.alloc(static_cast<size_t>(n_split) * nq * k * 8, st));
+    ARB_CUDA(pids.alloc(static_cast<size_t>(n_split) * nq * k * 8, st));
+    ps = pscores.as<double>();
+    pi = pids.as<int64_t>();
+  }
+  dim3 grid(static_cast<unsigned>(nq), static_cast<unsigned>(n_split));
+  bm25_topk_kernel<<<grid, BM25_THREADS, BM25_SMEM, st>>>(bm->dev, d_terms, max_qt, k, id_base, bps, nq, ps, pi);
+  ARB_LAUNCH_OK();
+  if (n_split > 1) {
+    rc = merge_topk_device(ARB_F64, ps, pi, n_split, nq, k, d_scores, d_ids, st);
+    if (rc) return rc;
+  }
+  if (!out_is_device) {
+    ARB_CUDA(cudaMemcpyAsync(out_scores, d_scores, static_cast<size_t>(nq) * k * 8, cudaMemcpyDeviceToHost, st));
+    ARB_CUDA(cudaMemcpyAsync(out_ids, d_ids, static_cast<size_t>(nq) * k * 8, cudaMemcpyDeviceToHost, st));
+    ARB_CUDA(cudaStreamSynchronize(st));
+  }
+  return ARB_OK;
+}
+
+extern "C" int arb_bm25_scores(const arb_bm25* bm, const int32_t* q_terms, int64_t nq, int max_qt, int q_is_device,
+                               int normalise, int64_t n_out, double* out, int out_is_device, void* stream) {
+  ARB_CHECK(bm != nullptr, ARB_EINVAL, "arb_bm25_scores: NULL index");
+  ARB_CHECK(nq >= 0 && (q_terms != nullptr || nq == 0), ARB_EINVAL, "arb_bm25_scores: bad q_terms/nq");
+  ARB_CHECK(max_qt >= 1 && max_qt <= ARB_MAX_QUERY_TERMS, ARB_ELIMIT, "arb_bm25_scores: max_qt must be in [1, 64]");
+  ARB_CHECK(n_out >= 0 && (out != nullptr || n_out == 0), ARB_EINVAL, "arb_bm25_scores: bad output");
+  ARB_CHECK(nq <= 65535 * 64ll, ARB_ELIMIT, "arb_bm25_scores: too many queries in one call");
+  if (nq == 0 || n_out == 0) return ARB_OK;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  int rc = bm25_set_smem_attrs();
+  if (rc) return rc;
+  AsyncBuf tbuf, obuf;
+  const int32_t* d_terms = nullptr;
+  rc = stage_terms(q_terms, nq, max_qt, q_is_device, tbuf, &d_terms, st);
+  if (rc) return rc;
+  double* d_out = out;
+  if (!out_is_device) { ARB_CUDA(obuf.alloc(static_cast<size_t>(nq) * n_out * 8, st)); d_out = obuf.as<double>(); }
+  const int64_t total = nq * n_out;
+  if (n_out > bm->dev.n_docs) {                                // pad slots beyond the corpus with 0.0 (:320-323)
+    fill_f64_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, st>>>(d_out, 0.0, total);
+    ARB_LAUNCH_OK();
+  }
+  const int nb_used = static_cast<int>(std::min<int64_t>(bm->dev.nb, (std::min(n_out, bm->dev.n_docs) + DOC_BLOCK - 1) / DOC_BLOCK));
+  if (nb_used > 0) {
+    dim3 grid(static_cast<unsigned>(nq), static_cast<unsigned>(nb_used));
+    bm25_scores_kernel<<<grid, BM25_THREADS, BM25_SMEM, st>>>(bm->dev, d_terms, max_qt, n_out, d_out);
+    ARB_LAUNCH_OK();
+  }
+  if (normalise) {
+    bm25_normalise_kernel<<<static_cast<unsigned>(nq), 1024, 0, st>>>(d_out, n_out);
+    ARB_LAUNCH_OK();
+  }
+  if (!out_is_device) {
+    ARB_CUDA(cudaMemcpyAsync(out, d_out, static_cast<size_t>(total) * 8, cudaMemcpyDeviceToHost, st));
+    ARB_CUDA(cudaStreamSynchronize(st));
+  }
+  return ARB_OK;
+}

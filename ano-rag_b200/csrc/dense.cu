@@ -1,0 +1,694 @@
+// Dense exact inner-product top-k for B200 (sm_100a).
+//
+// Replaces faiss.IndexFlatIP.search as called at reference
+// vector_store/vector_index.py:223 (and the row pre-processing :265-282).
+//
+//   scores[q, n] = sum over "terms" of  Qplane_a[q, :] . Xplane_b[n, :]
+//
+// runs as a persistent, warp-specialised tcgen05 GEMM (bf16 operands, fp32
+// accumulators in TMEM, operands staged by TMA with the 128B swizzle) whose
+// epilogue never writes the score block: each epilogue thread owns one query row
+// (one TMEM lane), compares every score with that query's running threshold and
+// appends the rare survivors to a small per-(work item, query) candidate list;
+// when a list fills, the warp selects its k best in registers and publishes the
+// k-th score as the new threshold (shared between all CTAs working on that query
+// through one atomicMax).  A second kernel merges the lists to the final top-k.
+//
+// fp32-exact mode: rows are stored as three bf16 planes (hi/mid/lo, exact split of
+// the fp32 value); the six largest cross terms are accumulated in fp32 on the
+// tensor cores, smallest first.
+#include "common.cuh"
+#include "ptx.cuh"
+
+#include <algorithm>
+#include <mutex>
+#include <vector>
+#include <math.h>
+#include <string.h>
+
+namespace arb {
+
+using namespace ptx;
+
+constexpr int BLOCK_M = 128;              // queries per tile (= TMEM lanes)
+constexpr int BLOCK_N = 256;              // corpus rows per tile (= UMMA N)
+constexpr int BLOCK_K = 64;               // bf16 per k-block: one 128 B swizzle row
+constexpr int UMMA_K = 16;
+constexpr int STAGES = 4;
+constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;
+constexpr int B_BYTES = BLOCK_N * BLOCK_K * 2;
+constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+constexpr int ACC_STAGES = 2;
+constexpr int TMEM_COLS = ACC_STAGES * BLOCK_N;   // 512: the whole TMEM of the SM
+constexpr int DENSE_THREADS = 192;                // warp0 TMA, warp1 MMA, warps2-5 epilogue
+constexpr int DENSE_SMEM = STAGES * STAGE_BYTES + 256 + 1024;
+constexpr int MAX_TERMS = 6;
+
+constexpr uint32_t KEY_NEG_INF = 0x007FFFFFu;     // f32_key(-inf)
+
+struct DenseParams {
+  int nq;
+  uint32_t n_rows;
+  int k;
+  int kb_per_term;          // d_pad / 64
+  int n_terms;
+  int a_col[MAX_TERMS];     // element offset of the plane inside a query row
+  int b_col[MAX_TERMS];     // element offset of the plane inside a corpus row
+  int n_qtiles, n_splits, tiles_per_split, n_ntiles, n_items;
+  uint2* lists;             // [n_items, 128, C] {row index, ordered score key}
+  int* counts;              // [n_items, 128]
+  uint32_t* gthr;           // [n_qtiles*128] shared per-query threshold key
+};
+
+// ----------------------------------------------------------------------------
+// Warp-cooperative selection: keep the k largest of list[0..cnt) (cnt <= 32*EPL)
+// in list[0..k), return the k-th largest key.  Exact ties at the k-th key are
+// filled in list order.  All 32 lanes participate.
+// ----------------------------------------------------------------------------
+__device__ __forceinline__ uint2 ld_volatile_u2(const uint2* p) {
+  uint2 v;
+  const volatile uint32_t* q = reinterpret_cast<const volatile uint32_t*>(p);
+  v.x = q[0];
+  v.y = q[1];
+  return v;
+}
+
+template <int EPL, bool GLOBAL>
+__device__ __forceinline__ uint32_t warp_select(uint2* list, int cnt, int k, int lane) {
+  uint32_t key[EPL], idx[EPL];
+  __syncwarp();
+#pragma unroll
+  for (int i = 0; i < EPL; ++i) {
+    int p = lane + 32 * i;
+    uint2 e = make_uint2(0u, 0u);
+    if (p < cnt) { if (GLOBAL) e = __ldcg(list + p); else e = ld_volatile_u2(list + p); }
+    idx[i] = e.x;
+    key[i] = e.y;
+  }
+  uint32_t T = 0;
+#pragma unroll 1
+  for (int bit = 31; bit >= 0; --bit) {
+    uint32_t cand = T | (1u << bit);
+    int c = 0;
+#pragma unroll
+    for (int i = 0; i < EPL; ++i) c += (key[i] >= cand) ? 1 : 0;
+    c = __reduce_add_sync(0xffffffffu, c);
+    if (c >= k) T = cand;
+  }
+  const uint32_t lt = (1u << lane) - 1u;
+  int base = 0;
+  __syncwarp();
+#pragma unroll
+  for (int i = 0; i < EPL; ++i) {
+    bool gt = key[i] > T;
+    uint32_t m = __ballot_sync(0xffffffffu, gt);
+    if (gt) list[base + __popc(m & lt)] = make_uint2(idx[i], key[i]);
+    base += __popc(m);
+  }
+  int need = k - base;
+  int tbase = 0;
+#pragma unroll
+  for (int i = 0; i < EPL; ++i) {
+    bool eq = (key[i] == T) && (T != 0u);
+    uint32_t m = __ballot_sync(0xffffffffu, eq);
+    int r = tbase + __popc(m & lt);
+    if (eq && r < need) list[base + r] = make_uint2(idx[i], key[i]);
+    tbase += __popc(m);
+  }
+  __syncwarp();
+  return T;
+}
+
+// ----------------------------------------------------------------------------
+// The fused GEMM + threshold-select kernel.
+// ----------------------------------------------------------------------------
+template <int EPL>
+__global__ void __launch_bounds__(DENSE_THREADS, 1)
+dense_topk_kernel(const __grid_constant__ CUtensorMap tmap_a,
+                  const __grid_constant__ CUtensorMap tmap_b, const DenseParams p) {
+  constexpr int C = 32 * EPL;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + STAGES;
+  uint64_t* tfull = bars + 2 * STAGES;
+  uint64_t* tempty = tfull + ACC_STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + ACC_STAGES);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tmap_a);
+    prefetch_tmap(&tmap_b);
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    for (int a = 0; a < ACC_STAGES; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], 4); }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
+
+  const int kb_total = p.n_terms * p.kb_per_term;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
+        const int qt = item % p.n_qtiles, sp = item / p.n_qtiles;
+        const int t0 = sp * p.tiles_per_split;
+        const int t1 = min(t0 + p.tiles_per_split, p.n_ntiles);
+        for (int t = t0; t < t1; ++t) {
+          for (int term = 0; term < p.n_terms; ++term) {
+            for (int kb = 0; kb < p.kb_per_term; ++kb) {
+              mbar_wait(&empty[stage], phase ^ 1u);
+              uint8_t* sa = smem + stage * STAGE_BYTES;
+              mbar_expect_tx(&full[stage], STAGE_BYTES);
+              tma_load_2d(&tmap_a, &full[stage], sa, p.a_col[term] + kb * BLOCK_K, qt * BLOCK_M, EVICT_LAST);
+              tma_load_2d(&tmap_b, &full[stage], sa + A_BYTES, p.b_col[term] + kb * BLOCK_K, t * BLOCK_N, EVICT_NORMAL);
+              if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(BLOCK_M, BLOCK_N);
+      int stage = 0; uint32_t phase = 0;
+      int acc = 0; uint32_t acc_phase = 0;
+      for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
+        const int sp = item / p.n_qtiles;
+        const int t0 = sp * p.tiles_per_split;
+        const int t1 = min(t0 + p.tiles_per_split, p.n_ntiles);
+        for (int t = t0; t < t1; ++t) {
+          mbar_wait(&tempty[acc], acc_phase ^ 1u);
+          tc_fence_after();
+          const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
+          for (int kb = 0; kb < kb_total; ++kb) {
+            mbar_wait(&full[stage], phase);
+            tc_fence_after();
+            const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
+            const uint64_t a_desc = umma_desc_k_sw128(sa);
+            const uint64_t b_desc = umma_desc_k_sw128(sa + A_BYTES);
+#pragma unroll
+            for (int kk = 0; kk < BLOCK_K / UMMA_K; ++kk) {
+              // +32 B per UMMA_K inside the 128 B swizzle row -> +2 in 16 B units
+              umma_bf16(d_tmem, a_desc + 2 * kk, b_desc + 2 * kk, idesc, (kb | kk) != 0 ? 1u : 0u);
+            }
+            umma_commit(&empty[stage]);          // frees the smem slot when these MMAs retire
+            if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+          }
+          umma_commit(&tfull[acc]);              // accumulator complete -> epilogue
+          if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1u; }
+        }
+      }
+    }
+  } else {
+    // ------------------------------------------------------------ epilogue (4 warps)
+    const int quad = warp & 3;                   // TMEM lane quadrant this warp may read
+    const int row = quad * 32 + lane;            // query row inside the tile
+    int acc = 0; uint32_t acc_phase = 0;
+    for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
+      const int qt = item % p.n_qtiles, sp = item / p.n_qtiles;
+      const int t0 = sp * p.tiles_per_split;
+      const int t1 = min(t0 + p.tiles_per_split, p.n_ntiles);
+      const int q = qt * BLOCK_M + row;
+      const bool valid = q < p.nq;
+      uint2* list = p.lists + (static_cast<size_t>(item) * BLOCK_M + row) * C;
+      int cnt = 0;
+      uint32_t thr_key = KEY_NEG_INF;
+      float thr = valid ? -INFINITY : INFINITY;
+      for (int t = t0; t < t1; ++t) {
+        if (valid) {
+          uint32_t g = __ldcg(p.gthr + q);
+          if (g > thr_key) { thr_key = g; thr = key_f32(g); }
+        }
+        mbar_wait(&tfull[acc], acc_phase);
+        tc_fence_after();
+        const uint32_t n_base = static_cast<uint32_t>(t) * BLOCK_N;
+        const bool tail = n_base + BLOCK_N > p.n_rows;
+        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * BLOCK_N;
+#pragma unroll 1
+        for (int c = 0; c < BLOCK_N / 32; ++c) {
+          uint32_t v[32];
+          tmem_ld_32x32(taddr + c * 32, v);
+          tmem_ld_wait();
+          if (c == BLOCK_N / 32 - 1) {
+            // all of this warp's reads of the accumulator are done: hand it back
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty[acc]);
+          }
+          const uint32_t idx0 = n_base + c * 32;
+          if (!tail) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              float s = __uint_as_float(v[j]);
+              if (s > thr) { list[cnt] = make_uint2(idx0 + j, f32_key(s)); ++cnt; }
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              float s = __uint_as_float(v[j]);
+              if (s > thr && idx0 + j < p.n_rows) { list[cnt] = make_uint2(idx0 + j, f32_key(s)); ++cnt; }
+            }
+          }
+          uint32_t need = __ballot_sync(0xffffffffu, cnt > C - 32);
+          while (need) {
+            const int r = __ffs(need) - 1;
+            need &= need - 1;
+            uint2* l = reinterpret_cast<uint2*>(__shfl_sync(0xffffffffu, reinterpret_cast<unsigned long long>(list), r));
+            const int c_r = __shfl_sync(0xffffffffu, cnt, r);
+            const uint32_t T = warp_select<EPL, true>(l, c_r, p.k, lane);
+            if (lane == r) {
+              cnt = p.k;
+              if (T > thr_key) { thr_key = T; thr = key_f32(T); }
+              atomicMax(p.gthr + q, T);
+            }
+          }
+        }
+        if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1u; }
+      }
+      p.counts[static_cast<size_t>(item) * BLOCK_M + row] = valid ? cnt : 0;
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
+// ----------------------------------------------------------------------------
+// Merge the per-item candidate lists of each query into its final top-k.
+// One warp per query.
+// ----------------------------------------------------------------------------
+template <int EPL>
+__global__ void __launch_bounds__(128)
+dense_merge_kernel(const DenseParams p, int64_t id_base, float* __restrict__ out_scores,
+                   int64_t* __restrict__ out_ids) {
+  constexpr int C = 32 * EPL;
+  extern __shared__ uint8_t msmem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q = blockIdx.x * (blockDim.x >> 5) + warp;
+  if (q >= p.nq) return;
+  uint2* buf = reinterpret_cast<uint2*>(msmem) + static_cast<size_t>(warp) * C;
+  const int qt = q / BLOCK_M, row = q % BLOCK_M;
+  const uint32_t lt = (1u << lane) - 1u;
+  uint32_t thr_key = p.gthr[q];
+  int cnt = 0;
+  for (int sp = 0; sp < p.n_splits; ++sp) {
+    const size_t slot = (static_cast<size_t>(sp) * p.n_qtiles + qt) * BLOCK_M + row;
+    const uint2* L = p.lists + slot * C;
+    const int n = p.counts[slot];
+    for (int b = 0; b < n; b += 32) {
+      uint2 e = make_uint2(0u, 0u);
+      if (b + lane < n) e = L[b + lane];
+      const bool pass = (b + lane < n) && e.y >= thr_key;
+      const uint32_t m = __ballot_sync(0xffffffffu, pass);
+      if (pass) buf[cnt + __popc(m & lt)] = e;
+      cnt += __popc(m);
+      if (cnt > C - 32) {
+        const uint32_t T = warp_select<EPL, false>(buf, cnt, p.k, lane);
+        cnt = p.k;
+        thr_key = max(thr_key, T);
+      }
+    }
+  }
+  __syncwarp();
+  if (cnt > p.k) { warp_select<EPL, false>(buf, cnt, p.k, lane); cnt = p.k; }
+  __syncwarp();
+  // rank by (score desc, id asc): cnt <= k <= 256, O(cnt^2 / 32) per lane
+  for (int j = lane; j < cnt; j += 32) {
+    const uint2 e = buf[j];
+    int rank = 0;
+    for (int i = 0; i < cnt; ++i) {
+      const uint2 o = ld_volatile_u2(buf + i);
+      rank += (o.y > e.y || (o.y == e.y && o.x < e.x)) ? 1 : 0;
+    }
+    out_scores[static_cast<size_t>(q) * p.k + rank] = key_f32(e.y);
+    out_ids[static_cast<size_t>(q) * p.k + rank] = id_base + static_cast<int64_t>(e.x);
+  }
+  for (int j = cnt + lane; j < p.k; j += 32) {
+    out_scores[static_cast<size_t>(q) * p.k + j] = -3.4028234663852886e38f;   // faiss "no result"
+    out_ids[static_cast<size_t>(q) * p.k + j] = -1;
+  }
+}
+
+__global__ void fill_u32_kernel(uint32_t* p, uint32_t v, size_t n) {
+  size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
+  if (i < n) p[i] = v;
+}
+
+// ----------------------------------------------------------------------------
+// Row pre-processing (vector_index.py:265-282): fp32 cast, optional L2
+// normalisation (norm == 0 -> 1), then bf16 planes.  One warp per row.
+//   planes == 1: round-to-nearest-even bf16
+//   planes == 3: exact truncation split hi/mid/lo (hi+mid+lo == fp32 value)
+// Output row layout: [plane0 d_pad | plane1 d_pad | plane2 d_pad], zero padded.
+// ----------------------------------------------------------------------------
+template <typename Tin>
+__device__ __forceinline__ float load_f32(const Tin* p);
+template <> __device__ __forceinline__ float load_f32<float>(const float* p) { return *p; }
+template <> __device__ __forceinline__ float load_f32<__nv_bfloat16>(const __nv_bfloat16* p) { return __bfloat162float(*p); }
+
+template <typename Tin>
+__global__ void __launch_bounds__(256)
+prep_rows_kernel(const Tin* __restrict__ in, int64_t n, int d, int d_pad, int planes, int normalize,
+                 __nv_bfloat16* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const int64_t r = blockIdx.x * static_cast<int64_t>(blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (r >= n) return;
+  const Tin* src = in + r * d;
+  float inv_norm_den = 1.0f;
+  if (normalize) {
+    float ss = 0.f;
+    for (int i = lane; i < d; i += 32) { float x = load_f32(src + i); ss = fmaf(x, x, ss); }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+    float nrm = sqrtf(ss);
+    inv_norm_den = (nrm == 0.f) ? 1.0f : nrm;
+  }
+  __nv_bfloat16* dst = out + r * static_cast<int64_t>(planes) * d_pad;
+  for (int i = lane; i < d_pad; i += 32) {
+    float x = 0.f;
+    if (i < d) {
+      x = load_f32(src + i);
+      if (normalize) x = __fdiv_rn(x, inv_norm_den);
+    }
+    if (planes == 1) {
+      dst[i] = __float2bfloat16_rn(x);
+    } else {
+      float rem = x;
+      for (int pl = 0; pl < planes; ++pl) {
+        float hi = __uint_as_float(__float_as_uint(rem) & 0xFFFF0000u);
+        dst[pl * d_pad + i] = __ushort_as_bfloat16(static_cast<unsigned short>(__float_as_uint(hi) >> 16));
+        rem = __fsub_rn(rem, hi);
+      }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256)
+reconstruct_rows_kernel(const __nv_bfloat16* __restrict__ rows, int64_t n, int d, int d_pad, int planes,
+                        float* __restrict__ out) {
+  const int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  if (i >= n * d) return;
+  const int64_t r = i / d;
+  const int c = static_cast<int>(i % d);
+  const __nv_bfloat16* src = rows + r * static_cast<int64_t>(planes) * d_pad;
+  float acc = 0.f;
+  for (int pl = planes - 1; pl >= 0; --pl) acc = __fadd_rn(acc, __bfloat162float(src[pl * d_pad + c]));
+  out[i] = acc;
+}
+
+// ----------------------------------------------------------------------------
+// Host side
+// ----------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* f = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(f);
+  });
+  return fn;
+}
+
+// bf16 matrix [rows, cols] row-major (pitch = cols), box {64, box_rows}, 128B swizzle.
+static int make_tmap(CUtensorMap* m, const void* base, uint64_t rows, uint64_t cols, uint32_t box_rows) {
+  EncodeTiledFn fn = get_encode_fn();
+  ARB_CHECK(fn != nullptr, ARB_ECUDA, "cuTensorMapEncodeTiled entry point unavailable");
+  cuuint64_t gdim[2] = {cols, rows};
+  cuuint64_t gstride[1] = {cols * 2};
+  cuuint32_t box[2] = {BLOCK_K, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstride, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed with CUresult " + std::to_string(static_cast<int>(r)));
+    return ARB_ECUDA;
+  }
+  return ARB_OK;
+}
+
+}  // namespace arb
+
+using namespace arb;
+
+struct arb_index {
+  int dim = 0, d_pad = 0, storage = 0, planes = 1, normalize = 1;
+  int device = 0;
+  int64_t n = 0, cap = 0;
+  __nv_bfloat16* rows = nullptr;       // [cap, planes*d_pad]
+  size_t row_elems() const { return static_cast<size_t>(planes) * d_pad; }
+};
+
+static int launch_prep(const void* src_dev, int dtype, int64_t n, int d, int d_pad, int planes, int normalize,
+                       __nv_bfloat16* dst, cudaStream_t st) {
+  if (n == 0) return ARB_OK;
+  const int wpb = 8;
+  const unsigned grid = static_cast<unsigned>((n + wpb - 1) / wpb);
+  if (dtype == ARB_F32)
+    prep_rows_kernel<float><<<grid, wpb * 32, 0, st>>>(static_cast<const float*>(src_dev), n, d, d_pad, planes, normalize, dst);
+  else
+    prep_rows_kernel<__nv_bfloat16><<<grid, wpb * 32, 0, st>>>(static_cast<const __nv_bfloat16*>(src_dev), n, d, d_pad, planes, normalize, dst);
+  ARB_LAUNCH_OK();
+  return ARB_OK;
+}
+
+extern "C" int arb_index_create(arb_index** out, int dim, int storage, int normalize) {
+  ARB_CHECK(out != nullptr, ARB_EINVAL, "arb_index_create: out is NULL");
+  ARB_CHECK(dim > 0 && dim <= 8192, ARB_EINVAL, "arb_index_create: dim must be in [1, 8192]");
+  ARB_CHECK(storage == ARB_STORE_BF16 || storage == ARB_STORE_FP32_SPLIT, ARB_EINVAL, "arb_index_create: unknown storage mode");
+  int dev = 0;
+  ARB_CUDA(cudaGetDevice(&dev));
+  arb_index* ix = new arb_index();
+  ix->dim = dim;
+  ix->d_pad = (dim + BLOCK_K - 1) / BLOCK_K * BLOCK_K;
+  ix->storage = storage;
+  ix->planes = storage == ARB_STORE_BF16 ? 1 : 3;
+  ix->normalize = normalize ? 1 : 0;
+  ix->device = dev;
+  *out = ix;
+  return ARB_OK;
+}
+
+extern "C" int arb_index_destroy(arb_index* ix) {
+  if (!ix) return ARB_OK;
+  if (ix->rows) cudaFree(ix->rows);
+  delete ix;
+  return ARB_OK;
+}
+
+extern "C" int arb_index_reset(arb_index* ix) {
+  ARB_CHECK(ix != nullptr, ARB_EINVAL, "arb_index_reset: NULL index");
+  ix->n = 0;
+  return ARB_OK;
+}
+
+extern "C" int64_t arb_index_ntotal(const arb_index* ix) { return ix ? ix->n : 0; }
+extern "C" int arb_index_dim(const arb_index* ix) { return ix ? ix->dim : 0; }
+
+extern "C" int arb_index_add(arb_index* ix, const void* rows, int dtype, int64_t n, int rows_is_device, void* stream) {
+  ARB_CHECK(ix != nullptr, ARB_EINVAL, "arb_index_add: NULL index");
+  ARB_CHECK(n >= 0 && (rows != nullptr || n == 0), ARB_EINVAL, "arb_index_add: bad rows/n");
+  ARB_CHECK(dtype == ARB_F32 || dtype == ARB_BF16, ARB_EINVAL, "arb_index_add: dtype must be ARB_F32 or ARB_BF16");
+  ARB_CHECK(ix->n + n <= 0xFFFFFFF0ll, ARB_ELIMIT, "arb_index_add: more than 2^32 rows per shard");
+  if (n == 0) return ARB_OK;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (ix->n + n > ix->cap) {
+    int64_t ncap = ix->cap + ix->cap / 2;
+    if (ncap < ix->n + n) ncap = ix->n + n;
+    __nv_bfloat16* nr = nullptr;
+    cudaError_t e = cudaMalloc(&nr, static_cast<size_t>(ncap) * ix->row_elems() * 2);
+    if (e != cudaSuccess) { cudaGetLastError(); set_error("arb_index_add: out of device memory"); return ARB_ENOMEM; }
+    if (ix->n > 0) {
+      ARB_CUDA(cudaMemcpyAsync(nr, ix->rows, static_cast<size_t>(ix->n) * ix->row_elems() * 2, cudaMemcpyDeviceToDevice, st));
+      ARB_CUDA(cudaStreamSynchronize(st));
+    }
+    if (ix->rows) cudaFree(ix->rows);
+    ix->rows = nr;
+    ix->cap = ncap;
+  }
+  const size_t esz = dtype == ARB_F32 ? 4 : 2;
+  __nv_bfloat16* dst = ix->rows + static_cast<size_t>(ix->n) * ix->row_elems();
+  if (rows_is_device) {
+    int rc = launch_prep(rows, dtype, n, ix->dim, ix->d_pad, ix->planes, ix->normalize, dst, st);
+    if (rc) return rc;
+  } else {
+    // stage host rows through a bounded device buffer
+    const int64_t chunk = std::max<int64_t>(1, (int64_t(256) << 20) / (ix->dim * esz));
+    AsyncBuf stagebuf;
+    ARB_CUDA(stagebuf.alloc(static_cast<size_t>(std::min(chunk, n)) * ix->dim * esz, st));
+    for (int64_t off = 0; off < n; off += chunk) {
+      const int64_t m = std::min(chunk, n - off);
+      ARB_CUDA(cudaMemcpyAsync(stagebuf.p, static_cast<const char*>(rows) + off * ix->dim * esz,
+                               static_cast<size_t>(m) * ix->dim * esz, cudaMemcpyHostToDevice, st));
+      int rc = launch_prep(stagebuf.p, dtype, m, ix->dim, ix->d_pad, ix->planes, ix->normalize,
+                           dst + static_cast<size_t>(off) * ix->row_elems(), st);
+      if (rc) return rc;
+    }
+    ARB_CUDA(cudaStreamSynchronize(st));
+  }
+  ix->n += n;
+  return ARB_OK;
+}
+
+extern "C" int arb_index_reconstruct(const arb_index* ix, int64_t row0, int64_t n, float* out, int out_is_device, void* stream) {
+  ARB_CHECK(ix != nullptr && out != nullptr, ARB_EINVAL, "arb_index_reconstruct: NULL argument");
+  ARB_CHECK(row0 >= 0 && n >= 0 && row0 + n <= ix->n, ARB_EINVAL, "arb_index_reconstruct: row range outside the index");
+  if (n == 0) return ARB_OK;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  AsyncBuf tmp;
+  float* dev_out = out;
+  if (!out_is_device) { ARB_CUDA(tmp.alloc(static_cast<size_t>(n) * ix->dim * 4, st)); dev_out = tmp.as<float>(); }
+  const int64_t total = n * ix->dim;
+  reconstruct_rows_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, st>>>(
+      ix->rows + static_cast<size_t>(row0) * ix->row_elems(), n, ix->dim, ix->d_pad, ix->planes, dev_out);
+  ARB_LAUNCH_OK();
+  if (!out_is_device) {
+    ARB_CUDA(cudaMemcpyAsync(out, dev_out, static_cast<size_t>(total) * 4, cudaMemcpyDeviceToHost, st));
+    ARB_CUDA(cudaStreamSynchronize(st));
+  }
+  return ARB_OK;
+}
+
+// choose how many corpus splits each query tile is cut into so that the persistent
+// grid finishes in the fewest n-tile steps (ties: fewer splits = fewer lists)
+static void plan_splits(int n_qtiles, int n_ntiles, int grid, int* n_splits, int* tiles_per_split) {
+  long best_cost = -1; int best_s = 1;
+  const int max_s = std::max(1, std::min(n_ntiles, 64 * std::max(1, grid / std::max(1, n_qtiles)) + 8));
+  for (int s = 1; s <= max_s; ++s) {
+    const int tps = (n_ntiles + s - 1) / s;
+    const int s_eff = (n_ntiles + tps - 1) / tps;
+    const long items = static_cast<long>(s_eff) * n_qtiles;
+    const long rounds = (items + grid - 1) / grid;
+    const long cost = rounds * tps * 64 + s_eff;       // makespan first, then fewer lists
+    if (best_cost < 0 || cost < best_cost) { best_cost = cost; best_s = s_eff; }
+  }
+  *n_splits = best_s;
+  *tiles_per_split = (n_ntiles + best_s - 1) / best_s;
+  *n_splits = (n_ntiles + *tiles_per_split - 1) / *tiles_per_split;
+}
+
+template <int EPL>
+static int run_dense(const arb_index* ix, const __nv_bfloat16* qplanes, int q_planes, int64_t nq, int k,
+                     int64_t id_base, float* d_scores, int64_t* d_ids, cudaStream_t st) {
+  constexpr int C = 32 * EPL;
+  DenseParams p;
+  memset(&p, 0, sizeof(p));
+  p.nq = static_cast<int>(nq);
+  p.n_rows = static_cast<uint32_t>(ix->n);
+  p.k = k;
+  p.kb_per_term = ix->d_pad / BLOCK_K;
+  // (query plane, corpus plane) pairs, smallest magnitude first
+  int terms[MAX_TERMS][2]; int nt = 0;
+  if (q_planes == 1 && ix->planes == 1) { terms[nt][0] = 0; terms[nt++][1] = 0; }
+  else if (q_planes == 3 && ix->planes == 1) { for (int a = 2; a >= 0; --a) { terms[nt][0] = a; terms[nt++][1] = 0; } }
+  else if (q_planes == 1 && ix->planes == 3) { for (int b = 2; b >= 0; --b) { terms[nt][0] = 0; terms[nt++][1] = b; } }
+  else {
+    const int order[6][2] = {{2, 0}, {0, 2}, {1, 1}, {1, 0}, {0, 1}, {0, 0}};
+    for (int i = 0; i < 6; ++i) { terms[nt][0] = order[i][0]; terms[nt++][1] = order[i][1]; }
+  }
+  p.n_terms = nt;
+  for (int i = 0; i < nt; ++i) { p.a_col[i] = terms[i][0] * ix->d_pad; p.b_col[i] = terms[i][1] * ix->d_pad; }
+  p.n_qtiles = static_cast<int>((nq + BLOCK_M - 1) / BLOCK_M);
+  p.n_ntiles = static_cast<int>((ix->n + BLOCK_N - 1) / BLOCK_N);
+  const int sms = num_sms();
+  plan_splits(p.n_qtiles, p.n_ntiles, sms, &p.n_splits, &p.tiles_per_split);
+  p.n_items = p.n_splits * p.n_qtiles;
+  const int grid = std::min(sms, p.n_items);
+
+  AsyncBuf lists, counts, gthr;
+  ARB_CUDA(lists.alloc(static_cast<size_t>(p.n_items) * BLOCK_M * C * sizeof(uint2), st));
+  ARB_CUDA(counts.alloc(static_cast<size_t>(p.n_items) * BLOCK_M * sizeof(int), st));
+  ARB_CUDA(gthr.alloc(static_cast<size_t>(p.n_qtiles) * BLOCK_M * sizeof(uint32_t), st));
+  p.lists = lists.as<uint2>();
+  p.counts = counts.as<int>();
+  p.gthr = gthr.as<uint32_t>();
+  const size_t ng = static_cast<size_t>(p.n_qtiles) * BLOCK_M;
+  fill_u32_kernel<<<static_cast<unsigned>((ng + 255) / 256), 256, 0, st>>>(p.gthr, KEY_NEG_INF, ng);
+  ARB_LAUNCH_OK();
+
+  CUtensorMap ta, tb;
+  int rc = make_tmap(&ta, qplanes, static_cast<uint64_t>(nq), static_cast<uint64_t>(q_planes) * ix->d_pad, BLOCK_M);
+  if (rc) return rc;
+  rc = make_tmap(&tb, ix->rows, static_cast<uint64_t>(ix->n), static_cast<uint64_t>(ix->planes) * ix->d_pad, BLOCK_N);
+  if (rc) return rc;
+
+  static std::once_flag attr_once;
+  static cudaError_t attr_err = cudaSuccess;
+  std::call_once(attr_once, [] {
+    attr_err = cudaFuncSetAttribute(dense_topk_kernel<EPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, DENSE_SMEM);
+  });
+  ARB_CUDA(attr_err);
+  dense_topk_kernel<EPL><<<grid, DENSE_THREADS, DENSE_SMEM, st>>>(ta, tb, p);
+  ARB_LAUNCH_OK();
+  const int wpb = 4;
+  dense_merge_kernel<EPL><<<static_cast<unsigned>((nq + wpb - 1) / wpb), wpb * 32, wpb * C * sizeof(uint2), st>>>(
+      p, id_base, d_scores, d_ids);
+  ARB_LAUNCH_OK();
+  return ARB_OK;
+}
+
+extern "C" int arb_index_search(const arb_index* ix, const void* queries, int dtype, int64_t nq, int queries_is_device,
+                                int k, int query_planes, int64_t id_base, float* out_scores, int64_t* out_ids,
+                                int out_is_device, void* stream) {
+  ARB_CHECK(ix != nullptr, ARB_EINVAL, "arb_index_search: NULL index");
+  ARB_CHECK(nq >= 0 && (queries != nullptr || nq == 0), ARB_EINVAL, "arb_index_search: bad queries/nq");
+  ARB_CHECK(out_scores != nullptr && out_ids != nullptr, ARB_EINVAL, "arb_index_search: NULL output");
+  ARB_CHECK(dtype == ARB_F32 || dtype == ARB_BF16, ARB_EINVAL, "arb_index_search: dtype must be ARB_F32 or ARB_BF16");
+  ARB_CHECK(k >= 1 && k <= ARB_MAX_TOPK, ARB_ELIMIT, "arb_index_search: k must be in [1, 256]");
+  ARB_CHECK(query_planes == 1 || query_planes == 3, ARB_EINVAL, "arb_index_search: query_planes must be 1 or 3");
+  ARB_CHECK(nq <= (1 << 24), ARB_ELIMIT, "arb_index_search: at most 2^24 queries per call");
+  ARB_CHECK(ix->n > 0, ARB_EINVAL, "arb_index_search: index is empty");
+  if (nq == 0) return ARB_OK;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const size_t esz = dtype == ARB_F32 ? 4 : 2;
+
+  AsyncBuf qstage, qplanes, oscores, oids;
+  const void* q_dev = queries;
+  if (!queries_is_device) {
+    ARB_CUDA(qstage.alloc(static_cast<size_t>(nq) * ix->dim * esz, st));
+    ARB_CUDA(cudaMemcpyAsync(qstage.p, queries, static_cast<size_t>(nq) * ix->dim * esz, cudaMemcpyHostToDevice, st));
+    q_dev = qstage.p;
+  }
+  ARB_CUDA(qplanes.alloc(static_cast<size_t>(nq) * query_planes * ix->d_pad * 2, st));
+  int rc = launch_prep(q_dev, dtype, nq, ix->dim, ix->d_pad, query_planes, ix->normalize, qplanes.as<__nv_bfloat16>(), st);
+  if (rc) return rc;
+
+  float* d_scores = out_scores;
+  int64_t* d_ids = out_ids;
+  if (!out_is_device) {
+    ARB_CUDA(oscores.alloc(static_cast<size_t>(nq) * k * 4, st));
+    ARB_CUDA(oids.alloc(static_cast<size_t>(nq) * k * 8, st));
+    d_scores = oscores.as<float>();
+    d_ids = oids.as<int64_t>();
+  }
+  if (k <= 128) rc = run_dense<16>(ix, qplanes.as<__nv_bfloat16>(), query_planes, nq, k, id_base, d_scores, d_ids, st);
+  else          rc = run_dense<32>(ix, qplanes.as<__nv_bfloat16>(), query_planes, nq, k, id_base, d_scores, d_ids, st);
+  if (rc) return rc;
+  if (!out_is_device) {
+    ARB_CUDA(cudaMemcpyAsync(out_scores, d_scores, static_cast<size_t>(nq) * k * 4, cudaMemcpyDeviceToHost, st));
+    ARB_CUDA(cudaMemcpyAsync(out_ids, d_ids, static_cast<size_t>(nq) * k * 8, cudaMemcpyDeviceToHost, st));
+    ARB_CUDA(cudaStreamSynchronize(st));
+  }
+  return ARB_OK;
+}

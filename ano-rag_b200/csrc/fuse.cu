@@ -1,0 +1,378 @@
+// Score fusion and top-k merging (sm_100a).
+//
+// fuse_kernel reproduces HybridSearcher.fuse (reference
+// retrieval/hybrid_search.py:34-103) for a batch of queries: per-source
+// max-normalisation + weighted sum ("linear", :83-100) or weighted reciprocal-rank
+// fusion ("rrf", :64-82), stable descending sort (:102) and the candidate_pool cut
+// (:103).  All arithmetic is fp64 with explicit round-to-nearest intrinsics so the
+// compiler cannot contract a*b+c into an FMA: Python evaluates each product and
+// sum separately.
+//
+// merge_topk_kernel merges per-shard / per-split top-k lists (new design, the
+// reference has no sharding): one CTA per query, bitonic sort in shared memory.
+#include "common.cuh"
+
+#include <algorithm>
+#include <mutex>
+
+namespace arb {
+
+constexpr int FUSE_THREADS = 256;
+constexpr int FUSE_MAXK = 256;                 // entries per source
+constexpr int FUSE_HASH = 2048;                // >= 2 * 4 * FUSE_MAXK / ... (load factor <= 0.5)
+constexpr int FUSE_MAXU = 4 * FUSE_MAXK;       // union size bound (also sort size, power of two)
+
+struct FuseParams {
+  int method;
+  double w[4];
+  double rrf_k;
+  int pool;
+  int64_t nq;
+  const int64_t* ids[4];
+  const void* scores[4];
+  int dtype[4];
+  int k[4];
+  int64_t* out_ids;
+  double* out_final;
+  double* out_src;
+  int32_t* out_count;
+};
+
+struct FuseSmem {
+  int64_t ids[4][FUSE_MAXK];
+  double sc[4][FUSE_MAXK];
+  short rank[4][FUSE_MAXK];          // 1-based stable descending rank inside the source (rrf)
+  unsigned long long hkey[FUSE_HASH];
+  short hpos[FUSE_HASH][4];          // position of the id in each source, -1 = absent
+  unsigned long long skey[FUSE_MAXU];
+  uint32_t sseq[FUSE_MAXU];
+  uint32_t sslot[FUSE_MAXU];
+  double hfin[FUSE_HASH];            // final score of the id in hash slot h
+  double maxv[4];
+  int cnt[4];
+  int n_union;
+  double red[FUSE_THREADS / 32];
+};
+
+constexpr unsigned long long HASH_EMPTY = 0xFFFFFFFFFFFFFFFFull;
+
+__device__ __forceinline__ uint32_t hash_id(unsigned long long x) {
+  x ^= x >> 33; x *= 0xff51afd7ed558ccdull; x ^= x >> 33; x *= 0xc4ceb9fe1a85ec53ull; x ^= x >> 33;
+  return static_cast<uint32_t>(x) & (FUSE_HASH - 1);
+}
+
+__global__ void __launch_bounds__(FUSE_THREADS)
+fuse_kernel(const FuseParams p) {
+  extern __shared__ __align__(16) uint8_t fsm_raw[];
+  FuseSmem& s = *reinterpret_cast<FuseSmem*>(fsm_raw);
+  const int tid = threadIdx.x;
+  const int64_t q = blockIdx.x;
+
+  // ---- load the four lists
+  for (int src = 0; src < 4; ++src) {
+    const int ks = p.k[src];
+    for (int j = tid; j < ks; j += FUSE_THREADS) {
+      const int64_t id = p.ids[src] ? p.ids[src][q * ks + j] : -1;
+      double v = 0.0;
+      if (id >= 0) {
+        v = p.dtype[src] == ARB_F32 ? static_cast<double>(static_cast<const float*>(p.scores[src])[q * ks + j])
+                                    : static_cast<const double*>(p.scores[src])[q * ks + j];
+      }
+      s.ids[src][j] = id;
+      s.sc[src][j] = v;
+    }
+  }
+  for (int i = tid; i < FUSE_HASH; i += FUSE_THREADS) {
+    s.hkey[i] = HASH_EMPTY;
+    s.hpos[i][0] = s.hpos[i][1] = s.hpos[i][2] = s.hpos[i][3] = -1;
+  }
+  if (tid < 4) { s.cnt[tid] = 0; s.maxv[tid] = 0.0; }
+  if (tid == 0) s.n_union = 0;
+  __syncthreads();
+
+  // ---- per-source valid count and max (hybrid_search.py:29 `max(scores.values())`)
+  for (int src = 0; src < 4; ++src) {
+    const int ks = p.k[src];
+    double m = -INFINITY; int c = 0;
+    for (int j = tid; j < ks; j += FUSE_THREADS)
+      if (s.ids[src][j] >= 0) { m = fmax(m, s.sc[src][j]); ++c; }
+    for (int o = 16; o > 0; o >>= 1) { m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o)); c += __shfl_xor_sync(0xffffffffu, c, o); }
+    if ((tid & 31) == 0) { s.red[tid >> 5] = m; atomicAdd(&s.cnt[src], c); }
+    __syncthreads();
+    if (tid == 0) {
+      double mm = -INFINITY;
+      for (int w = 0; w < FUSE_THREADS / 32; ++w) mm = fmax(mm, s.red[w]);
+      s.maxv[src] = mm;
+    }
+    __syncthreads();
+  }
+
+  // ---- stable descending rank inside each source (sorted(..., reverse=True) keeps
+  //      the original order of equal scores, hybrid_search.py:67)
+  for (int src = 0; src < 3; ++src) {
+    const int ks = p.k[src];
+    for (int j = tid; j < ks; j += FUSE_THREADS) {
+      if (s.ids[src][j] < 0) { s.rank[src][j] = 0; continue; }
+      const double v = s.sc[src][j];
+      int r = 1;
+      for (int i = 0; i < ks; ++i) {
+        if (s.ids[src][i] < 0) continue;
+        const double o = s.sc[src][i];
+        r += (o > v || (o == v && i < j)) ? 1 : 0;
+      }
+      s.rank[src][j] = static_cast<short>(r);
+    }
+  }
+
+  // ---- union of ids via a shared-memory hash table
+  for (int src = 0; src < 4; ++src) {
+    const int ks = p.k[src];
+    for (int j = tid; j < ks; j += FUSE_THREADS) {
+      const int64_t id = s.ids[src][j];
+      if (id < 0) continue;
+      const unsigned long long key = static_cast<unsigned long long>(id);
+      uint32_t h = hash_id(key);
+      while (true) {
+        const unsigned long long prev = atomicCAS(&s.hkey[h], HASH_EMPTY, key);
+        if (prev == HASH_EMPTY || prev == key) { s.hpos[h][src] = static_cast<short>(j); break; }
+        h = (h + 1) & (FUSE_HASH - 1);
+      }
+    }
+  }
+  __syncthreads();
+
+  // offsets of each source inside the traversal sequence that fixes tie order
+  const int offs[4] = {0, p.k[0], p.k[0] + p.k[1], p.k[0] + p.k[1] + p.k[2]};
+
+  // ---- score every union member
+  for (int i = tid; i < FUSE_MAXU; i += FUSE_THREADS) { s.skey[i] = 0ull; s.sseq[i] = 0xFFFFFFFFu; s.sslot[i] = 0xFFFFFFFFu; }
+  __syncthreads();
+  for (int h = tid; h < FUSE_HASH; h += FUSE_THREADS) {
+    if (s.hkey[h] == HASH_EMPTY) continue;
+    const short pd = s.hpos[h][0], pb = s.hpos[h][1], pg = s.hpos[h][2], pp = s.hpos[h][3];
+    const short pos[4] = {pd, pb, pg, pp};
+    double fin;
+    uint32_t seq = 0;
+    if (p.method == ARB_FUSE_RRF) {
+      if (pd < 0 && pb < 0 && pg < 0) continue;                    // path-only ids are not emitted (:64-82)
+      double acc = 0.0;                                            // ranks.setdefault(nid, 0.0)
+      bool first = true;
+      for (int src = 0; src < 3; ++src) {
+        if (pos[src] < 0) continue;
+        const int r = s.rank[src][pos[src]];
+        acc = __dadd_rn(acc, __ddiv_rn(p.w[src], __dadd_rn(p.rrf_k, static_cast<double>(r))));
+        if (first) { seq = offs[src] + (r - 1); first = false; }
+      }
+      const double pv = pp >= 0 ? s.sc[3][pp] : 0.0;
+      fin = __dadd_rn(acc, __dmul_rn(p.w[3], pv));
+    } else {
+      double nv[3];
+      for (int src = 0; src < 3; ++src) {
+        double v = 0.0;
+        if (pos[src] >= 0) {
+          const double m = s.maxv[src];
+          v = (m == 0.0) ? 0.0 : __ddiv_rn(s.sc[src][pos[src]], m);   // _normalize :26-32
+        }
+        nv[src] = v;
+      }
+      const double pv = pp >= 0 ? s.sc[3][pp] : 0.0;
+      fin = __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(p.w[0], nv[0]), __dmul_rn(p.w[1], nv[1])), __dmul_rn(p.w[2], nv[2])),
+                      __dmul_rn(p.w[3], pv));
+      for (int src = 0; src < 4; ++src) if (pos[src] >= 0) { seq = offs[src] + pos[src]; break; }
+    }
+    const int slot = atomicAdd(&s.n_union, 1);
+    double cmp = (fin == 0.0) ? 0.0 : fin;                          // -0.0 == 0.0 in Python's sort
+    unsigned long long key = f64_key(cmp);
+    if (fin != fin) key = 1ull;                                     // NaN sorts last
+    s.skey[slot] = key;
+    s.sseq[slot] = seq;
+    s.sslot[slot] = static_cast<uint32_t>(h);
+    s.hfin[h] = fin;
+  }
+  __syncthreads();
+
+  // ---- stable descending sort: (final desc, traversal sequence asc)
+  for (int size = 2; size <= FUSE_MAXU; size <<= 1) {
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+      for (int i = tid; i < FUSE_MAXU / 2; i += FUSE_THREADS) {
+        const int lo = 2 * i - (i & (stride - 1));
+        const int hi = lo + stride;
+        const bool best_first = ((lo & size) == 0);
+        const unsigned long long ka = s.skey[lo], kb = s.skey[hi];
+        const uint32_t qa = s.sseq[lo], qb = s.sseq[hi];
+        const bool a_before_b = (ka > kb) || (ka == kb && qa < qb);
+        if (a_before_b != best_first) {
+          s.skey[lo] = kb; s.skey[hi] = ka;
+          s.sseq[lo] = qb; s.sseq[hi] = qa;
+          const uint32_t ta = s.sslot[lo]; s.sslot[lo] = s.sslot[hi]; s.sslot[hi] = ta;
+        }
+      }
+      __syncthreads();
+    }
+  }
+
+  // ---- emit the pool
+  const int n_out = min(s.n_union, p.pool);
+  for (int i = tid; i < p.pool; i += FUSE_THREADS) {
+    int64_t* oid = p.out_ids + q * p.pool + i;
+    double* ofin = p.out_final + q * p.pool + i;
+    double* osrc = p.out_src + (q * p.pool + i) * 4;
+    if (i < n_out) {
+      const uint32_t h = s.sslot[i];
+      *oid = static_cast<int64_t>(s.hkey[h]);
+      *ofin = s.hfin[h];
+      for (int src = 0; src < 4; ++src) {
+        const short ps = s.hpos[h][src];
+        osrc[src] = ps >= 0 ? s.sc[src][ps] : __longlong_as_double(0x7ff8000000000000ll);
+      }
+    } else {
+      *oid = -1; *ofin = 0.0;
+      for (int src = 0; src < 4; ++src) osrc[src] = __longlong_as_double(0x7ff8000000000000ll);
+    }
+  }
+  if (tid == 0) p.out_count[q] = n_out;
+}
+
+// ----------------------------------------------------------------------------
+// merge: scores/ids [parts, nq, k] -> [nq, k]; descending score, ascending id.
+// ----------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256)
+merge_topk_kernel(const T* __restrict__ scores, const int64_t* __restrict__ ids, int parts, int64_t nq, int k,
+                  int n_pow2, T* __restrict__ out_scores, int64_t* __restrict__ out_ids, T pad_score) {
+  extern __shared__ __align__(16) uint8_t msm[];
+  unsigned long long* key = reinterpret_cast<unsigned long long*>(msm);
+  int64_t* id = reinterpret_cast<int64_t*>(msm + static_cast<size_t>(n_pow2) * 8);
+  const int tid = threadIdx.x;
+  const int64_t q = blockIdx.x;
+  const int m = parts * k;
+  for (int i = tid; i < n_pow2; i += blockDim.x) {
+    unsigned long long kk = 0ull; int64_t ii = 0x7fffffffffffffffll;
+    if (i < m) {
+      const int part = i / k, j = i % k;
+      const int64_t v = ids[(static_cast<int64_t>(part) * nq + q) * k + j];
+      if (v >= 0) { ii = v; kk = f64_key(static_cast<double>(scores[(static_cast<int64_t>(part) * nq + q) * k + j])); }
+    }
+    key[i] = kk; id[i] = ii;
+  }
+  __syncthreads();
+  for (int size = 2; size <= n_pow2; size <<= 1) {
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+      for (int i = tid; i < n_pow2 / 2; i += blockDim.x) {
+        const int lo = 2 * i - (i & (stride - 1));
+        const int hi = lo + stride;
+        const bool best_first = ((lo & size) == 0);
+        const unsigned long long ka = key[lo], kb = key[hi];
+        const int64_t ia = id[lo], ib = id[hi];
+        const bool a_before_b = (ka > kb) || (ka == kb && ia < ib);
+        if (a_before_b != best_first) { key[lo] = kb; key[hi] = ka; id[lo] = ib; id[hi] = ia; }
+      }
+      __syncthreads();
+    }
+  }
+  for (int i = tid; i < k; i += blockDim.x) {
+    const bool ok = i < n_pow2 && key[i] != 0ull;
+    out_scores[q * k + i] = ok ? static_cast<T>(key_f64(key[i])) : pad_score;
+    out_ids[q * k + i] = ok ? id[i] : -1;
+  }
+}
+
+int merge_topk_device(int score_dtype, const void* scores, const int64_t* ids, int parts, int64_t nq, int k,
+                      void* out_scores, int64_t* out_ids, cudaStream_t st) {
+  ARB_CHECK(score_dtype == ARB_F32 || score_dtype == ARB_F64, ARB_EINVAL, "merge_topk: score dtype must be f32 or f64");
+  ARB_CHECK(parts >= 1 && k >= 1 && nq >= 0, ARB_EINVAL, "merge_topk: bad shape");
+  const int64_t m = static_cast<int64_t>(parts) * k;
+  ARB_CHECK(m <= 8192, ARB_ELIMIT, "merge_topk: parts * k must be <= 8192");
+  if (nq == 0) return ARB_OK;
+  int n_pow2 = 2;
+  while (n_pow2 < m) n_pow2 <<= 1;
+  const size_t smem = static_cast<size_t>(n_pow2) * 16;
+  static std::once_flag once;
+  static cudaError_t err = cudaSuccess;
+  std::call_once(once, [] {
+    err = cudaFuncSetAttribute(merge_topk_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8192 * 16);
+    if (err == cudaSuccess)
+      err = cudaFuncSetAttribute(merge_topk_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8192 * 16);
+  });
+  ARB_CUDA(err);
+  if (score_dtype == ARB_F32)
+    merge_topk_kernel<float><<<static_cast<unsigned>(nq), 256, smem, st>>>(
+        static_cast<const float*>(scores), ids, parts, nq, k, n_pow2, static_cast<float*>(out_scores), out_ids,
+        -3.4028234663852886e38f);
+  else
+    merge_topk_kernel<double><<<static_cast<unsigned>(nq), 256, smem, st>>>(
+        static_cast<const double*>(scores), ids, parts, nq, k, n_pow2, static_cast<double*>(out_scores), out_ids, 0.0);
+  ARB_LAUNCH_OK();
+  return ARB_OK;
+}
+
+}  // namespace arb
+
+using namespace arb;
+
+extern "C" int arb_merge_topk(int score_dtype, const void* scores, const int64_t* ids, int parts, int64_t nq, int k,
+                              int positive_only, void* out_scores, int64_t* out_ids, void* stream) {
+  (void)positive_only;   // shard lists already exclude non-positive BM25 scores
+  ARB_CHECK(scores && ids && out_scores && out_ids, ARB_EINVAL, "arb_merge_topk: NULL argument");
+  return merge_topk_device(score_dtype, scores, ids, parts, nq, k, out_scores, out_ids, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int arb_fuse(int method, const double weights[4], double rrf_k, int pool, int64_t nq,
+                        const int64_t* const ids[4], const void* const scores[4], const int score_dtype[4],
+                        const int k_src[4], int64_t* out_ids, double* out_final, double* out_src,
+                        int32_t* out_count, int is_device, void* stream) {
+  ARB_CHECK(method == ARB_FUSE_LINEAR || method == ARB_FUSE_RRF, ARB_EINVAL, "arb_fuse: unknown method");
+  ARB_CHECK(weights && ids && scores && score_dtype && k_src, ARB_EINVAL, "arb_fuse: NULL argument");
+  ARB_CHECK(out_ids && out_final && out_src && out_count, ARB_EINVAL, "arb_fuse: NULL output");
+  ARB_CHECK(pool >= 1 && pool <= FUSE_MAXU, ARB_ELIMIT, "arb_fuse: candidate_pool must be in [1, 1024]");
+  ARB_CHECK(nq >= 0 && nq <= 2147483647ll, ARB_EINVAL, "arb_fuse: bad nq");
+  if (nq == 0) return ARB_OK;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  FuseParams p;
+  memset(&p, 0, sizeof(p));
+  p.method = method; p.rrf_k = rrf_k; p.pool = pool; p.nq = nq;
+  AsyncBuf din_ids[4], din_sc[4], d_oid, d_ofin, d_osrc, d_ocnt;
+  for (int sidx = 0; sidx < 4; ++sidx) {
+    p.w[sidx] = weights[sidx];
+    p.k[sidx] = (ids[sidx] && scores[sidx]) ? k_src[sidx] : 0;
+    ARB_CHECK(p.k[sidx] >= 0 && p.k[sidx] <= FUSE_MAXK, ARB_ELIMIT, "arb_fuse: at most 256 entries per source");
+    p.dtype[sidx] = score_dtype[sidx];
+    ARB_CHECK(p.k[sidx] == 0 || p.dtype[sidx] == ARB_F32 || p.dtype[sidx] == ARB_F64, ARB_EINVAL, "arb_fuse: score dtype must be f32 or f64");
+    p.ids[sidx] = p.k[sidx] ? ids[sidx] : nullptr;
+    p.scores[sidx] = p.k[sidx] ? scores[sidx] : nullptr;
+    if (!is_device && p.k[sidx]) {
+      const size_t n = static_cast<size_t>(nq) * p.k[sidx];
+      const size_t esz = p.dtype[sidx] == ARB_F32 ? 4 : 8;
+      ARB_CUDA(din_ids[sidx].alloc(n * 8, st));
+      ARB_CUDA(din_sc[sidx].alloc(n * esz, st));
+      ARB_CUDA(cudaMemcpyAsync(din_ids[sidx].p, ids[sidx], n * 8, cudaMemcpyHostToDevice, st));
+      ARB_CUDA(cudaMemcpyAsync(din_sc[sidx].p, scores[sidx], n * esz, cudaMemcpyHostToDevice, st));
+      p.ids[sidx] = din_ids[sidx].as<int64_t>();
+      p.scores[sidx] = din_sc[sidx].p;
+    }
+  }
+  p.out_ids = out_ids; p.out_final = out_final; p.out_src = out_src; p.out_count = out_count;
+  const size_t np = static_cast<size_t>(nq) * pool;
+  if (!is_device) {
+    ARB_CUDA(d_oid.alloc(np * 8, st)); ARB_CUDA(d_ofin.alloc(np * 8, st));
+    ARB_CUDA(d_osrc.alloc(np * 32, st)); ARB_CUDA(d_ocnt.alloc(static_cast<size_t>(nq) * 4, st));
+    p.out_ids = d_oid.as<int64_t>(); p.out_final = d_ofin.as<double>();
+    p.out_src = d_osrc.as<double>(); p.out_count = d_ocnt.as<int32_t>();
+  }
+  static std::once_flag once;
+  static cudaError_t err = cudaSuccess;
+  std::call_once(once, [] {
+    err = cudaFuncSetAttribute(fuse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sizeof(FuseSmem)));
+  });
+  ARB_CUDA(err);
+  fuse_kernel<<<static_cast<unsigned>(nq), FUSE_THREADS, sizeof(FuseSmem), st>>>(p);
+  ARB_LAUNCH_OK();
+  if (!is_device) {
+    ARB_CUDA(cudaMemcpyAsync(out_ids, p.out_ids, np * 8, cudaMemcpyDeviceToHost, st));
+    ARB_CUDA(cudaMemcpyAsync(out_final, p.out_final, np * 8, cudaMemcpyDeviceToHost, st));
+    ARB_CUDA(cudaMemcpyAsync(out_src, p.out_src, np * 32, cudaMemcpyDeviceToHost, st));
+    ARB_CUDA(cudaMemcpyAsync(out_count, p.out_count, static_cast<size_t>(nq) * 4, cudaMemcpyDeviceToHost, st));
+    ARB_CUDA(cudaStreamSynchronize(st));
+  }
+  return ARB_OK;
+}

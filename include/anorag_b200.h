@@ -1,0 +1,182 @@
+/*
+ * anorag_b200.h -- C ABI of the B200-native candidate-scoring library
+ * (libanorag_b200.so, built from ano-rag_b200/csrc for sm_100a).
+ *
+ * The reference (Kevinwu901113/ano-rag) is pure Python; its "FFI" for this path
+ * is the set of calls it makes into the external faiss / rank_bm25 packages and
+ * its own pure-Python fusion.  Each entry point below replaces one of those call
+ * sites (reference file:line given per function).  The Python classes in
+ * ano-rag_b200/ (VectorIndex, VectorRetriever, bm25_search, HybridSearcher) bind
+ * these symbols with ctypes -- see INTEGRATION.md for the stub.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; no torch / C++ types cross this boundary.
+ *   - every function returns 0 on success, a negative ARB_E* code otherwise;
+ *     arb_last_error() returns a thread-local message for the last failure.
+ *   - `*_is_device` says whether a buffer is device memory (1) or host memory (0);
+ *     host buffers are staged by the library with cudaMemcpyAsync on `stream`
+ *     (pinned host memory keeps that asynchronous).
+ *   - `stream` is a cudaStream_t passed as void* (NULL = default stream).  Work is
+ *     enqueued on it; functions that write HOST outputs synchronise the stream
+ *     before returning, functions with device outputs do not.
+ *   - handles are opaque.  Searches on a handle are re-entrant (per-call,
+ *     stream-ordered scratch; the index is read-only during search); create /
+ *     add / reset / destroy are single-writer.
+ *   - there is NO CPU fallback: without a CUDA device every compute entry point
+ *     fails with ARB_ECUDA.
+ */
+#ifndef ANORAG_B200_H_
+#define ANORAG_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ARB_ABI_VERSION 1
+
+#if defined(__GNUC__)
+#define ARB_API __attribute__((visibility("default")))
+#else
+#define ARB_API
+#endif
+
+#define ARB_OK        0
+#define ARB_EINVAL   -1   /* bad argument                         */
+#define ARB_ECUDA    -2   /* CUDA runtime / driver error          */
+#define ARB_ENOMEM   -3   /* allocation failure                   */
+#define ARB_ELIMIT   -4   /* argument outside a documented limit  */
+
+/* element types of caller buffers */
+#define ARB_F32   0
+#define ARB_BF16  1
+#define ARB_F64   2
+
+/* dense storage modes */
+#define ARB_STORE_BF16       0  /* one bf16 plane per row: bf16(normalised row)            */
+#define ARB_STORE_FP32_SPLIT 1  /* three bf16 planes hi/mid/lo, hi+mid+lo == fp32 row      */
+
+/* fusion methods (retrieval/hybrid_search.py:22) */
+#define ARB_FUSE_LINEAR 0
+#define ARB_FUSE_RRF    1
+
+/* BM25 variants */
+#define ARB_BM25_OKAPI  0  /* rank_bm25.BM25Okapi arithmetic  (b*dl/avgdl)                 */
+#define ARB_BM25_SIMPLE 1  /* utils/bm25_search.py:16-63      (b*(dl/avgdl))               */
+
+#define ARB_MAX_TOPK        256   /* dense and BM25 top-k per call                          */
+#define ARB_MAX_QUERY_TERMS 64    /* BM25 query tokens per query (duplicates count)         */
+
+typedef struct arb_index arb_index;   /* dense flat inner-product index       */
+typedef struct arb_bm25  arb_bm25;    /* BM25 block-partitioned inverted index */
+
+ARB_API int         arb_abi_version(void);
+ARB_API const char* arb_last_error(void);
+/* number of CUDA devices visible, or a negative ARB_E* code */
+ARB_API int         arb_device_count(void);
+/* kernels launched by this library on the calling thread since the last reset
+ * (bench.py reports it as gpu_launches) */
+ARB_API int64_t     arb_launch_count(int reset);
+
+/* ------------------------------------------------------------------------- *
+ * Dense: exact inner-product top-k (replaces faiss.IndexFlatIP behind
+ * VectorIndex -- vector_store/vector_index.py:79 create, :187-196 add,
+ * :223 search, :265-282 pre-processing).
+ * ------------------------------------------------------------------------- */
+
+/* vector_index.py:61-124 (create_index 'Flat' + cosine/IP).  `normalize` != 0
+ * applies the row L2 normalisation of _preprocess_vectors (:276-280) to added
+ * rows and to queries on the device. */
+ARB_API int arb_index_create(arb_index** out, int dim, int storage, int normalize);
+ARB_API int arb_index_destroy(arb_index* index);
+/* vector_index.py:171-204 add_vectors: append `n` rows of `dim` elements
+ * (row-major, `dtype` ARB_F32 or ARB_BF16).  Row order is the id (:194-196). */
+ARB_API int arb_index_add(arb_index* index, const void* rows, int dtype, int64_t n,
+                  int rows_is_device, void* stream);
+ARB_API int arb_index_reset(arb_index* index);                    /* :409-421 reset_index */
+ARB_API int64_t arb_index_ntotal(const arb_index* index);         /* faiss ntotal (:381)   */
+ARB_API int arb_index_dim(const arb_index* index);
+/* stored rows back as fp32 (sum of planes) -- used by save_index (:284-321) */
+ARB_API int arb_index_reconstruct(const arb_index* index, int64_t row0, int64_t n, float* out,
+                          int out_is_device, void* stream);
+
+/* vector_index.py:223 `scores, indices = self.index.search(q, k)`.
+ *   queries       [nq, dim] row-major, ARB_F32 or ARB_BF16
+ *   query_planes  1 = queries rounded to bf16 (one tensor-core pass per plane pair)
+ *                 3 = queries split hi/mid/lo (fp32-exact queries)
+ *   out_scores    [nq, k] fp32, descending; slots beyond ntotal hold -3.4028235e38
+ *   out_ids       [nq, k] int64 = id_base + row; -1 beyond ntotal (faiss contract)
+ * Ties: equal scores are ordered by ascending id.  k <= ARB_MAX_TOPK. */
+ARB_API int arb_index_search(const arb_index* index, const void* queries, int dtype, int64_t nq,
+                     int queries_is_device, int k, int query_planes, int64_t id_base,
+                     float* out_scores, int64_t* out_ids, int out_is_device, void* stream);
+
+/* ------------------------------------------------------------------------- *
+ * BM25 (replaces corpus.get_scores at utils/bm25_search.py:309 /
+ * SimpleBM25.get_scores :43-63, and the max-normalisation :329-333).
+ *
+ * The host builds the term dictionary (strings never reach the device) and
+ * passes a term-major CSR: postings of term t are
+ * [term_ptr[t], term_ptr[t+1]) sorted by ascending doc id; post_gcode indexes
+ * `gtab`, the table of distinct per-(tf, doc_len) factors
+ *     g = tf*(k1+1) / (tf + k1*(1 - b + b*dl/avgdl))        (fp64, reference order)
+ * so that a posting's contribution is exactly idf[t] * g, the two roundings the
+ * reference performs.  All host pointers.  n_docs <= 2^31-1, n_g <= 2^18.
+ * ------------------------------------------------------------------------- */
+ARB_API int arb_bm25_create(arb_bm25** out, int64_t n_docs, int64_t n_terms,
+                    const int64_t* term_ptr, const int32_t* post_doc, const int32_t* post_gcode,
+                    const double* idf, const double* gtab, int64_t n_g, void* stream);
+ARB_API int arb_bm25_destroy(arb_bm25* bm);
+ARB_API int64_t arb_bm25_ndocs(const arb_bm25* bm);
+ARB_API int64_t arb_bm25_npostings(const arb_bm25* bm);
+/* sum over the given query terms (with multiplicity) of df(t): the algorithmic
+ * posting count the roofline figure is computed from.  Host q_terms. */
+ARB_API int64_t arb_bm25_query_postings(const arb_bm25* bm, const int32_t* q_terms, int64_t nq, int max_qt);
+
+/* Batched top-k.  q_terms [nq, max_qt] int32 term ids in QUERY TOKEN ORDER,
+ * duplicates kept, -1 = padding / unknown token.  Per query, per doc:
+ * score = (((0 + c_1) + c_2) + ...) in fp64, c_j = idf[t_j]*g(posting), exactly
+ * the order of rank_bm25 get_scores.  Output: descending score, ascending doc id
+ * on ties, docs with score <= 0 excluded, ids = id_base + doc, -1 / 0.0 padding. */
+ARB_API int arb_bm25_search(const arb_bm25* bm, const int32_t* q_terms, int64_t nq, int max_qt,
+                    int q_is_device, int k, int64_t id_base, double* out_scores, int64_t* out_ids,
+                    int out_is_device, void* stream);
+/* Full score vectors (bm25_scores, utils/bm25_search.py:286-340): out [nq, n_out]
+ * fp64; docs >= n_out are truncated, slots >= n_docs padded with 0.0 (:320-327);
+ * `normalise` != 0 divides by the per-query max when it is > 0 (:329-333). */
+ARB_API int arb_bm25_scores(const arb_bm25* bm, const int32_t* q_terms, int64_t nq, int max_qt,
+                    int q_is_device, int normalise, int64_t n_out, double* out,
+                    int out_is_device, void* stream);
+
+/* ------------------------------------------------------------------------- *
+ * Fusion (replaces HybridSearcher.fuse, retrieval/hybrid_search.py:34-103).
+ * Each source s in {dense, bm25, graph, path} is a [nq, k_s] list of
+ * (id int64, score) with id < 0 = empty slot; ids are unique inside a list.
+ * `score_dtype[s]` is ARB_F32 or ARB_F64.  Arithmetic is fp64 in the reference's
+ * operation order (no fused multiply-add).  Output per query: up to `pool`
+ * entries, descending final score, exact ties in first-appearance order of the
+ * dense -> bm25 -> graph -> path traversal:
+ *   out_ids   [nq, pool] int64 (-1 padding)
+ *   out_final [nq, pool] fp64
+ *   out_src   [nq, pool, 4] fp64 raw per-source score, NaN where absent
+ *   out_count [nq] int32
+ * All buffers device memory (is_device=1) or all host (0).  k_s <= 256 each. */
+ARB_API int arb_fuse(int method, const double weights[4], double rrf_k, int pool, int64_t nq,
+             const int64_t* const ids[4], const void* const scores[4], const int score_dtype[4],
+             const int k_src[4], int64_t* out_ids, double* out_final, double* out_src,
+             int32_t* out_count, int is_device, void* stream);
+
+/* ------------------------------------------------------------------------- *
+ * Multi-GPU merge (new design): `parts` per-shard top-k lists,
+ * laid out [parts, nq, k] as an NCCL all-gather leaves them, merged to the global
+ * top-k (descending score, ascending id; id < 0 = empty).  Device buffers.
+ * ------------------------------------------------------------------------- */
+ARB_API int arb_merge_topk(int score_dtype, const void* scores, const int64_t* ids, int parts,
+                   int64_t nq, int k, int positive_only, void* out_scores, int64_t* out_ids,
+                   void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ANORAG_B200_H_ */
