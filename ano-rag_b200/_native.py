@@ -48,6 +48,8 @@ _SIGS = {
     "arb_last_error": (c_char_p, []),
     "arb_device_count": (c_int, []),
     "arb_launch_count": (c_int64, [c_int]),
+    "arb_profile": (c_int, [c_int]),
+    "arb_profile_collect": (c_int, [POINTER(c_double), POINTER(c_int64)]),
     "arb_index_create": (c_int, [POINTER(c_void_p), c_int, c_int, c_int]),
     "arb_index_destroy": (c_int, [c_void_p]),
     "arb_index_add": (c_int, [c_void_p, c_void_p, c_int, c_int64, c_int, c_void_p]),
@@ -99,3 +101,18 @@ def device_count() -> int:
 
 def launch_count(reset: bool = False) -> int:
     return int(lib.arb_launch_count(1 if reset else 0))
+
+
+PROFILE_KINDS = ("dense_topk", "bm25_topk", "fuse", "dense_merge")
+
+
+def profile(enable: bool) -> None:
+    check(lib.arb_profile(1 if enable else 0))
+
+
+def profile_collect():
+    """-> {kind: (total_ms, launches)} for the kernels bracketed since profile(True)."""
+    ms = (c_double * 4)()
+    cnt = (c_int64 * 4)()
+    check(lib.arb_profile_collect(ms, cnt))
+    return {k: (float(ms[i]), int(cnt[i])) for i, k in enumerate(PROFILE_KINDS)}

@@ -408,7 +408,10 @@ extern "C" int arb_bm25_search(const arb_bm25* bm, const int32_t* q_terms, int64
     pi = pids.as<int64_t>();
   }
   dim3 grid(static_cast<unsigned>(nq), static_cast<unsigned>(n_split));
-  bm25_topk_kernel<<<grid, BM25_THREADS, BM25_SMEM, st>>>(bm->dev, d_terms, max_qt, k, id_base, bps, nq, ps, pi);
+  {
+    ProfileScope pscope(PROF_BM25_TOPK, st);
+    bm25_topk_kernel<<<grid, BM25_THREADS, BM25_SMEM, st>>>(bm->dev, d_terms, max_qt, k, id_base, bps, nq, ps, pi);
+  }
   ARB_LAUNCH_OK();
   if (n_split > 1) {
     rc = merge_topk_device(ARB_F64, ps, pi, n_split, nq, k, d_scores, d_ids, st);

@@ -2,6 +2,7 @@
 #include "common.cuh"
 
 #include <mutex>
+#include <vector>
 
 namespace arb {
 
@@ -18,6 +19,21 @@ int cuda_fail(cudaError_t e, const char* what, const char* file, int line) {
 }
 
 void count_launch(int n) { g_launches += n; }
+
+struct ProfRec { int kind; cudaEvent_t e0, e1; };
+static thread_local bool g_prof_on = false;
+static thread_local std::vector<ProfRec> g_prof;
+
+ProfileScope::ProfileScope(int kind_, cudaStream_t st_) : kind(kind_), st(st_), on(g_prof_on && g_prof.size() < 65536) {
+  if (!on) return;
+  if (cudaEventCreate(&e0) != cudaSuccess || cudaEventCreate(&e1) != cudaSuccess) { on = false; return; }
+  cudaEventRecord(e0, st);
+}
+ProfileScope::~ProfileScope() {
+  if (!on) return;
+  cudaEventRecord(e1, st);
+  g_prof.push_back({kind, e0, e1});
+}
 
 int num_sms() {
   static int sms[64] = {0};
@@ -48,4 +64,25 @@ extern "C" int64_t arb_launch_count(int reset) {
   int64_t v = arb::g_launches;
   if (reset) arb::g_launches = 0;
   return v;
+}
+
+extern "C" int arb_profile(int enable) {
+  arb::g_prof_on = enable != 0;
+  return ARB_OK;
+}
+
+extern "C" int arb_profile_collect(double* out_ms, int64_t* out_count) {
+  for (int i = 0; i < arb::PROF_KINDS; ++i) { if (out_ms) out_ms[i] = 0.0; if (out_count) out_count[i] = 0; }
+  int rc = ARB_OK;
+  for (auto& r : arb::g_prof) {
+    float ms = 0.f;
+    cudaError_t e = cudaEventSynchronize(r.e1);
+    if (e == cudaSuccess) e = cudaEventElapsedTime(&ms, r.e0, r.e1);
+    if (e != cudaSuccess) rc = arb::cuda_fail(e, "arb_profile_collect", __FILE__, __LINE__);
+    else { if (out_ms) out_ms[r.kind] += ms; if (out_count) out_count[r.kind] += 1; }
+    cudaEventDestroy(r.e0);
+    cudaEventDestroy(r.e1);
+  }
+  arb::g_prof.clear();
+  return rc;
 }

@@ -57,6 +57,15 @@ struct AsyncBuf {
 
 int num_sms();
 
+// Optional per-thread kernel timing (bench.py roofline): when enabled, the dominant
+// kernels are bracketed by CUDA events on their launch stream.
+enum { PROF_DENSE_TOPK = 0, PROF_BM25_TOPK = 1, PROF_FUSE = 2, PROF_DENSE_MERGE = 3, PROF_KINDS = 4 };
+struct ProfileScope {
+  int kind; cudaStream_t st; cudaEvent_t e0 = nullptr, e1 = nullptr; bool on;
+  ProfileScope(int kind, cudaStream_t st);
+  ~ProfileScope();
+};
+
 // order-preserving map fp32 -> uint32 (larger float <=> larger key); 0 is never
 // produced by a finite value, so 0 doubles as "empty".
 __host__ __device__ __forceinline__ uint32_t f32_key(float f) {

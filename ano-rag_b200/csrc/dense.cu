@@ -639,11 +639,17 @@ static int run_dense(const arb_index* ix, const __nv_bfloat16* qplanes, int q_pl
     attr_err = cudaFuncSetAttribute(dense_topk_kernel<EPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, DENSE_SMEM);
   });
   ARB_CUDA(attr_err);
-  dense_topk_kernel<EPL><<<grid, DENSE_THREADS, DENSE_SMEM, st>>>(ta, tb, p);
+  {
+    ProfileScope ps(PROF_DENSE_TOPK, st);
+    dense_topk_kernel<EPL><<<grid, DENSE_THREADS, DENSE_SMEM, st>>>(ta, tb, p);
+  }
   ARB_LAUNCH_OK();
   const int wpb = 4;
-  dense_merge_kernel<EPL><<<static_cast<unsigned>((nq + wpb - 1) / wpb), wpb * 32, wpb * C * sizeof(uint2), st>>>(
-      p, id_base, d_scores, d_ids);
+  {
+    ProfileScope ps(PROF_DENSE_MERGE, st);
+    dense_merge_kernel<EPL><<<static_cast<unsigned>((nq + wpb - 1) / wpb), wpb * 32, wpb * C * sizeof(uint2), st>>>(
+        p, id_base, d_scores, d_ids);
+  }
   ARB_LAUNCH_OK();
   return ARB_OK;
 }

@@ -365,7 +365,10 @@ extern "C" int arb_fuse(int method, const double weights[4], double rrf_k, int p
     err = cudaFuncSetAttribute(fuse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sizeof(FuseSmem)));
   });
   ARB_CUDA(err);
-  fuse_kernel<<<static_cast<unsigned>(nq), FUSE_THREADS, sizeof(FuseSmem), st>>>(p);
+  {
+    ProfileScope ps(PROF_FUSE, st);
+    fuse_kernel<<<static_cast<unsigned>(nq), FUSE_THREADS, sizeof(FuseSmem), st>>>(p);
+  }
   ARB_LAUNCH_OK();
   if (!is_device) {
     ARB_CUDA(cudaMemcpyAsync(out_ids, p.out_ids, np * 8, cudaMemcpyDeviceToHost, st));

@@ -1,0 +1,83 @@
+"""The hybrid candidate-scoring step as one call: dense top-k + BM25 top-k (+ the
+cross-GPU exchange when the corpus is row-sharded) + fusion.
+
+This is the batched form of what the reference executes per query in
+QueryProcessor (vector_retriever.search -> bm25_scores -> fusion,
+query/query_processor.py:1964,3706-3758) expressed over the same three components
+(VectorIndex / bm25_search / HybridSearcher).
+
+Sharding (new design): rank g holds rows [base_g, base_g + n_g) of
+the embedding matrix and the postings of exactly those docs, with corpus-GLOBAL
+BM25 statistics.  Per batch each rank computes its local top-k with global ids,
+one all-gather per source moves [world, nq, k] candidates over NVLink (NCCL), and
+every rank merges and fuses a slice of the queries (nq / world each), so the merge
+work is not replicated.
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import numpy as np
+import torch
+
+from . import engine
+from .retrieval.hybrid_search import HybridSearcher
+
+
+class HybridPipeline:
+    def __init__(self, dense: engine.DenseIndex, bm25: Optional[engine.BM25Index], searcher: HybridSearcher,
+                 k_dense: int = 100, k_bm25: int = 100, pool: Optional[int] = None, id_base: int = 0,
+                 query_planes: Optional[int] = None, group=None, device: Optional[torch.device] = None):
+        self.dense, self.bm25, self.searcher = dense, bm25, searcher
+        self.k_dense, self.k_bm25 = int(k_dense), int(k_bm25)
+        self.pool = int(pool if pool is not None else searcher.candidate_pool)
+        self.id_base = int(id_base)
+        self.query_planes = query_planes
+        self.group = group
+        self.device = device or torch.device("cuda", torch.cuda.current_device())
+        self.world = 1
+        self.rank = 0
+        if group is not None or (torch.distributed.is_available() and torch.distributed.is_initialized()):
+            self.world = torch.distributed.get_world_size(group)
+            self.rank = torch.distributed.get_rank(group)
+
+    # ------------------------------------------------------------------ device-resident inputs
+    def _gather(self, t: torch.Tensor) -> torch.Tensor:
+        out = torch.empty((self.world,) + tuple(t.shape), dtype=t.dtype, device=t.device)
+        torch.distributed.all_gather_into_tensor(out, t.contiguous(), group=self.group)
+        return out
+
+    def search_device(self, q_emb: torch.Tensor, q_terms: Optional[torch.Tensor]):
+        """q_emb [nq, d] CUDA (fp32 or bf16), q_terms [nq, max_qt] CUDA int32 (or None: dense only).
+        -> (ids [nq,pool] int64, final [nq,pool] fp64, src [nq,pool,4] fp64, count [nq] int32) on the device.
+        With world > 1 every rank returns the rows of its own query slice
+        [rank*ceil(nq/world), ...) -- see ``query_slice``."""
+        d_sc, d_id = self.dense.search(q_emb, self.k_dense, query_planes=self.query_planes, id_base=self.id_base)
+        b_sc = b_id = None
+        if self.bm25 is not None and q_terms is not None:
+            b_sc, b_id = self.bm25.search(q_terms, self.k_bm25, id_base=self.id_base)
+        if self.world > 1:
+            lo, hi = self.query_slice(q_emb.shape[0])
+            d_sc, d_id = engine.merge_topk(self._gather(d_sc)[:, lo:hi].contiguous(), self._gather(d_id)[:, lo:hi].contiguous())
+            if b_sc is not None:
+                b_sc, b_id = engine.merge_topk(self._gather(b_sc)[:, lo:hi].contiguous(), self._gather(b_id)[:, lo:hi].contiguous())
+        return self.searcher.fuse_tensors(dense=(d_id, d_sc), bm25=(b_id, b_sc) if b_sc is not None else None,
+                                          pool=self.pool)
+
+    def query_slice(self, nq: int):
+        if self.world == 1:
+            return 0, nq
+        per = (nq + self.world - 1) // self.world
+        return min(nq, self.rank * per), min(nq, (self.rank + 1) * per)
+
+    # ------------------------------------------------------------------ host buffers (the end-to-end call)
+    def search_host(self, q_emb_host, q_terms_host, return_src: bool = False):
+        """Host (ideally pinned) inputs -> host numpy outputs (ids, final, count[, src]); the H2D copy of
+        the batch and the D2H copy of the fused result are part of the call."""
+        q_emb = torch.as_tensor(q_emb_host).to(self.device, non_blocking=True)
+        q_terms = None
+        if q_terms_host is not None:
+            q_terms = torch.as_tensor(q_terms_host).to(self.device, non_blocking=True)
+        ids, fin, src, cnt = self.search_device(q_emb, q_terms)
+        out = (ids.cpu().numpy(), fin.cpu().numpy(), cnt.cpu().numpy())
+        return out + (src.cpu().numpy(),) if return_src else out

@@ -1,0 +1,160 @@
+"""BM25 over the B200 inverted-index kernel -- drop-in for reference
+utils/bm25_search.py (tokenize_text :237-241, build_bm25_corpus :244-283,
+bm25_scores :286-340; SimpleBM25 :16-63 and rank_bm25.BM25Okapi are replaced by
+``GpuBM25``).
+
+Host side here: tokenisation, the str -> term-id dictionary and the idf table
+(``math.log``, bit-identical to the reference).  Every score is computed on the
+device in fp64 in the reference's operation order (csrc/bm25.cu); there is no CPU
+scorer behind this module.
+"""
+from __future__ import annotations
+
+import re
+from typing import Any, Callable, Dict, List, Optional, Sequence
+
+import numpy as np
+
+from .._log import logger
+from ..config import config
+from .. import bm25_build as bb
+from .. import engine
+from .._native import MAX_QUERY_TERMS
+
+RANK_BM25_AVAILABLE = False     # kept for import compatibility (bm25_search.py:7-13); the GPU back-end is used
+
+_TOKEN_RE = re.compile(r"\b\w+\b")
+
+
+def tokenize_text(text: str) -> List[str]:
+    """Lower-case word tokens (reference :237-241)."""
+    return _TOKEN_RE.findall(text.lower())
+
+
+class GpuBM25:
+    """Corpus object returned by ``build_bm25_corpus``.
+
+    variant='okapi' reproduces rank_bm25.BM25Okapi (k1=1.5, b=0.75, epsilon=0.25: the
+    library defaults, because the reference passes none at :273); variant='simple'
+    reproduces the in-repo SimpleBM25 (:16-63)."""
+
+    def __init__(self, tokenized_corpus: List[List[str]], variant: str = "okapi", k1: float = bb.K1_DEFAULT,
+                 b: float = bb.B_DEFAULT, epsilon: float = bb.EPS_DEFAULT):
+        self.variant = variant
+        self.k1, self.b, self.epsilon = k1, b, epsilon
+        self.vocab = bb.Vocabulary()
+        doc_ptr, doc_tok = self.vocab.encode_docs(tokenized_corpus)
+        arrays = bb.build_arrays(doc_ptr, doc_tok, len(self.vocab), variant=variant, k1=k1, b=b, epsilon=epsilon)
+        self._finish(arrays)
+
+    @classmethod
+    def from_token_ids(cls, doc_ptr: np.ndarray, doc_tok: np.ndarray, n_terms: int, variant: str = "okapi",
+                       k1: float = bb.K1_DEFAULT, b: float = bb.B_DEFAULT, epsilon: float = bb.EPS_DEFAULT,
+                       stats: Optional[bb.BM25Stats] = None) -> "GpuBM25":
+        """Corpus given as integer term ids (synthetic corpora, shards with global ``stats``)."""
+        self = cls.__new__(cls)
+        self.variant = variant
+        self.k1, self.b, self.epsilon = k1, b, epsilon
+        self.vocab = None
+        self._finish(bb.build_arrays(doc_ptr, doc_tok, n_terms, variant=variant, k1=k1, b=b, epsilon=epsilon,
+                                     stats=stats))
+        return self
+
+    def _finish(self, arrays: bb.BM25Arrays) -> None:
+        st = arrays.stats
+        self.stats = st
+        self.corpus_size = self.doc_count = arrays.n_docs_local
+        self.avgdl = st.avgdl
+        self.doc_len = arrays.doc_len.tolist() if arrays.n_docs_local <= 1_000_000 else arrays.doc_len
+        self.average_idf = st.average_idf
+        self.index = engine.BM25Index(arrays.n_docs_local, arrays.term_ptr, arrays.post_doc, arrays.post_gcode,
+                                      st.idf, arrays.gtab)
+        self.n_g = len(arrays.gtab)
+
+    @property
+    def idf(self) -> Dict[str, float]:
+        if self.vocab is None:
+            return {}
+        idf = self.stats.idf
+        return {w: float(idf[t]) for w, t in self.vocab.ids.items()}
+
+    # -- encoding of queries into padded term-id matrices
+    def encode_queries(self, token_lists: Sequence[Sequence[Any]]) -> np.ndarray:
+        width = max(1, max((len(t) for t in token_lists), default=1))
+        if width > MAX_QUERY_TERMS:
+            raise ValueError(f"queries longer than {MAX_QUERY_TERMS} tokens are outside the kernel's limit")
+        out = np.full((len(token_lists), width), -1, dtype=np.int32)
+        for i, toks in enumerate(token_lists):
+            if not toks:
+                continue
+            ids = self.vocab.encode_query(toks) if self.vocab is not None else [int(t) for t in toks]
+            out[i, :len(ids)] = ids
+        return out
+
+    # -- reference-shaped scoring
+    def get_scores(self, query: Sequence[Any]) -> np.ndarray:
+        """Raw scores of every doc for one tokenised query (BM25Okapi.get_scores contract:
+        float64 ndarray of length N)."""
+        return self.index.scores(self.encode_queries([list(query)]))[0]
+
+    # -- batched GPU paths (additions)
+    def scores_batch(self, queries: Sequence[str], n_out: Optional[int] = None, normalise: bool = True) -> np.ndarray:
+        return self.index.scores(self.encode_queries([tokenize_text(q) for q in queries]), n_out=n_out,
+                                 normalise=normalise)
+
+    def search_batch(self, queries: Sequence[str], k: int, id_base: int = 0):
+        """Top-k per query: (scores fp64 [nq,k], ids int64 [nq,k]), score desc / doc asc, zero scores excluded."""
+        return self.index.search(self.encode_queries([tokenize_text(q) for q in queries]), k, id_base=id_base)
+
+    def search_terms(self, q_terms, k: int, id_base: int = 0):
+        return self.index.search(q_terms, k, id_base=id_base)
+
+    def close(self):
+        self.index.close()
+
+
+def build_bm25_corpus(notes: List[Dict[str, Any]], text_fn: Callable[[Dict[str, Any]], str]) -> Any:
+    """Reference :244-283: tokenise every note (``[]`` on empty text or error), then
+    build the corpus object.  Okapi first (what runs wherever rank_bm25 is installed);
+    its constructor raises on degenerate corpora exactly where the library does, and
+    the SimpleBM25 arithmetic takes over as in the reference (:276-283)."""
+    tokenized_corpus: List[List[str]] = []
+    for note in notes:
+        try:
+            text = text_fn(note)
+            tokenized_corpus.append(tokenize_text(text) if text else [])
+        except Exception as e:
+            logger.warning(f"Error extracting text from note: {e}")
+            tokenized_corpus.append([])
+    backend = config.get("b200.bm25_backend", "okapi")
+    if backend == "okapi":
+        try:
+            corpus = GpuBM25(tokenized_corpus, variant="okapi")
+            logger.debug(f"Built BM25 corpus with {len(tokenized_corpus)} documents (okapi arithmetic, B200)")
+            return corpus
+        except ZeroDivisionError as e:
+            logger.error(f"Error building BM25 corpus with okapi arithmetic: {e}")
+    corpus = GpuBM25(tokenized_corpus, variant="simple")
+    logger.debug(f"Built BM25 corpus with {len(tokenized_corpus)} documents (simple arithmetic, B200)")
+    return corpus
+
+
+def bm25_scores(corpus: Any, docs: List[Dict[str, Any]], query: str) -> List[float]:
+    """Reference :286-340: scores of the WHOLE corpus for ``query``, padded / truncated to
+    ``len(docs)`` (:320-327), divided by their max when it is positive (:329-333); zeros
+    on an empty query (:302-304) or any error (:338-340)."""
+    try:
+        query_tokens = tokenize_text(query)
+        if not query_tokens:
+            logger.warning("Empty query tokens, returning zero scores")
+            return [0.0] * len(docs)
+        if isinstance(corpus, GpuBM25):
+            if len(docs) == 0:
+                return []
+            return corpus.index.scores(corpus.encode_queries([query_tokens]), n_out=len(docs),
+                                       normalise=True)[0].tolist()
+        logger.error("Invalid corpus object")
+        return [0.0] * len(docs)
+    except Exception as e:
+        logger.error(f"Error calculating BM25 scores: {e}")
+        return [0.0] * len(docs)

@@ -78,6 +78,12 @@ ARB_API int         arb_device_count(void);
 /* kernels launched by this library on the calling thread since the last reset
  * (bench.py reports it as gpu_launches) */
 ARB_API int64_t     arb_launch_count(int reset);
+/* Per-thread kernel timing for the roofline report: while enabled, the dominant
+ * kernels are bracketed by CUDA events on their launch stream.  collect() waits for
+ * them and returns summed milliseconds / launch counts per kind, then clears:
+ * [0] dense GEMM+select  [1] BM25 top-k  [2] fusion  [3] dense list merge. */
+ARB_API int         arb_profile(int enable);
+ARB_API int         arb_profile_collect(double out_ms[4], int64_t out_count[4]);
 
 /* ------------------------------------------------------------------------- *
  * Dense: exact inner-product top-k (replaces faiss.IndexFlatIP behind

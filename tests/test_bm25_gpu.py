@@ -1,0 +1,108 @@
+"""BM25 on the B200: bit-exact against the reference's golden outputs and the oracle."""
+import json
+import os
+import random
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def fh(x):
+    return float.fromhex(x)
+
+
+def test_reference_golden_simple_bm25_bit_exact(golden_dir):
+    import ano_rag_b200  # noqa: F401
+    from ano_rag_b200.config import config
+    from ano_rag_b200.utils.bm25_search import build_bm25_corpus, bm25_scores
+    config.set("b200.bm25_backend", "simple")
+    with open(os.path.join(golden_dir, "bm25_simple_golden.json")) as f:
+        golden = json.load(f)
+    for case in golden["cases"]:
+        notes = [{"content": d} for d in case["docs"]]
+        corpus = build_bm25_corpus(notes, lambda n: n.get("content", ""))
+        assert corpus.variant == "simple" and corpus.avgdl == fh(case["avgdl"])
+        assert corpus.idf == {t: fh(v) for t, v in case["idf"].items()}
+        for q in case["queries"]:
+            if q["tokens"]:
+                assert corpus.get_scores(q["tokens"]).tolist() == [fh(v) for v in q["raw"]], (case["name"], q["query"])
+            assert bm25_scores(corpus, notes, q["query"]) == [fh(v) for v in q["normalised"]]
+            half = notes[: max(1, len(notes) // 2)]
+            assert bm25_scores(corpus, half, q["query"]) == [fh(v) for v in q["normalised_truncated"]]
+        longer = notes + [{"content": "x"}] * 3                 # padding branch (:320-323)
+        got = bm25_scores(corpus, longer, case["queries"][0]["query"])
+        assert got[: len(notes)] == [fh(v) for v in case["queries"][0]["normalised"]] and got[len(notes):] == [0.0] * 3
+    config.reset()
+
+
+def test_okapi_matches_restated_rank_bm25():
+    import ano_rag_b200  # noqa: F401
+    from ano_rag_b200.utils.bm25_search import build_bm25_corpus, bm25_scores
+    from oracle import bm25 as obm
+    rng = random.Random(4)
+    for n_docs, vocab in [(4, 30), (90, 25), (600, 300)]:
+        docs = [" ".join(f"w{rng.randrange(vocab)}" for _ in range(rng.randint(1, 40))) for _ in range(n_docs)]
+        if n_docs == 90:
+            docs = [d + " common" for d in docs]                # df == N: negative idf -> epsilon * average_idf
+        notes = [{"content": d} for d in docs]
+        gpu = build_bm25_corpus(notes, lambda n: n["content"])
+        ora = obm.build_bm25_corpus(notes, lambda n: n["content"], backend="okapi")
+        assert gpu.variant == "okapi" and gpu.average_idf == ora.average_idf
+        for _ in range(10):
+            q = " ".join(f"w{rng.randrange(vocab + 3)}" for _ in range(rng.randint(1, 9)))
+            if n_docs == 90:
+                q += " common common"
+            assert gpu.get_scores(obm.tokenize_text(q)).tolist() == ora.get_scores(obm.tokenize_text(q)).tolist()
+            assert bm25_scores(gpu, notes, q) == obm.bm25_scores(ora, notes, q)
+    assert bm25_scores(gpu, notes, "") == [0.0] * len(notes)     # empty query (:302-304)
+    assert bm25_scores(gpu, notes, "?? !!") == [0.0] * len(notes)
+    assert bm25_scores(object(), notes, "w1") == [0.0] * len(notes)
+
+
+def test_degenerate_corpora_fall_back_to_simple():
+    import ano_rag_b200  # noqa: F401
+    from ano_rag_b200.utils.bm25_search import build_bm25_corpus, bm25_scores
+    c = build_bm25_corpus([{"content": ""}, {"content": ""}], lambda n: n["content"])
+    assert c.variant == "simple" and bm25_scores(c, [{}, {}], "anything") == [0.0, 0.0]
+    c = build_bm25_corpus([], lambda n: n["content"])
+    assert c.variant == "simple" and bm25_scores(c, [], "x") == [] and bm25_scores(c, [{}], "x") == [0.0]
+    c = build_bm25_corpus([{"content": "a b"}, {"nope": 1}], lambda n: n["content"])   # text_fn raises -> []
+    assert c.doc_len == [2, 0]
+
+
+@pytest.mark.parametrize("variant,n,v,nq,k", [("okapi", 50_000, 4000, 300, 100), ("simple", 20_000, 500, 8, 40),
+                                              ("okapi", 16_385, 50, 3, 256), ("okapi", 100, 10, 2, 100)])
+def test_topk_and_full_scores_match_array_oracle(variant, n, v, nq, k):
+    import ano_rag_b200  # noqa: F401
+    from ano_rag_b200.utils.bm25_search import GpuBM25
+    from oracle import bm25 as obm
+    rng = np.random.default_rng(n + v)
+    lens = np.maximum(1, rng.poisson(25, n))
+    ptr = np.zeros(n + 1, np.int64)
+    ptr[1:] = np.cumsum(lens)
+    p = 1.0 / np.arange(1, v + 1)
+    p /= p.sum()
+    tok = rng.choice(v, size=int(ptr[-1]), p=p)
+    gpu = GpuBM25.from_token_ids(ptr, tok, v, variant=variant)
+    ora = obm.ArrayBM25Oracle(ptr, tok, variant=variant)
+    qt = rng.choice(v, size=(nq, 8), p=p).astype(np.int32)
+    qt[0, 2:] = -1
+    qt[1, 5] = qt[1, 0]                                          # duplicated token counts twice
+    if nq > 2:
+        qt[2, :] = -1                                            # nothing known -> empty result
+    s, i = gpu.search_terms(qt, k)
+    rows = range(nq) if nq <= 16 else list(range(8)) + rng.integers(0, nq, 8).tolist()
+    full = gpu.index.scores(qt[list(rows)])
+    for j, r in enumerate(rows):
+        want = ora.get_scores([t for t in qt[r] if t >= 0])
+        assert np.array_equal(full[j], want), f"query {r}"
+        ws, wi = obm.topk_positive(want, k)
+        assert np.array_equal(i[r], wi) and np.array_equal(s[r], ws), f"query {r}"
+    # device-resident query terms give the same answer
+    import torch
+    s2, i2 = gpu.search_terms(torch.from_numpy(qt).cuda(), k)
+    assert np.array_equal(s2.cpu().numpy(), s) and np.array_equal(i2.cpu().numpy(), i)
+    assert gpu.index.query_postings(qt) == sum(int(ora.df[ora.term_slot[int(t)]]) for t in qt.ravel() if int(t) in ora.term_slot)
+    gpu.close()

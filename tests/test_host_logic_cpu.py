@@ -1,0 +1,90 @@
+"""Host-side logic that runs without a GPU: index-build arithmetic against the oracle,
+config shim, tokeniser, query encoding."""
+import random
+
+import numpy as np
+import pytest
+
+import ano_rag_b200  # noqa: F401
+from ano_rag_b200 import bm25_build as bb
+from ano_rag_b200.config import Config
+from oracle import bm25 as obm
+
+
+def random_corpus(rng, n_docs, vocab, lo, hi):
+    docs = [[rng.randrange(vocab) for _ in range(rng.randint(lo, hi))] for _ in range(n_docs)]
+    ptr = np.zeros(n_docs + 1, dtype=np.int64)
+    ptr[1:] = np.cumsum([len(d) for d in docs])
+    tok = np.array([t for d in docs for t in d], dtype=np.int64)
+    return docs, ptr, tok
+
+
+@pytest.mark.parametrize("variant", ["okapi", "simple"])
+def test_build_arrays_reproduce_oracle_impacts(variant):
+    rng = random.Random(11)
+    for n_docs, vocab in [(5, 4), (64, 20), (700, 150)]:
+        docs, ptr, tok = random_corpus(rng, n_docs, vocab, 1, 30)
+        if n_docs == 64:
+            tok[ptr[:-1]] = 0          # term 0 in every doc -> negative okapi idf -> epsilon floor
+        arr = bb.build_arrays(ptr, tok, vocab, variant=variant)
+        ora = obm.ArrayBM25Oracle(ptr, tok, variant=variant)
+        assert arr.stats.avgdl == ora.avgdl
+        for slot, term in enumerate(ora.vocab.tolist()):
+            assert arr.stats.idf[term] == ora.idf[slot], (variant, term)
+            s, e = arr.term_ptr[term], arr.term_ptr[term + 1]
+            docs_o, imp_o = ora.impacts(slot)
+            assert np.array_equal(arr.post_doc[s:e], docs_o)
+            assert np.array_equal(arr.stats.idf[term] * arr.gtab[arr.post_gcode[s:e]], imp_o)
+        if variant == "okapi":
+            assert arr.stats.average_idf == ora.average_idf
+
+
+def test_okapi_degenerate_corpora_raise_like_rank_bm25():
+    with pytest.raises(ZeroDivisionError):
+        bb.build_arrays(np.zeros(1, np.int64), np.zeros(0, np.int64), 0, variant="okapi")          # no docs
+    with pytest.raises(ZeroDivisionError):
+        bb.build_arrays(np.zeros(4, np.int64), np.zeros(0, np.int64), 0, variant="okapi")          # docs, no tokens
+    arr = bb.build_arrays(np.zeros(4, np.int64), np.zeros(0, np.int64), 0, variant="simple")       # SimpleBM25 copes
+    assert arr.stats.avgdl == 0 and len(arr.post_doc) == 0
+
+
+def test_vocabulary_first_appearance_and_query_encoding():
+    v = bb.Vocabulary()
+    ptr, tok = v.encode_docs([["b", "a", "b"], [], ["c", "a"]])
+    assert ptr.tolist() == [0, 3, 3, 5] and tok.tolist() == [0, 1, 0, 2, 1]
+    assert v.encode_query(["a", "zzz", "b", "a"]) == [1, -1, 0, 1]
+    assert bb.first_appearance_order(np.array([3, 1, 3, 0]), 5).tolist() == [3, 1, 0]
+
+
+def test_shard_arrays_with_global_stats_match_single_index():
+    rng = random.Random(2)
+    docs, ptr, tok = random_corpus(rng, 300, 40, 1, 20)
+    whole = bb.build_arrays(ptr, tok, 40)
+    half = 150
+    for lo, hi in [(0, half), (half, 300)]:
+        sptr = ptr[lo:hi + 1] - ptr[lo]
+        stok = tok[ptr[lo]:ptr[hi]]
+        shard = bb.build_arrays(sptr, stok, 40, stats=whole.stats)
+        for t in range(40):
+            s, e = shard.term_ptr[t], shard.term_ptr[t + 1]
+            ws, we = whole.term_ptr[t], whole.term_ptr[t + 1]
+            sel = (whole.post_doc[ws:we] >= lo) & (whole.post_doc[ws:we] < hi)
+            assert np.array_equal(shard.post_doc[s:e] + lo, whole.post_doc[ws:we][sel])
+            assert np.array_equal(shard.gtab[shard.post_gcode[s:e]], whole.gtab[whole.post_gcode[ws:we][sel]])
+
+
+def test_config_shim_dotted_get_and_effective_defaults():
+    c = Config()
+    assert c.get("vector_store.top_k") == 20 and c.get("retrieval.candidate_pool") == 80
+    assert c.get("retrieval.hybrid.weights.bm25") == 0.5 and c.get("nope.x", 7) == 7
+    c.update({"retrieval": {"hybrid": {"fusion_method": "rrf"}}})
+    assert c.get("retrieval.hybrid.fusion_method") == "rrf" and c.get("retrieval.hybrid.rrf_k") == 60
+    assert c.load_config()["retrieval"]["hybrid"]["weights"]["dense"] == 1.0
+    c.set("b200.storage", "bf16")
+    assert c.get("b200.storage") == "bf16"
+
+
+def test_tokenizer_matches_oracle():
+    from ano_rag_b200.utils.bm25_search import tokenize_text
+    for s in ["The quick-brown fox_1 jumps!", "", "ÀÉ ünïcode 42x", "a.b,c;d"]:
+        assert tokenize_text(s) == obm.tokenize_text(s)
