@@ -13,7 +13,7 @@
 //
 // Layout in HBM: postings are term-major, doc-sorted, and cut at doc-block
 // boundaries (DOC_BLOCK = 16384 docs = one 128 KB fp64 accumulator tile in shared
-// memory).  post[i] = (doc % DOC_BLOCK) << 18 | gcode  (4 B per posting);
+// memory).  post[i] = gcode << 14 | (doc % DOC_BLOCK)  (4 B per posting);
 // blk_off[t*NB + b] is where block b of term t starts.
 #include "common.cuh"
 
@@ -27,6 +27,8 @@ constexpr int DOC_BLOCK_LOG2 = 14;
 constexpr int DOC_BLOCK = 1 << DOC_BLOCK_LOG2;       // docs per accumulator tile
 constexpr int GCODE_BITS = 18;
 constexpr uint32_t GCODE_MASK = (1u << GCODE_BITS) - 1u;
+__host__ __device__ __forceinline__ uint32_t post_doc(uint32_t u) { return u & (DOC_BLOCK - 1); }
+__host__ __device__ __forceinline__ uint32_t post_code(uint32_t u) { return u >> DOC_BLOCK_LOG2; }
 constexpr int BM25_THREADS = 1024;
 constexpr int CAND_CAP = 2048;                        // candidate buffer (power of two)
 constexpr int GTAB_SMEM = 4096;                       // g-table entries cached in smem
@@ -40,13 +42,17 @@ struct Bm25Dev {
   const uint32_t* post;         // [n_post]
   const double* idf;            // [n_terms]
   const double* gtab;           // [n_g]
+  int n_slices;                 // 512-doc slices (one warp each)
+  int n_dense;                  // terms with per-slice offsets
+  const int* dense_slot;        // [n_terms] index into fine_off or -1
+  const uint32_t* fine_off;     // [n_dense * (n_slices + 1)]
 };
 
 // ---------------------------------------------------------------- build kernels
 __global__ void bm25_pack_kernel(const int32_t* __restrict__ doc, const int32_t* __restrict__ gcode, int64_t n,
                                  uint32_t* __restrict__ post) {
   int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
-  if (i < n) post[i] = (static_cast<uint32_t>(doc[i]) & (DOC_BLOCK - 1)) << GCODE_BITS | (static_cast<uint32_t>(gcode[i]) & GCODE_MASK);
+  if (i < n) post[i] = (static_cast<uint32_t>(gcode[i]) & GCODE_MASK) << DOC_BLOCK_LOG2 | (static_cast<uint32_t>(doc[i]) & (DOC_BLOCK - 1));
 }
 
 // one thread per (term, block): first posting of term t whose doc >= b*DOC_BLOCK
@@ -63,6 +69,23 @@ __global__ void bm25_blkoff_kernel(const int64_t* __restrict__ term_ptr, const i
     if (doc[mid] < lo_doc) lo = mid + 1; else hi = mid;
   }
   blk_off[i] = static_cast<uint32_t>(lo);
+}
+
+// one thread per (dense term, slice boundary): first posting of the term whose doc >= slice*512
+__global__ void bm25_fineoff_kernel(const int64_t* __restrict__ term_ptr, const int32_t* __restrict__ doc,
+                                    const int32_t* __restrict__ dense_terms, int n_dense, int n_slices,
+                                    uint32_t* __restrict__ fine_off) {
+  int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  if (i >= static_cast<int64_t>(n_dense) * (n_slices + 1)) return;
+  const int t = dense_terms[i / (n_slices + 1)];
+  const int64_t sl = i % (n_slices + 1);
+  int64_t lo = term_ptr[t], hi = term_ptr[t + 1];
+  const int64_t lo_doc = sl << (DOC_BLOCK_LOG2 - 5);
+  while (lo < hi) {
+    int64_t mid = (lo + hi) >> 1;
+    if (doc[mid] < lo_doc) lo = mid + 1; else hi = mid;
+  }
+  fine_off[i] = static_cast<uint32_t>(lo);
 }
 
 // ---------------------------------------------------------------- scoring core
@@ -110,9 +133,9 @@ __device__ __forceinline__ void bm25_accumulate_block(const Bm25Dev& ix, const B
     if (idf != 0.0) {                                          // (idf.get(q) or 0): adds +0.0, a no-op
       for (uint32_t i = lo + tid; i < hi; i += BM25_THREADS) {
         const uint32_t u = __ldg(ix.post + i);
-        const uint32_t code = u & GCODE_MASK;
+        const uint32_t code = post_code(u);
         const double g = g_in_smem ? s.gtab[code] : __ldg(ix.gtab + code);
-        const uint32_t d = u >> GCODE_BITS;
+        const uint32_t d = post_doc(u);
         s.acc[d] = __dadd_rn(s.acc[d], __dmul_rn(idf, g));
       }
     }
@@ -143,65 +166,283 @@ __device__ __forceinline__ void bitonic_sort_cands(const Bm25Smem& s) {
   __syncthreads();
 }
 
-// Top-k kernel: grid (nq, n_split).  Each CTA walks its doc blocks in ascending
-// order keeping a running candidate set; a candidate must beat the current k-th
-// score strictly, which is exact because later docs have larger ids.
-__global__ void __launch_bounds__(BM25_THREADS, 1)
+// ----------------------------------------------------------------------------
+// Top-k kernel.  grid (nq, n_split); one CTA of 16 warps walks its doc blocks.
+//
+// Ownership: warp w (of 32) owns docs [512*w, 512*w+512) of the current 16K-doc block, i.e.
+// its own 4 KB slice of the fp64 accumulator tile.  Only that warp touches the slice,
+// so the query-token order of the per-doc additions needs nothing stronger than
+// __syncwarp() between terms (the first version used ~500 block barriers per query
+// and was bound by shared-memory bank-conflict replays; profiles/r1_ncu_summary.md).
+//   * dense terms (df >= n_docs/256) carry per-slice offsets (fine_off): the warp
+//     streams exactly its postings from L2 with unrolled, coalesced 4-byte loads;
+//   * sparse terms have few postings per block: every warp scans the block segment
+//     and keeps the postings of its own slice.
+// The (tf, dl) factor table is replicated across shared-memory banks so the random
+// table lookups of a warp do not serialise.  After the last term each warp scans its
+// slice (fused with re-zeroing) and appends docs that beat the running k-th
+// (score, doc) pair to the CTA's candidate buffer.
+// ----------------------------------------------------------------------------
+constexpr int TOPK_WARPS = 32;
+constexpr int TOPK_THREADS = TOPK_WARPS * 32;
+constexpr int SLICE_LOG2 = DOC_BLOCK_LOG2 - 5;       // 512 docs owned by one warp
+constexpr int SLICE = 1 << SLICE_LOG2;
+constexpr int CAP2 = 1024;                           // candidate buffer (power of two)
+constexpr int GREP_BYTES = 65536;                    // replicated factor table
+constexpr int TOPK_SMEM = DOC_BLOCK * 8 + 256 + GREP_BYTES + CAP2 * 12 + ARB_MAX_QUERY_TERMS * 16 + 64;
+constexpr uint32_t NULL_POSTING = 0xFFFFFFFFu;       // never a real posting: n_g < 2^18
+
+struct TopkSmem {
+  double* acc; double* grep; unsigned long long* ckey; uint32_t* cdoc; double* idf; int* dslot; int* misc;
+  const double* gglobal;
+};
+__device__ __forceinline__ TopkSmem carve_topk(uint8_t* b) {
+  TopkSmem s;
+  s.acc = reinterpret_cast<double*>(b);                 b += DOC_BLOCK * 8 + 256;   // + one dummy slot per lane
+  s.grep = reinterpret_cast<double*>(b);                b += GREP_BYTES;
+  s.ckey = reinterpret_cast<unsigned long long*>(b);    b += CAP2 * 8;
+  s.idf = reinterpret_cast<double*>(b);                 b += ARB_MAX_QUERY_TERMS * 8;
+  s.cdoc = reinterpret_cast<uint32_t*>(b);              b += CAP2 * 4;
+  s.dslot = reinterpret_cast<int*>(b);                  b += ARB_MAX_QUERY_TERMS * 4;
+  s.misc = reinterpret_cast<int*>(b);
+  s.gglobal = nullptr;
+  return s;
+}
+
+// bitonic sort of the candidate buffer by (key desc, doc asc); whole CTA
+__device__ __forceinline__ void sort_cands(const TopkSmem& s, int tid) {
+  for (int size = 2; size <= CAP2; size <<= 1) {
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+      __syncthreads();
+      for (int i = tid; i < CAP2 / 2; i += TOPK_THREADS) {
+        const int lo = 2 * i - (i & (stride - 1));
+        const int hi = lo + stride;
+        const bool best_first = ((lo & size) == 0);
+        const unsigned long long ka = s.ckey[lo], kb = s.ckey[hi];
+        const uint32_t da = s.cdoc[lo], db = s.cdoc[hi];
+        const bool a_before_b = (ka > kb) || (ka == kb && da < db);
+        if (a_before_b != best_first) { s.ckey[lo] = kb; s.ckey[hi] = ka; s.cdoc[lo] = db; s.cdoc[hi] = da; }
+      }
+    }
+  }
+  __syncthreads();
+}
+
+// one posting -> acc[doc] += idf * g[code]; a NULL posting goes to the lane's dummy slot behind the tile
+template <int REP_LOG2, bool CHECK>
+__device__ __forceinline__ void apply_posting(const TopkSmem& s, uint32_t u, double idf, int lane) {
+  uint32_t code = post_code(u);
+  uint32_t doc = post_doc(u);
+  if (CHECK) {
+    const bool null = u == NULL_POSTING;
+    code = null ? 0u : code;
+    doc = null ? static_cast<uint32_t>(DOC_BLOCK + lane) : doc;
+  }
+  double g;
+  if (REP_LOG2 < 0) g = __ldg(s.gglobal + code);
+  else g = s.grep[(code << (REP_LOG2 < 0 ? 0 : REP_LOG2)) + (lane & ((1 << (REP_LOG2 < 0 ? 0 : REP_LOG2)) - 1))];
+  s.acc[doc] = __dadd_rn(s.acc[doc], __dmul_rn(idf, g));
+}
+
+// Dense term: every posting in [lo, hi) belongs to this warp's slice (hi - lo <= SLICE).
+// Register double-buffered: the next 128 postings are in flight while the current 128 are applied.
+template <int REP_LOG2>
+__device__ __forceinline__ void accumulate_dense(const TopkSmem& s, const uint32_t* __restrict__ post, uint32_t lo,
+                                                 uint32_t hi, double idf, int lane) {
+  constexpr int U = 4;
+  uint32_t cur[U], nxt[U];
+  uint32_t base = lo;
+#pragma unroll
+  for (int r = 0; r < U; ++r) { const uint32_t i = base + r * 32 + lane; cur[r] = i < hi ? __ldg(post + i) : NULL_POSTING; }
+  while (true) {
+    const uint32_t nbase = base + 32 * U;
+    const bool more = nbase < hi;
+    if (more) {
+#pragma unroll
+      for (int r = 0; r < U; ++r) { const uint32_t i = nbase + r * 32 + lane; nxt[r] = i < hi ? __ldg(post + i) : NULL_POSTING; }
+    }
+    if (nbase <= hi) {                               // full chunk: no NULL postings
+#pragma unroll
+      for (int r = 0; r < U; ++r) apply_posting<REP_LOG2, false>(s, cur[r], idf, lane);
+    } else {
+#pragma unroll
+      for (int r = 0; r < U; ++r) apply_posting<REP_LOG2, true>(s, cur[r], idf, lane);
+    }
+    if (!more) break;
+#pragma unroll
+    for (int r = 0; r < U; ++r) cur[r] = nxt[r];
+    base = nbase;
+  }
+}
+
+// Sparse term: few postings per 16K block; every warp scans them and keeps those of its own slice.
+template <int REP_LOG2>
+__device__ __forceinline__ void accumulate_sparse(const TopkSmem& s, const uint32_t* __restrict__ post, uint32_t lo,
+                                                  uint32_t hi, double idf, int lane, int warp) {
+  for (uint32_t i = lo + lane; i < hi; i += 32) {
+    const uint32_t u = __ldg(post + i);
+    if (static_cast<int>(post_doc(u) >> SLICE_LOG2) == warp) apply_posting<REP_LOG2, false>(s, u, idf, lane);
+  }
+}
+
+template <int REP_LOG2>
+__device__ __forceinline__ void bm25_topk_body(const Bm25Dev& ix, const TopkSmem& s, const int32_t* __restrict__ q_terms,
+                                               int max_qt, int k, int64_t id_base, int b0, int b1,
+                                               double* __restrict__ os, int64_t* __restrict__ oi) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  // the (up to two) query terms whose offsets this lane fetches for the warp
+  int t_a = -1, t_b = -1, d_a = -1, d_b = -1;
+  if (lane < max_qt) { t_a = q_terms[lane]; if (t_a >= ix.n_terms) t_a = -1; }
+  if (lane + 32 < max_qt) { t_b = q_terms[lane + 32]; if (t_b >= ix.n_terms) t_b = -1; }
+  if (t_a >= 0 && s.idf[lane] == 0.0) t_a = -1;            // idf 0 adds +0.0: a no-op in the reference
+  if (t_b >= 0 && s.idf[lane + 32] == 0.0) t_b = -1;
+  if (t_a >= 0) d_a = s.dslot[lane];
+  if (t_b >= 0) d_b = s.dslot[lane + 32];
+  const int nsl = ix.n_slices;
+
+  auto load_range = [&](int t, int dslot, int b, uint32_t& lo, uint32_t& hi) {
+    lo = hi = 0;
+    if (t < 0 || b >= b1) return;
+    if (dslot >= 0) {
+      const int64_t sl = (static_cast<int64_t>(b) << (DOC_BLOCK_LOG2 - SLICE_LOG2)) + warp;
+      if (sl < nsl) {
+        lo = __ldg(ix.fine_off + static_cast<int64_t>(dslot) * (nsl + 1) + sl);
+        hi = __ldg(ix.fine_off + static_cast<int64_t>(dslot) * (nsl + 1) + sl + 1);
+      }
+    } else {
+      lo = __ldg(ix.blk_off + static_cast<int64_t>(t) * ix.nb + b);
+      hi = __ldg(ix.blk_off + static_cast<int64_t>(t) * ix.nb + b + 1);
+    }
+  };
+
+  unsigned long long thr_key = f64_key(0.0);     // a candidate needs score > 0 ...
+  uint32_t thr_doc = 0u;                          // ... or a tie with the k-th score at a smaller doc id
+  double2* my_acc2 = reinterpret_cast<double2*>(s.acc + (warp << SLICE_LOG2));
+
+  uint32_t lo_a, hi_a, lo_b, hi_b;
+  load_range(t_a, d_a, b0, lo_a, hi_a);
+  load_range(t_b, d_b, b0, lo_b, hi_b);
+  for (int b = b0; b < b1; ++b) {
+    uint32_t nlo_a, nhi_a, nlo_b, nhi_b;          // prefetch the next block's ranges
+    load_range(t_a, d_a, b + 1, nlo_a, nhi_a);
+    load_range(t_b, d_b, b + 1, nlo_b, nhi_b);
+    // which terms have postings for this warp in this block (bit j of the masks)
+    const uint32_t ne_a = __ballot_sync(0xffffffffu, hi_a > lo_a);
+    const uint32_t ne_b = __ballot_sync(0xffffffffu, hi_b > lo_b);
+    const uint32_t dn_a = __ballot_sync(0xffffffffu, d_a >= 0);
+    const uint32_t dn_b = __ballot_sync(0xffffffffu, d_b >= 0);
+    const bool touched = (ne_a | ne_b) != 0u;
+    for (int half = 0; half < 2; ++half) {
+      uint32_t ne = half ? ne_b : ne_a;
+      const uint32_t dn = half ? dn_b : dn_a;
+      while (ne) {                                 // ascending j = query token order
+        const int jl = __ffs(ne) - 1;
+        ne &= ne - 1;
+        const uint32_t lo = __shfl_sync(0xffffffffu, half ? lo_b : lo_a, jl);
+        const uint32_t hi = __shfl_sync(0xffffffffu, half ? hi_b : hi_a, jl);
+        const double idf = s.idf[half * 32 + jl];
+        if ((dn >> jl) & 1u) accumulate_dense<REP_LOG2>(s, ix.post, lo, hi, idf, lane);
+        else                 accumulate_sparse<REP_LOG2>(s, ix.post, lo, hi, idf, lane, warp);
+        __syncwarp();                              // the next term may hit the same docs from other lanes
+      }
+    }
+    lo_a = nlo_a; hi_a = nhi_a; lo_b = nlo_b; hi_b = nhi_b;
+
+    // ---- harvest this warp's slice and re-zero it; re-scan after a compaction if the buffer overflowed
+    const uint32_t doc0 = (static_cast<uint32_t>(b) << DOC_BLOCK_LOG2) + (static_cast<uint32_t>(warp) << SLICE_LOG2);
+    bool need_scan = touched;
+    while (true) {
+      if (need_scan) {
+#pragma unroll 2
+        for (int i = 0; i < SLICE / 64; ++i) {
+          const double2 v2 = my_acc2[i * 32 + lane];
+          if (v2.x != 0.0 || v2.y != 0.0) {
+            double2 left = make_double2(0.0, 0.0);
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+              const double v = h ? v2.y : v2.x;
+              if (v != 0.0) {
+                const uint32_t doc = doc0 + (i * 32 + lane) * 2 + h;
+                const unsigned long long key = f64_key(v);
+                if (key > thr_key || (key == thr_key && doc < thr_doc)) {
+                  const int pos = atomicAdd(&s.misc[0], 1);
+                  if (pos < CAP2) { s.ckey[pos] = key; s.cdoc[pos] = doc; }
+                  else { s.misc[1] = 1; if (h) left.y = v; else left.x = v; }   // overflowed: leave for the re-scan
+                }
+              }
+            }
+            my_acc2[i * 32 + lane] = left;
+          }
+        }
+      }
+      __syncthreads();
+      const int overflow = s.misc[1];
+      const int cnt = min(s.misc[0], CAP2);
+      __syncthreads();                             // everyone has read the counters before anyone moves on
+      if (!overflow && cnt <= CAP2 / 2) break;
+      // buffer filling up: keep the k best, tighten the threshold, re-scan what was left behind
+      if (tid == 0) s.misc[0] = cnt;
+      sort_cands(s, tid);
+      const int keep = min(cnt, k);
+      if (cnt >= k) { thr_key = s.ckey[k - 1]; thr_doc = s.cdoc[k - 1]; }
+      __syncthreads();
+      for (int i = keep + tid; i < CAP2; i += TOPK_THREADS) { s.ckey[i] = 0ull; s.cdoc[i] = 0xFFFFFFFFu; }
+      if (tid == 0) { s.misc[0] = keep; s.misc[1] = 0; }
+      __syncthreads();
+      if (!overflow) break;
+      need_scan = true;
+    }
+  }
+  // ---- final ordering and output
+  __syncthreads();
+  sort_cands(s, tid);
+  const int cnt = min(min(s.misc[0], CAP2), k);
+  for (int i = tid; i < k; i += TOPK_THREADS) {
+    if (i < cnt) { os[i] = key_f64(s.ckey[i]); oi[i] = id_base + static_cast<int64_t>(s.cdoc[i]); }
+    else         { os[i] = 0.0; oi[i] = -1; }
+  }
+}
+
+__global__ void __launch_bounds__(TOPK_THREADS, 1)
 bm25_topk_kernel(const Bm25Dev ix, const int32_t* __restrict__ q_terms_all, int max_qt, int k, int64_t id_base,
                  int blocks_per_split, int64_t nq, double* __restrict__ part_scores, int64_t* __restrict__ part_ids) {
-  extern __shared__ __align__(16) uint8_t bsm[];
-  const Bm25Smem s = carve(bsm);
-  const int tid = threadIdx.x, lane = tid & 31;
+  extern __shared__ __align__(128) uint8_t bsm[];
+  TopkSmem s = carve_topk(bsm);
+  s.gglobal = ix.gtab;
+  const int tid = threadIdx.x;
   const int64_t q = blockIdx.x;
   const int split = blockIdx.y;
   const int32_t* q_terms = q_terms_all + q * max_qt;
-  const bool g_in_smem = ix.n_g <= GTAB_SMEM;
-  if (g_in_smem) for (int i = tid; i < ix.n_g; i += BM25_THREADS) s.gtab[i] = ix.gtab[i];
-  for (int i = tid; i < CAND_CAP; i += BM25_THREADS) { s.ckey[i] = 0ull; s.cdoc[i] = 0xFFFFFFFFu; }
-  if (tid == 0) s.misc[0] = 0;
-  __syncthreads();
-
-  double thr = 0.0;                               // docs with score <= 0 are never candidates
   const int b0 = split * blocks_per_split;
   const int b1 = min(b0 + blocks_per_split, ix.nb);
-  for (int b = b0; b < b1; ++b) {
-    bm25_accumulate_block(ix, s, q_terms, max_qt, b, g_in_smem);
-    const int64_t doc0 = static_cast<int64_t>(b) << DOC_BLOCK_LOG2;
-    const int n_here = static_cast<int>(min(static_cast<long long>(DOC_BLOCK), static_cast<long long>(ix.n_docs - doc0)));
-    for (int base = 0; base < n_here; base += BM25_THREADS) {
-      const int d = base + tid;
-      const double v = d < n_here ? s.acc[d] : 0.0;
-      const bool pass = v > thr;
-      const uint32_t m = __ballot_sync(0xffffffffu, pass);
-      int pos = 0;
-      if (lane == 0 && m) pos = atomicAdd(&s.misc[0], __popc(m));
-      pos = __shfl_sync(0xffffffffu, pos, 0);
-      if (pass) {
-        const int slot = pos + __popc(m & ((1u << lane) - 1u));
-        s.ckey[slot] = f64_key(v);
-        s.cdoc[slot] = static_cast<uint32_t>(doc0 + d);
-      }
-      __syncthreads();
-      const int cnt = s.misc[0];
-      if (cnt > CAND_CAP - BM25_THREADS) {        // next sweep could overflow: keep the k best
-        bitonic_sort_cands(s);
-        const int keep = min(cnt, k);
-        if (cnt >= k) thr = key_f64(s.ckey[k - 1]);
-        __syncthreads();
-        for (int i = keep + tid; i < CAND_CAP; i += BM25_THREADS) { s.ckey[i] = 0ull; s.cdoc[i] = 0xFFFFFFFFu; }
-        if (tid == 0) s.misc[0] = keep;
-        __syncthreads();
-      }
-    }
-    __syncthreads();
+  // replication factor of the factor table: as many bank-shifted copies as fit in 64 KB (at most 8)
+  int rep_log2 = -1;
+  if (ix.n_g * 8 <= GREP_BYTES) {
+    rep_log2 = 0;
+    while (rep_log2 < 3 && ((ix.n_g * 8) << (rep_log2 + 1)) <= GREP_BYTES) ++rep_log2;
   }
-  bitonic_sort_cands(s);
-  const int cnt = min(s.misc[0], k);
+  if (rep_log2 >= 0) {
+    const int rep = 1 << rep_log2;
+    for (int i = tid; i < ix.n_g * rep; i += TOPK_THREADS) s.grep[i] = ix.gtab[i >> rep_log2];
+  }
+  for (int i = tid; i < DOC_BLOCK / 2; i += TOPK_THREADS) reinterpret_cast<double2*>(s.acc)[i] = make_double2(0.0, 0.0);
+  for (int i = tid; i < CAP2; i += TOPK_THREADS) { s.ckey[i] = 0ull; s.cdoc[i] = 0xFFFFFFFFu; }
+  if (tid < max_qt) {
+    const int t = q_terms[tid];
+    const bool ok = t >= 0 && t < ix.n_terms;
+    s.idf[tid] = ok ? ix.idf[t] : 0.0;
+    s.dslot[tid] = ok ? ix.dense_slot[t] : -1;
+  }
+  if (tid == 0) { s.misc[0] = 0; s.misc[1] = 0; }
+  __syncthreads();
   double* os = part_scores + (static_cast<int64_t>(split) * nq + q) * k;
   int64_t* oi = part_ids + (static_cast<int64_t>(split) * nq + q) * k;
-  for (int i = tid; i < k; i += BM25_THREADS) {
-    if (i < cnt) { os[i] = key_f64(s.ckey[i]); oi[i] = id_base + static_cast<int64_t>(s.cdoc[i]); }
-    else         { os[i] = 0.0; oi[i] = -1; }
+  switch (rep_log2) {
+    case 3:  bm25_topk_body<3>(ix, s, q_terms, max_qt, k, id_base, b0, b1, os, oi); break;
+    case 2:  bm25_topk_body<2>(ix, s, q_terms, max_qt, k, id_base, b0, b1, os, oi); break;
+    case 1:  bm25_topk_body<1>(ix, s, q_terms, max_qt, k, id_base, b0, b1, os, oi); break;
+    case 0:  bm25_topk_body<0>(ix, s, q_terms, max_qt, k, id_base, b0, b1, os, oi); break;
+    default: bm25_topk_body<-1>(ix, s, q_terms, max_qt, k, id_base, b0, b1, os, oi); break;
   }
 }
 
@@ -262,6 +503,8 @@ struct arb_bm25 {
   uint32_t* post = nullptr;
   double* idf = nullptr;
   double* gtab = nullptr;
+  int* dense_slot = nullptr;
+  uint32_t* fine_off = nullptr;
   std::vector<int64_t> df;      // host copy of per-term df (roofline accounting)
 };
 
@@ -269,7 +512,7 @@ static int bm25_set_smem_attrs() {
   static std::once_flag once;
   static cudaError_t err = cudaSuccess;
   std::call_once(once, [] {
-    err = cudaFuncSetAttribute(bm25_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, BM25_SMEM);
+    err = cudaFuncSetAttribute(bm25_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TOPK_SMEM);
     if (err == cudaSuccess)
       err = cudaFuncSetAttribute(bm25_scores_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, BM25_SMEM);
   });
@@ -283,7 +526,7 @@ extern "C" int arb_bm25_create(arb_bm25** out, int64_t n_docs, int64_t n_terms, 
   ARB_CHECK(out != nullptr, ARB_EINVAL, "arb_bm25_create: out is NULL");
   ARB_CHECK(n_docs >= 0 && n_docs < (int64_t(1) << 31), ARB_ELIMIT, "arb_bm25_create: n_docs must be < 2^31");
   ARB_CHECK(n_terms >= 0 && term_ptr != nullptr, ARB_EINVAL, "arb_bm25_create: bad term table");
-  ARB_CHECK(n_g >= 0 && n_g <= (int64_t(1) << GCODE_BITS), ARB_ELIMIT, "arb_bm25_create: more than 2^18 distinct (tf, doc_len) pairs");
+  ARB_CHECK(n_g >= 0 && n_g < (int64_t(1) << GCODE_BITS), ARB_ELIMIT, "arb_bm25_create: 2^18 or more distinct (tf, doc_len) pairs");
   const int64_t n_post = term_ptr[n_terms];
   ARB_CHECK(n_post >= 0 && n_post < 0xFFFFFFF0ll, ARB_ELIMIT, "arb_bm25_create: more than 2^32 postings per shard");
   ARB_CHECK(n_post == 0 || (post_doc && post_gcode && idf && gtab), ARB_EINVAL, "arb_bm25_create: NULL posting arrays");
@@ -294,7 +537,7 @@ extern "C" int arb_bm25_create(arb_bm25** out, int64_t n_docs, int64_t n_terms, 
   arb_bm25* bm = new arb_bm25();
   auto fail = [&](int rc) { arb_bm25_destroy(bm); return rc; };
   const size_t n_off = static_cast<size_t>(n_terms) * nb + 1;
-  if (cudaMalloc(&bm->blk_off, n_off * 4) != cudaSuccess || cudaMalloc(&bm->post, std::max<size_t>(n_post, 1) * 4) != cudaSuccess ||
+  if (cudaMalloc(&bm->blk_off, n_off * 4) != cudaSuccess || cudaMalloc(&bm->post, (std::max<size_t>(n_post, 1) + 8) * 4) != cudaSuccess ||
       cudaMalloc(&bm->idf, std::max<size_t>(n_terms, 1) * 8) != cudaSuccess || cudaMalloc(&bm->gtab, std::max<size_t>(n_g, 1) * 8) != cudaSuccess) {
     cudaGetLastError();
     set_error("arb_bm25_create: out of device memory");
@@ -320,6 +563,33 @@ extern "C" int arb_bm25_create(arb_bm25** out, int64_t n_docs, int64_t n_terms, 
     }
     bm25_blkoff_kernel<<<static_cast<unsigned>((n_off + 255) / 256), 256, 0, st>>>(d_ptr.as<int64_t>(), d_doc.as<int32_t>(), n_terms, nb, n_post, bm->blk_off);
     count_launch();
+    // dense terms (df >= n_docs/256, at least 256 postings) get per-512-doc-slice offsets
+    {
+      const int n_slices = static_cast<int>(std::max<int64_t>(1, (n_docs + 511) / 512));
+      std::vector<int32_t> slot(std::max<int64_t>(n_terms, 1), -1), dterms;
+      const int64_t thresh = std::max<int64_t>(256, n_docs / 256);
+      for (int64_t t = 0; t < n_terms; ++t)
+        if (term_ptr[t + 1] - term_ptr[t] >= thresh) { slot[t] = static_cast<int32_t>(dterms.size()); dterms.push_back(static_cast<int32_t>(t)); }
+      const size_t n_fine = std::max<size_t>(1, dterms.size() * static_cast<size_t>(n_slices + 1));
+      if (cudaMalloc(&bm->dense_slot, slot.size() * 4) != cudaSuccess || cudaMalloc(&bm->fine_off, n_fine * 4) != cudaSuccess) {
+        cudaGetLastError(); set_error("arb_bm25_create: out of device memory (fine offsets)"); return fail(ARB_ENOMEM);
+      }
+      e = cudaMemcpyAsync(bm->dense_slot, slot.data(), slot.size() * 4, cudaMemcpyHostToDevice, st);
+      AsyncBuf d_dt;
+      if (e == cudaSuccess && !dterms.empty()) {
+        e = d_dt.alloc(dterms.size() * 4, st);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(d_dt.p, dterms.data(), dterms.size() * 4, cudaMemcpyHostToDevice, st);
+        if (e == cudaSuccess) {
+          bm25_fineoff_kernel<<<static_cast<unsigned>((n_fine + 255) / 256), 256, 0, st>>>(
+              d_ptr.as<int64_t>(), d_doc.as<int32_t>(), d_dt.as<int32_t>(), static_cast<int>(dterms.size()), n_slices, bm->fine_off);
+          count_launch();
+        }
+      }
+      if (e == cudaSuccess) e = cudaStreamSynchronize(st);       // host vectors die at scope end
+      if (e != cudaSuccess) return fail(cuda_fail(e, "bm25 fine offsets", __FILE__, __LINE__));
+      bm->dev.n_slices = n_slices;
+      bm->dev.n_dense = static_cast<int>(dterms.size());
+    }
     e = cudaGetLastError();
     if (e == cudaSuccess) e = cudaStreamSynchronize(st);
     if (e != cudaSuccess) return fail(cuda_fail(e, "bm25 build kernels", __FILE__, __LINE__));
@@ -329,6 +599,7 @@ extern "C" int arb_bm25_create(arb_bm25** out, int64_t n_docs, int64_t n_terms, 
   bm->dev.n_docs = n_docs; bm->dev.n_terms = n_terms; bm->dev.n_post = n_post;
   bm->dev.nb = nb; bm->dev.n_g = static_cast<int>(n_g);
   bm->dev.blk_off = bm->blk_off; bm->dev.post = bm->post; bm->dev.idf = bm->idf; bm->dev.gtab = bm->gtab;
+  bm->dev.dense_slot = bm->dense_slot; bm->dev.fine_off = bm->fine_off;
   *out = bm;
   return ARB_OK;
 }
@@ -339,6 +610,8 @@ extern "C" int arb_bm25_destroy(arb_bm25* bm) {
   if (bm->post) cudaFree(bm->post);
   if (bm->idf) cudaFree(bm->idf);
   if (bm->gtab) cudaFree(bm->gtab);
+  if (bm->dense_slot) cudaFree(bm->dense_slot);
+  if (bm->fine_off) cudaFree(bm->fine_off);
   delete bm;
   return ARB_OK;
 }
@@ -410,7 +683,7 @@ extern "C" int arb_bm25_search(const arb_bm25* bm, const int32_t* q_terms, int64
   dim3 grid(static_cast<unsigned>(nq), static_cast<unsigned>(n_split));
   {
     ProfileScope pscope(PROF_BM25_TOPK, st);
-    bm25_topk_kernel<<<grid, BM25_THREADS, BM25_SMEM, st>>>(bm->dev, d_terms, max_qt, k, id_base, bps, nq, ps, pi);
+    bm25_topk_kernel<<<grid, TOPK_THREADS, TOPK_SMEM, st>>>(bm->dev, d_terms, max_qt, k, id_base, bps, nq, ps, pi);
   }
   ARB_LAUNCH_OK();
   if (n_split > 1) {
