@@ -35,6 +35,23 @@ ProfileScope::~ProfileScope() {
   g_prof.push_back({kind, e0, e1});
 }
 
+// Keep freed scratch in the stream-ordered pool instead of returning it to the driver at
+// every synchronisation (the default release threshold is 0): per-call scratch such as the
+// dense candidate lists would otherwise be re-mapped on every search.
+void configure_pool_once() {
+  static std::once_flag once[64];
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return;
+  std::call_once(once[dev], [dev] {
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+      uint64_t keep = ~0ull;
+      cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    }
+    cudaGetLastError();
+  });
+}
+
 int num_sms() {
   static int sms[64] = {0};
   int dev = 0;

@@ -20,6 +20,7 @@ namespace arb {
 void set_error(const std::string& msg);
 int  cuda_fail(cudaError_t e, const char* what, const char* file, int line);
 void count_launch(int n = 1);
+void configure_pool_once();
 
 #define ARB_CUDA(expr)                                                         \
   do {                                                                         \
@@ -44,6 +45,7 @@ struct AsyncBuf {
   void* p = nullptr;
   cudaStream_t s = nullptr;
   cudaError_t alloc(size_t bytes, cudaStream_t stream) {
+    configure_pool_once();
     s = stream;
     if (bytes == 0) bytes = 16;
     return cudaMallocAsync(&p, bytes, stream);

@@ -1,0 +1,66 @@
+"""World-size-2 gloo test of the sharding host logic (runs on CPU): global BM25 statistics from
+per-rank shards must equal the single-corpus statistics bit for bit, and the shard index arrays
+must hold exactly the single index's postings."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+import ano_rag_b200  # noqa: F401
+from ano_rag_b200 import bm25_build as bb
+from ano_rag_b200 import sharded, synth
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, n_docs, vocab, out):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        ptr, tok = synth.bm25_corpus(n_docs, vocab, mean_len=12, seed=5)
+        lo, hi = sharded.shard_range(n_docs, world, rank)
+        sptr = ptr[lo:hi + 1] - ptr[lo]
+        stok = tok[ptr[lo]:ptr[hi]]
+        base = sharded.token_bases(len(stok))
+        assert base == int(ptr[lo])
+        stats = sharded.global_bm25_stats(sptr, stok, vocab, base)
+        arr = bb.build_arrays(sptr, stok, vocab, stats=stats)
+        np.savez(os.path.join(out, f"r{rank}.npz"), idf=stats.idf, df=stats.df, avgdl=stats.avgdl,
+                 average_idf=stats.average_idf, n=stats.n_docs, term_ptr=arr.term_ptr, post_doc=arr.post_doc + lo,
+                 g=arr.gtab[arr.post_gcode])
+    finally:
+        dist.destroy_process_group()
+
+
+def test_global_stats_and_shards_world2(tmp_path):
+    n_docs, vocab, world = 700, 90, 2
+    mp.spawn(_worker, args=(world, _free_port(), n_docs, vocab, str(tmp_path)), nprocs=world, join=True)
+    ptr, tok = synth.bm25_corpus(n_docs, vocab, mean_len=12, seed=5)
+    whole = bb.build_arrays(ptr, tok, vocab)
+    shards = [np.load(os.path.join(str(tmp_path), f"r{r}.npz")) for r in range(world)]
+    for z in shards:
+        assert int(z["n"]) == n_docs and float(z["avgdl"]) == whole.stats.avgdl
+        assert float(z["average_idf"]) == whole.stats.average_idf
+        assert np.array_equal(z["idf"], whole.stats.idf) and np.array_equal(z["df"], whole.stats.df)
+    for t in range(vocab):
+        docs = np.concatenate([z["post_doc"][z["term_ptr"][t]:z["term_ptr"][t + 1]] for z in shards])
+        g = np.concatenate([z["g"][z["term_ptr"][t]:z["term_ptr"][t + 1]] for z in shards])
+        s, e = whole.term_ptr[t], whole.term_ptr[t + 1]
+        assert np.array_equal(docs, whole.post_doc[s:e])
+        assert np.array_equal(g, whole.gtab[whole.post_gcode[s:e]])
+
+
+def test_shard_range_covers_rows():
+    for n, w in [(10, 3), (1_000_000, 8), (5, 8), (0, 2)]:
+        spans = [sharded.shard_range(n, w, r) for r in range(w)]
+        assert spans[0][0] == 0 and spans[-1][1] == n
+        assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
