@@ -69,6 +69,7 @@ _SIGS = {
                                 c_int, c_void_p]),
     "arb_bm25_scores": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_int, c_int, c_int64, c_void_p, c_int,
                                 c_void_p]),
+    "arb_combine_fields": (c_int, [c_int, POINTER(c_void_p), POINTER(c_double), c_int64, c_int64, c_void_p, c_void_p]),
     "arb_fuse": (c_int, [c_int, POINTER(c_double), c_double, c_int, c_int64, POINTER(c_void_p), POINTER(c_void_p),
                          POINTER(c_int), POINTER(c_int), c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
     "arb_merge_topk": (c_int, [c_int, c_void_p, c_void_p, c_int, c_int64, c_int, c_int, c_void_p, c_void_p,

@@ -485,6 +485,15 @@ bm25_normalise_kernel(double* __restrict__ out, int64_t n_out) {
     for (int64_t i = threadIdx.x; i < n_out; i += blockDim.x) row[i] = __ddiv_rn(row[i], m);
 }
 
+struct FieldPtrs { const double* s[8]; double w[8]; };
+__global__ void combine_fields_kernel(FieldPtrs f, int n_fields, int64_t n, double* __restrict__ out) {
+  int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  if (i >= n) return;
+  double total = 0.0;
+  for (int k = 0; k < n_fields; ++k) total = __dadd_rn(total, __dmul_rn(f.w[k], f.s[k][i]));
+  out[i] = total;
+}
+
 __global__ void fill_f64_kernel(double* p, double v, int64_t n) {
   int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
   if (i < n) p[i] = v;
@@ -733,6 +742,24 @@ extern "C" int arb_bm25_scores(const arb_bm25* bm, const int32_t* q_terms, int64
   if (!out_is_device) {
     ARB_CUDA(cudaMemcpyAsync(out, d_out, static_cast<size_t>(total) * 8, cudaMemcpyDeviceToHost, st));
     ARB_CUDA(cudaStreamSynchronize(st));
+  }
+  return ARB_OK;
+}
+
+extern "C" int arb_combine_fields(int n_fields, const double* const* field_scores, const double* weights, int64_t n,
+                                  int64_t nq, double* out, void* stream) {
+  ARB_CHECK(n_fields >= 1 && n_fields <= 8, ARB_ELIMIT, "arb_combine_fields: 1..8 fields");
+  ARB_CHECK(field_scores && weights && out && n >= 0, ARB_EINVAL, "arb_combine_fields: bad argument");
+  ARB_CHECK(nq == 0 || (nq > 0 && n % nq == 0), ARB_EINVAL, "arb_combine_fields: n must be a multiple of nq");
+  if (n == 0) return ARB_OK;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  FieldPtrs f;
+  for (int k = 0; k < 8; ++k) { f.s[k] = k < n_fields ? field_scores[k] : nullptr; f.w[k] = k < n_fields ? weights[k] : 0.0; }
+  combine_fields_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, st>>>(f, n_fields, n, out);
+  ARB_LAUNCH_OK();
+  if (nq > 0) {
+    bm25_normalise_kernel<<<static_cast<unsigned>(nq), 1024, 0, st>>>(out, n / nq);
+    ARB_LAUNCH_OK();
   }
   return ARB_OK;
 }

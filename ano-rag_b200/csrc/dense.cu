@@ -46,6 +46,8 @@ constexpr int MAX_TERMS = 6;
 
 constexpr uint32_t KEY_NEG_INF = 0x007FFFFFu;     // f32_key(-inf)
 
+struct IvfItem { uint32_t row_lo, row_hi; };   // rows of the inverted list this A-tile (item i = gathered rows [128i, 128i+128)) scans
+
 struct DenseParams {
   int nq;
   uint32_t n_rows;
@@ -58,6 +60,13 @@ struct DenseParams {
   uint2* lists;             // [n_items, 128, C] {row index, ordered score key}
   int* counts;              // [n_items, 128]
   uint32_t* gthr;           // [n_qtiles*128] shared per-query threshold key
+  // IVF list scan (template flag IVF): work items come from a device-built table
+  const IvfItem* items;     // [n_items] A-tile of gathered queries x one inverted list
+  const int* n_items_ptr;   // number of items (known only on the device)
+  const int* row_query;     // [pair rows] query of each gathered row, -1 = padding
+  const int* pair_pos;      // [nq, nprobe] gathered-row position of each (query, probe) pair
+  int nprobe;
+  const int64_t* row_ids;   // [n_rows] original id of each stored (list-grouped) row
 };
 
 // ----------------------------------------------------------------------------
@@ -122,7 +131,7 @@ __device__ __forceinline__ uint32_t warp_select(uint2* list, int cnt, int k, int
 // ----------------------------------------------------------------------------
 // The fused GEMM + threshold-select kernel.
 // ----------------------------------------------------------------------------
-template <int EPL>
+template <int EPL, bool IVF>
 __global__ void __launch_bounds__(DENSE_THREADS, 1)
 dense_topk_kernel(const __grid_constant__ CUtensorMap tmap_a,
                   const __grid_constant__ CUtensorMap tmap_b, const DenseParams p) {
@@ -153,23 +162,36 @@ dense_topk_kernel(const __grid_constant__ CUtensorMap tmap_a,
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
 
   const int kb_total = p.n_terms * p.kb_per_term;
+  const int n_items = IVF ? __ldg(p.n_items_ptr) : p.n_items;
+  // work item -> (A tile row, first B row, n-tile range, end of the valid B rows)
+  auto decode = [&](int item, int& a_row0, uint32_t& b_row0, int& t0, int& t1, uint32_t& b_end) {
+    if (IVF) {
+      const IvfItem it = p.items[item];
+      a_row0 = item * BLOCK_M; b_row0 = it.row_lo; b_end = it.row_hi;
+      t0 = 0; t1 = static_cast<int>((it.row_hi - it.row_lo + BLOCK_N - 1) / BLOCK_N);
+    } else {
+      const int qt = item % p.n_qtiles, sp = item / p.n_qtiles;
+      a_row0 = qt * BLOCK_M; b_row0 = 0; b_end = p.n_rows;
+      t0 = sp * p.tiles_per_split; t1 = min(t0 + p.tiles_per_split, p.n_ntiles);
+    }
+  };
 
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
-      for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
-        const int qt = item % p.n_qtiles, sp = item / p.n_qtiles;
-        const int t0 = sp * p.tiles_per_split;
-        const int t1 = min(t0 + p.tiles_per_split, p.n_ntiles);
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+        int a_row0, t0, t1; uint32_t b_row0, b_end;
+        decode(item, a_row0, b_row0, t0, t1, b_end);
         for (int t = t0; t < t1; ++t) {
           for (int term = 0; term < p.n_terms; ++term) {
             for (int kb = 0; kb < p.kb_per_term; ++kb) {
               mbar_wait(&empty[stage], phase ^ 1u);
               uint8_t* sa = smem + stage * STAGE_BYTES;
               mbar_expect_tx(&full[stage], STAGE_BYTES);
-              tma_load_2d(&tmap_a, &full[stage], sa, p.a_col[term] + kb * BLOCK_K, qt * BLOCK_M, EVICT_LAST);
-              tma_load_2d(&tmap_b, &full[stage], sa + A_BYTES, p.b_col[term] + kb * BLOCK_K, t * BLOCK_N, EVICT_NORMAL);
+              tma_load_2d(&tmap_a, &full[stage], sa, p.a_col[term] + kb * BLOCK_K, a_row0, EVICT_LAST);
+              tma_load_2d(&tmap_b, &full[stage], sa + A_BYTES, p.b_col[term] + kb * BLOCK_K,
+                          static_cast<int32_t>(b_row0) + t * BLOCK_N, EVICT_NORMAL);
               if (++stage == STAGES) { stage = 0; phase ^= 1u; }
             }
           }
@@ -182,10 +204,9 @@ dense_topk_kernel(const __grid_constant__ CUtensorMap tmap_a,
       constexpr uint32_t idesc = umma_idesc_bf16(BLOCK_M, BLOCK_N);
       int stage = 0; uint32_t phase = 0;
       int acc = 0; uint32_t acc_phase = 0;
-      for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
-        const int sp = item / p.n_qtiles;
-        const int t0 = sp * p.tiles_per_split;
-        const int t1 = min(t0 + p.tiles_per_split, p.n_ntiles);
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+        int a_row0, t0, t1; uint32_t b_row0, b_end;
+        decode(item, a_row0, b_row0, t0, t1, b_end);
         for (int t = t0; t < t1; ++t) {
           mbar_wait(&tempty[acc], acc_phase ^ 1u);
           tc_fence_after();
@@ -214,12 +235,11 @@ dense_topk_kernel(const __grid_constant__ CUtensorMap tmap_a,
     const int quad = warp & 3;                   // TMEM lane quadrant this warp may read
     const int row = quad * 32 + lane;            // query row inside the tile
     int acc = 0; uint32_t acc_phase = 0;
-    for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
-      const int qt = item % p.n_qtiles, sp = item / p.n_qtiles;
-      const int t0 = sp * p.tiles_per_split;
-      const int t1 = min(t0 + p.tiles_per_split, p.n_ntiles);
-      const int q = qt * BLOCK_M + row;
-      const bool valid = q < p.nq;
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+      int a_row0, t0, t1; uint32_t b_row0, b_end;
+      decode(item, a_row0, b_row0, t0, t1, b_end);
+      const int q = IVF ? __ldg(p.row_query + a_row0 + row) : a_row0 + row;
+      const bool valid = q >= 0 && q < p.nq;
       uint2* list = p.lists + (static_cast<size_t>(item) * BLOCK_M + row) * C;
       int cnt = 0;
       uint32_t thr_key = KEY_NEG_INF;
@@ -231,8 +251,8 @@ dense_topk_kernel(const __grid_constant__ CUtensorMap tmap_a,
         }
         mbar_wait(&tfull[acc], acc_phase);
         tc_fence_after();
-        const uint32_t n_base = static_cast<uint32_t>(t) * BLOCK_N;
-        const bool tail = n_base + BLOCK_N > p.n_rows;
+        const uint32_t n_base = b_row0 + static_cast<uint32_t>(t) * BLOCK_N;
+        const bool tail = n_base + BLOCK_N > b_end;
         const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * BLOCK_N;
 #pragma unroll 1
         for (int c = 0; c < BLOCK_N / 32; ++c) {
@@ -256,7 +276,7 @@ dense_topk_kernel(const __grid_constant__ CUtensorMap tmap_a,
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
               float s = __uint_as_float(v[j]);
-              if (s > thr && idx0 + j < p.n_rows) { list[cnt] = make_uint2(idx0 + j, f32_key(s)); ++cnt; }
+              if (s > thr && idx0 + j < b_end) { list[cnt] = make_uint2(idx0 + j, f32_key(s)); ++cnt; }
             }
           }
           uint32_t need = __ballot_sync(0xffffffffu, cnt > C - 32);
@@ -269,7 +289,7 @@ dense_topk_kernel(const __grid_constant__ CUtensorMap tmap_a,
             if (lane == r) {
               cnt = p.k;
               if (T > thr_key) { thr_key = T; thr = key_f32(T); }
-              atomicMax(p.gthr + q, T);
+              atomicMax(p.gthr + (valid ? q : 0), T);
             }
           }
         }
@@ -291,7 +311,7 @@ dense_topk_kernel(const __grid_constant__ CUtensorMap tmap_a,
 // Merge the per-item candidate lists of each query into its final top-k.
 // One warp per query.
 // ----------------------------------------------------------------------------
-template <int EPL>
+template <int EPL, bool IVF>
 __global__ void __launch_bounds__(128)
 dense_merge_kernel(const DenseParams p, int64_t id_base, float* __restrict__ out_scores,
                    int64_t* __restrict__ out_ids) {
@@ -305,8 +325,16 @@ dense_merge_kernel(const DenseParams p, int64_t id_base, float* __restrict__ out
   const uint32_t lt = (1u << lane) - 1u;
   uint32_t thr_key = p.gthr[q];
   int cnt = 0;
-  for (int sp = 0; sp < p.n_splits; ++sp) {
-    const size_t slot = (static_cast<size_t>(sp) * p.n_qtiles + qt) * BLOCK_M + row;
+  const int n_parts = IVF ? p.nprobe : p.n_splits;
+  for (int sp = 0; sp < n_parts; ++sp) {
+    size_t slot;
+    if (IVF) {
+      const int pos = p.pair_pos[static_cast<size_t>(q) * p.nprobe + sp];
+      if (pos < 0) continue;
+      slot = static_cast<size_t>(pos);
+    } else {
+      slot = (static_cast<size_t>(sp) * p.n_qtiles + qt) * BLOCK_M + row;
+    }
     const uint2* L = p.lists + slot * C;
     const int n = p.counts[slot];
     for (int b = 0; b < n; b += 32) {
@@ -335,7 +363,7 @@ dense_merge_kernel(const DenseParams p, int64_t id_base, float* __restrict__ out
       rank += (o.y > e.y || (o.y == e.y && o.x < e.x)) ? 1 : 0;
     }
     out_scores[static_cast<size_t>(q) * p.k + rank] = key_f32(e.y);
-    out_ids[static_cast<size_t>(q) * p.k + rank] = id_base + static_cast<int64_t>(e.x);
+    out_ids[static_cast<size_t>(q) * p.k + rank] = id_base + (IVF ? p.row_ids[e.x] : static_cast<int64_t>(e.x));
   }
   for (int j = cnt + lane; j < p.k; j += 32) {
     out_scores[static_cast<size_t>(q) * p.k + j] = -3.4028234663852886e38f;   // faiss "no result"
@@ -636,18 +664,18 @@ static int run_dense(const arb_index* ix, const __nv_bfloat16* qplanes, int q_pl
   static std::once_flag attr_once;
   static cudaError_t attr_err = cudaSuccess;
   std::call_once(attr_once, [] {
-    attr_err = cudaFuncSetAttribute(dense_topk_kernel<EPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, DENSE_SMEM);
+    attr_err = cudaFuncSetAttribute(dense_topk_kernel<EPL, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, DENSE_SMEM);
   });
   ARB_CUDA(attr_err);
   {
     ProfileScope ps(PROF_DENSE_TOPK, st);
-    dense_topk_kernel<EPL><<<grid, DENSE_THREADS, DENSE_SMEM, st>>>(ta, tb, p);
+    dense_topk_kernel<EPL, false><<<grid, DENSE_THREADS, DENSE_SMEM, st>>>(ta, tb, p);
   }
   ARB_LAUNCH_OK();
   const int wpb = 4;
   {
     ProfileScope ps(PROF_DENSE_MERGE, st);
-    dense_merge_kernel<EPL><<<static_cast<unsigned>((nq + wpb - 1) / wpb), wpb * 32, wpb * C * sizeof(uint2), st>>>(
+    dense_merge_kernel<EPL, false><<<static_cast<unsigned>((nq + wpb - 1) / wpb), wpb * 32, wpb * C * sizeof(uint2), st>>>(
         p, id_base, d_scores, d_ids);
   }
   ARB_LAUNCH_OK();

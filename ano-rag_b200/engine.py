@@ -200,6 +200,18 @@ class BM25Index:
                                           ids.ctypes.data, 0, _stream_ptr()))
         return scores, ids
 
+    def scores_device(self, q_terms, n_out: Optional[int] = None, normalise: bool = False):
+        """Full fp64 score vectors [nq, n_out] left on the device (torch CUDA tensor)."""
+        b = self._terms(q_terms)
+        nq, mq = b.shape
+        n_out = self.n_docs if n_out is None else int(n_out)
+        device = b.device if b.is_device else torch.device("cuda", torch.cuda.current_device())
+        with torch.cuda.device(device):
+            out = torch.empty((nq, n_out), dtype=torch.float64, device=device)
+            nat.check(nat.lib.arb_bm25_scores(self._h, b.ptr, nq, mq, b.is_device, 1 if normalise else 0, n_out,
+                                              out.data_ptr(), 1, _stream_ptr(device)))
+        return out
+
     def scores(self, q_terms, n_out: Optional[int] = None, normalise: bool = False) -> np.ndarray:
         """Full fp64 score vectors [nq, n_out] on the host (bm25_scores semantics)."""
         b = self._terms(q_terms)
@@ -214,6 +226,19 @@ class BM25Index:
             nat.check(nat.lib.arb_bm25_scores(self._h, b.ptr, nq, mq, 0, 1 if normalise else 0, n_out,
                                               out.ctypes.data, 0, _stream_ptr()))
         return out
+
+
+def combine_fields(field_scores: Sequence, weights: Sequence[float], normalise_rows: bool):
+    """FieldWeightedBM25 combination of per-field CUDA score tensors [nq, n] -> CUDA tensor [nq, n]."""
+    first = field_scores[0]
+    nq, n = first.shape
+    out = torch.empty_like(first)
+    ptrs = (ctypes.c_void_p * len(field_scores))(*[t.data_ptr() for t in field_scores])
+    w = (ctypes.c_double * len(weights))(*[float(x) for x in weights])
+    with torch.cuda.device(first.device):
+        nat.check(nat.lib.arb_combine_fields(len(field_scores), ptrs, w, nq * n, nq if normalise_rows else 0,
+                                             out.data_ptr(), _stream_ptr(first.device)))
+    return out
 
 
 _SRC = ("dense", "bm25", "graph", "path")

@@ -113,6 +113,66 @@ class GpuBM25:
         self.index.close()
 
 
+class FieldWeightedBM25:
+    """Reference :66-145: per-field (title, entities, content) BM25 with SimpleBM25 arithmetic and
+    per-field idf / avgdl, combined as ``total += weight * field_score`` in field order.  Each field is
+    its own device index; the combination and the max-normalisation run on the device (csrc/bm25.cu)."""
+
+    def __init__(self, corpus: List[Dict[str, List[str]]], field_weights: Dict[str, float] = None, k1: float = 1.5,
+                 b: float = 0.75):
+        self.corpus = corpus
+        self.field_weights = field_weights or {"title": 2.0, "entities": 1.5, "content": 1.0}
+        self.k1, self.b = k1, b
+        self.doc_count = len(corpus)
+        self.fields = {f: GpuBM25([doc.get(f, []) for doc in corpus], variant="simple", k1=k1, b=b)
+                       for f in self.field_weights}
+        self.field_stats = {f: {"doc_lens": c.doc_len, "avgdl": c.avgdl} for f, c in self.fields.items()}
+        self.field_idf = {f: c.idf for f, c in self.fields.items()}
+
+    def _scores_device(self, query_tokens: Sequence[str], normalise: bool, n_out: Optional[int] = None):
+        per_field = [c.index.scores_device(c.encode_queries([list(query_tokens)]), n_out=n_out)
+                     for c in self.fields.values()]
+        return engine.combine_fields(per_field, list(self.field_weights.values()), normalise)
+
+    def get_scores(self, query: List[str]) -> List[float]:
+        if self.doc_count == 0:
+            return []
+        return self._scores_device(query, False)[0].cpu().numpy().tolist()
+
+    def close(self):
+        for c in self.fields.values():
+            c.close()
+
+
+def build_field_weighted_bm25_corpus(notes: List[Dict[str, Any]], field_weights: Dict[str, float] = None) -> FieldWeightedBM25:
+    """Reference :148-190: title / entities (joined list) / content, each tokenised with tokenize_text."""
+    if field_weights is None:
+        field_weights = {"title": 2.0, "entities": 1.5, "content": 1.0}
+    field_corpus = []
+    for note in notes:
+        entities = note.get("entities", []) or []
+        entities_text = " ".join(entities) if isinstance(entities, list) else str(entities)
+        field_corpus.append({"title": tokenize_text(note.get("title", "") or ""),
+                             "entities": tokenize_text(entities_text),
+                             "content": tokenize_text(note.get("content", "") or "")})
+    return FieldWeightedBM25(field_corpus, field_weights)
+
+
+def field_weighted_bm25_scores(corpus: FieldWeightedBM25, docs: List[Dict[str, Any]], query: str) -> List[float]:
+    """Reference :193-234: same wrapper as bm25_scores (pad / truncate to len(docs), max-normalise)."""
+    try:
+        query_tokens = tokenize_text(query)
+        if not query_tokens:
+            logger.warning("Empty query tokens, returning zero scores")
+            return [0.0] * len(docs)
+        if len(docs) == 0:
+            return []
+        return corpus._scores_device(query_tokens, True, n_out=len(docs))[0].cpu().numpy().tolist()
+    except Exception as e:
+        logger.error(f"Error calculating field-weighted BM25 scores: {e}")
+        return [0.0] * len(docs)
+
+
 def build_bm25_corpus(notes: List[Dict[str, Any]], text_fn: Callable[[Dict[str, Any]], str]) -> Any:
     """Reference :244-283: tokenise every note (``[]`` on empty text or error), then
     build the corpus object.  Okapi first (what runs wherever rank_bm25 is installed);

@@ -155,6 +155,12 @@ ARB_API int arb_bm25_scores(const arb_bm25* bm, const int32_t* q_terms, int64_t 
                     int q_is_device, int normalise, int64_t n_out, double* out,
                     int out_is_device, void* stream);
 
+/* FieldWeightedBM25.get_scores combination (utils/bm25_search.py:117-145):
+ * out[i] = ((0.0 + w[0]*s[0][i]) + w[1]*s[1][i]) + ... in fp64, fields in the given order; then, if
+ * `nq` > 0, every row of length n/nq is divided by its max when that is > 0 (:219-223).  Device buffers. */
+ARB_API int arb_combine_fields(int n_fields, const double* const* field_scores, const double* weights,
+                               int64_t n, int64_t nq, double* out, void* stream);
+
 /* ------------------------------------------------------------------------- *
  * Fusion (replaces HybridSearcher.fuse, retrieval/hybrid_search.py:34-103).
  * Each source s in {dense, bm25, graph, path} is a [nq, k_s] list of

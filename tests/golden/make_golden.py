@@ -90,6 +90,37 @@ def main():
     with open(os.path.join(HERE, "bm25_simple_golden.json"), "w") as f:
         json.dump(out, f, indent=0)
 
+    # ---------------- FieldWeightedBM25 (utils/bm25_search.py:66-234) ----------------
+    fw = {"source": "reference utils/bm25_search.py FieldWeightedBM25 / field_weighted_bm25_scores", "cases": []}
+    rng = random.Random(4242)
+    for ci, (n_docs, vocab) in enumerate([(12, 8), (80, 30), (150, 120)]):
+        words = [f"w{i}" for i in range(vocab)]
+        notes = []
+        for di in range(n_docs):
+            notes.append({
+                "title": " ".join(rng.choices(words, k=rng.randint(0, 4))),
+                "entities": rng.choices(words, k=rng.randint(0, 3)) if di % 5 else [],
+                "content": " ".join(rng.choices(words, k=rng.randint(0, 25))),
+            })
+        if ci == 0:
+            for n in notes:
+                n["entities"] = []                      # a field with avgdl == 0
+        weights = None if ci != 2 else {"title": 3.0, "entities": 0.5, "content": 1.25}
+        corpus = bm.build_field_weighted_bm25_corpus(notes, weights)
+        case = {"name": f"fw{ci}", "notes": notes, "weights": weights, "queries": []}
+        for qi in range(8):
+            q = " ".join(rng.choices(words + ["zzz"], k=rng.randint(1, 6)))
+            if qi == 2:
+                q = q + " " + q.split()[0]
+            raw = corpus.get_scores(bm.tokenize_text(q))
+            norm = bm.field_weighted_bm25_scores(corpus, notes, q)
+            case["queries"].append({"query": q, "raw": [hx(v) for v in raw], "normalised": [hx(v) for v in norm]})
+        case["queries"].append({"query": "", "raw": [hx(0.0)] * n_docs,
+                                "normalised": [hx(v) for v in bm.field_weighted_bm25_scores(corpus, notes, "")]})
+        fw["cases"].append(case)
+    with open(os.path.join(HERE, "bm25_field_golden.json"), "w") as f:
+        json.dump(fw, f, indent=0)
+
     # ---------------- HybridSearcher.fuse ----------------
     fz = {"source": "reference retrieval/hybrid_search.py HybridSearcher.fuse", "cases": []}
 

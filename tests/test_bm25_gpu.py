@@ -106,3 +106,20 @@ def test_topk_and_full_scores_match_array_oracle(variant, n, v, nq, k):
     assert np.array_equal(s2.cpu().numpy(), s) and np.array_equal(i2.cpu().numpy(), i)
     assert gpu.index.query_postings(qt) == sum(int(ora.df[ora.term_slot[int(t)]]) for t in qt.ravel() if int(t) in ora.term_slot)
     gpu.close()
+
+
+def test_reference_golden_field_weighted_bm25(golden_dir):
+    """FieldWeightedBM25 (utils/bm25_search.py:66-234) against the reference's own outputs, bit-exact."""
+    import ano_rag_b200  # noqa: F401
+    from ano_rag_b200.utils.bm25_search import (build_field_weighted_bm25_corpus, field_weighted_bm25_scores,
+                                                tokenize_text)
+    with open(os.path.join(golden_dir, "bm25_field_golden.json")) as f:
+        golden = json.load(f)
+    for case in golden["cases"]:
+        corpus = build_field_weighted_bm25_corpus(case["notes"], case["weights"])
+        for q in case["queries"]:
+            toks = tokenize_text(q["query"])
+            if toks:
+                assert corpus.get_scores(toks) == [fh(v) for v in q["raw"]], (case["name"], q["query"])
+            assert field_weighted_bm25_scores(corpus, case["notes"], q["query"]) == [fh(v) for v in q["normalised"]]
+        corpus.close()
