@@ -69,6 +69,7 @@ _SIGS = {
                                 c_int, c_void_p]),
     "arb_bm25_scores": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_int, c_int, c_int64, c_void_p, c_int,
                                 c_void_p]),
+    "arb_bm25_batch_stats": (c_int, [POINTER(c_int64), c_int]),
     "arb_combine_fields": (c_int, [c_int, POINTER(c_void_p), POINTER(c_double), c_int64, c_int64, c_void_p, c_void_p]),
     "arb_fuse": (c_int, [c_int, POINTER(c_double), c_double, c_int, c_int64, POINTER(c_void_p), POINTER(c_void_p),
                          POINTER(c_int), POINTER(c_int), c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
@@ -104,7 +105,8 @@ def launch_count(reset: bool = False) -> int:
     return int(lib.arb_launch_count(1 if reset else 0))
 
 
-PROFILE_KINDS = ("dense_topk", "bm25_topk", "fuse", "dense_merge")
+PROFILE_KINDS = ("dense_topk", "bm25_topk", "fuse", "dense_merge", "bm25_sparse", "bm25_planes", "bm25_final",
+                 "ivf_coarse")
 
 
 def profile(enable: bool) -> None:
@@ -113,7 +115,15 @@ def profile(enable: bool) -> None:
 
 def profile_collect():
     """-> {kind: (total_ms, launches)} for the kernels bracketed since profile(True)."""
-    ms = (c_double * 4)()
-    cnt = (c_int64 * 4)()
+    ms = (c_double * len(PROFILE_KINDS))()
+    cnt = (c_int64 * len(PROFILE_KINDS))()
     check(lib.arb_profile_collect(ms, cnt))
     return {k: (float(ms[i]), int(cnt[i])) for i, k in enumerate(PROFILE_KINDS)}
+
+
+def bm25_batch_stats(reset: bool = True):
+    """Diagnostics of the batched BM25 pipeline (needs ARB_BM25_STATS=1 in the environment)."""
+    out = (c_int64 * 4)()
+    check(lib.arb_bm25_batch_stats(out, 1 if reset else 0))
+    return {"queries": int(out[0]), "fallback_queries": int(out[1]), "emissions": int(out[2]),
+            "max_emissions": int(out[3])}

@@ -15,38 +15,19 @@
 // boundaries (DOC_BLOCK = 16384 docs = one 128 KB fp64 accumulator tile in shared
 // memory).  post[i] = gcode << 14 | (doc % DOC_BLOCK)  (4 B per posting);
 // blk_off[t*NB + b] is where block b of term t starts.
-#include "common.cuh"
+#include "bm25.cuh"
 
 #include <algorithm>
+#include <cstdlib>
 #include <mutex>
 #include <vector>
 
 namespace arb {
 
-constexpr int DOC_BLOCK_LOG2 = 14;
-constexpr int DOC_BLOCK = 1 << DOC_BLOCK_LOG2;       // docs per accumulator tile
-constexpr int GCODE_BITS = 18;
-constexpr uint32_t GCODE_MASK = (1u << GCODE_BITS) - 1u;
-__host__ __device__ __forceinline__ uint32_t post_doc(uint32_t u) { return u & (DOC_BLOCK - 1); }
-__host__ __device__ __forceinline__ uint32_t post_code(uint32_t u) { return u >> DOC_BLOCK_LOG2; }
 constexpr int BM25_THREADS = 1024;
 constexpr int CAND_CAP = 2048;                        // candidate buffer (power of two)
 constexpr int GTAB_SMEM = 4096;                       // g-table entries cached in smem
 constexpr int BM25_SMEM = DOC_BLOCK * 8 + CAND_CAP * 12 + GTAB_SMEM * 8 + 2 * ARB_MAX_QUERY_TERMS * 4 + 64;
-
-struct Bm25Dev {
-  int64_t n_docs, n_terms, n_post;
-  int nb;                       // doc blocks
-  int n_g;
-  const uint32_t* blk_off;      // [n_terms*nb + 1]
-  const uint32_t* post;         // [n_post]
-  const double* idf;            // [n_terms]
-  const double* gtab;           // [n_g]
-  int n_slices;                 // 512-doc slices (one warp each)
-  int n_dense;                  // terms with per-slice offsets
-  const int* dense_slot;        // [n_terms] index into fine_off or -1
-  const uint32_t* fine_off;     // [n_dense * (n_slices + 1)]
-};
 
 // ---------------------------------------------------------------- build kernels
 __global__ void bm25_pack_kernel(const int32_t* __restrict__ doc, const int32_t* __restrict__ gcode, int64_t n,
@@ -86,6 +67,17 @@ __global__ void bm25_fineoff_kernel(const int64_t* __restrict__ term_ptr, const 
     if (doc[mid] < lo_doc) lo = mid + 1; else hi = mid;
   }
   fine_off[i] = static_cast<uint32_t>(lo);
+}
+
+// one thread per posting of a plane term: planes[tile][slot][doc % 256] = idf * g  (the term's whole
+// contribution: the same single rounding the per-posting path performs)
+__global__ void bm25_plane_fill_kernel(const int32_t* __restrict__ doc, const int32_t* __restrict__ gcode, int64_t lo,
+                                       int64_t hi, double idf, const double* __restrict__ gtab, int slot, int n_planes,
+                                       double* __restrict__ planes) {
+  const int64_t i = lo + blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  if (i >= hi) return;
+  const int64_t d = doc[i];
+  planes[((d >> PLANE_TILE_LOG2) * n_planes + slot) * PLANE_TILE + plane_pos(static_cast<uint32_t>(d) & (PLANE_TILE - 1))] = __dmul_rn(idf, gtab[gcode[i]]);
 }
 
 // ---------------------------------------------------------------- scoring core
@@ -185,8 +177,6 @@ __device__ __forceinline__ void bitonic_sort_cands(const Bm25Smem& s) {
 // ----------------------------------------------------------------------------
 constexpr int TOPK_WARPS = 32;
 constexpr int TOPK_THREADS = TOPK_WARPS * 32;
-constexpr int SLICE_LOG2 = DOC_BLOCK_LOG2 - 5;       // 512 docs owned by one warp
-constexpr int SLICE = 1 << SLICE_LOG2;
 constexpr int CAP2 = 1024;                           // candidate buffer (power of two)
 constexpr int GREP_BYTES = 65536;                    // replicated factor table
 constexpr int TOPK_SMEM = DOC_BLOCK * 8 + 256 + GREP_BYTES + CAP2 * 12 + ARB_MAX_QUERY_TERMS * 16 + 64;
@@ -405,14 +395,14 @@ __device__ __forceinline__ void bm25_topk_body(const Bm25Dev& ix, const TopkSmem
 
 __global__ void __launch_bounds__(TOPK_THREADS, 1)
 bm25_topk_kernel(const Bm25Dev ix, const int32_t* __restrict__ q_terms_all, int max_qt, int k, int64_t id_base,
-                 int blocks_per_split, int64_t nq, double* __restrict__ part_scores, int64_t* __restrict__ part_ids) {
+                 int blocks_per_split, int64_t nq, const int* __restrict__ flag_list,
+                 const int* __restrict__ flag_count, double* __restrict__ part_scores,
+                 int64_t* __restrict__ part_ids) {
   extern __shared__ __align__(128) uint8_t bsm[];
   TopkSmem s = carve_topk(bsm);
   s.gglobal = ix.gtab;
   const int tid = threadIdx.x;
-  const int64_t q = blockIdx.x;
   const int split = blockIdx.y;
-  const int32_t* q_terms = q_terms_all + q * max_qt;
   const int b0 = split * blocks_per_split;
   const int b1 = min(b0 + blocks_per_split, ix.nb);
   // replication factor of the factor table: as many bank-shifted copies as fit in 64 KB (at most 8)
@@ -425,24 +415,32 @@ bm25_topk_kernel(const Bm25Dev ix, const int32_t* __restrict__ q_terms_all, int 
     const int rep = 1 << rep_log2;
     for (int i = tid; i < ix.n_g * rep; i += TOPK_THREADS) s.grep[i] = ix.gtab[i >> rep_log2];
   }
-  for (int i = tid; i < DOC_BLOCK / 2; i += TOPK_THREADS) reinterpret_cast<double2*>(s.acc)[i] = make_double2(0.0, 0.0);
-  for (int i = tid; i < CAP2; i += TOPK_THREADS) { s.ckey[i] = 0ull; s.cdoc[i] = 0xFFFFFFFFu; }
-  if (tid < max_qt) {
-    const int t = q_terms[tid];
-    const bool ok = t >= 0 && t < ix.n_terms;
-    s.idf[tid] = ok ? ix.idf[t] : 0.0;
-    s.dslot[tid] = ok ? ix.dense_slot[t] : -1;
-  }
-  if (tid == 0) { s.misc[0] = 0; s.misc[1] = 0; }
-  __syncthreads();
-  double* os = part_scores + (static_cast<int64_t>(split) * nq + q) * k;
-  int64_t* oi = part_ids + (static_cast<int64_t>(split) * nq + q) * k;
-  switch (rep_log2) {
-    case 3:  bm25_topk_body<3>(ix, s, q_terms, max_qt, k, id_base, b0, b1, os, oi); break;
-    case 2:  bm25_topk_body<2>(ix, s, q_terms, max_qt, k, id_base, b0, b1, os, oi); break;
-    case 1:  bm25_topk_body<1>(ix, s, q_terms, max_qt, k, id_base, b0, b1, os, oi); break;
-    case 0:  bm25_topk_body<0>(ix, s, q_terms, max_qt, k, id_base, b0, b1, os, oi); break;
-    default: bm25_topk_body<-1>(ix, s, q_terms, max_qt, k, id_base, b0, b1, os, oi); break;
+  // Without a flag list CTA x scores query x; with one (the batched pipeline's fallback) CTA x walks
+  // the listed queries x, x + gridDim.x, ...
+  const int n_listed = flag_list ? *flag_count : 1;
+  for (int slot = flag_list ? blockIdx.x : 0; slot < n_listed; slot += gridDim.x) {
+    const int64_t q = flag_list ? flag_list[slot] : blockIdx.x;
+    const int32_t* q_terms = q_terms_all + q * max_qt;
+    __syncthreads();                                 // the previous query's output loop is done with the buffers
+    for (int i = tid; i < DOC_BLOCK / 2; i += TOPK_THREADS) reinterpret_cast<double2*>(s.acc)[i] = make_double2(0.0, 0.0);
+    for (int i = tid; i < CAP2; i += TOPK_THREADS) { s.ckey[i] = 0ull; s.cdoc[i] = 0xFFFFFFFFu; }
+    if (tid < max_qt) {
+      const int t = q_terms[tid];
+      const bool ok = t >= 0 && t < ix.n_terms;
+      s.idf[tid] = ok ? ix.idf[t] : 0.0;
+      s.dslot[tid] = ok ? ix.dense_slot[t] : -1;
+    }
+    if (tid == 0) { s.misc[0] = 0; s.misc[1] = 0; }
+    __syncthreads();
+    double* os = part_scores + (static_cast<int64_t>(split) * nq + q) * k;
+    int64_t* oi = part_ids + (static_cast<int64_t>(split) * nq + q) * k;
+    switch (rep_log2) {
+      case 3:  bm25_topk_body<3>(ix, s, q_terms, max_qt, k, id_base, b0, b1, os, oi); break;
+      case 2:  bm25_topk_body<2>(ix, s, q_terms, max_qt, k, id_base, b0, b1, os, oi); break;
+      case 1:  bm25_topk_body<1>(ix, s, q_terms, max_qt, k, id_base, b0, b1, os, oi); break;
+      case 0:  bm25_topk_body<0>(ix, s, q_terms, max_qt, k, id_base, b0, b1, os, oi); break;
+      default: bm25_topk_body<-1>(ix, s, q_terms, max_qt, k, id_base, b0, b1, os, oi); break;
+    }
   }
 }
 
@@ -499,25 +497,21 @@ __global__ void fill_f64_kernel(double* p, double v, int64_t n) {
   if (i < n) p[i] = v;
 }
 
-int merge_topk_device(int score_dtype, const void* scores, const int64_t* ids, int parts, int64_t nq, int k,
-                      void* out_scores, int64_t* out_ids, cudaStream_t st);   // fuse.cu
-
 }  // namespace arb
 
 using namespace arb;
 
-struct arb_bm25 {
-  Bm25Dev dev;
-  uint32_t* blk_off = nullptr;
-  uint32_t* post = nullptr;
-  double* idf = nullptr;
-  double* gtab = nullptr;
-  int* dense_slot = nullptr;
-  uint32_t* fine_off = nullptr;
-  std::vector<int64_t> df;      // host copy of per-term df (roofline accounting)
-};
+int arb::launch_bm25_topk(const Bm25Dev& ix, const int32_t* d_terms, int max_qt, int k, int64_t id_base, int64_t nq,
+                          int n_split, int blocks_per_split, const int* flag_list, const int* flag_count, int grid_x,
+                          double* part_scores, int64_t* part_ids, cudaStream_t st) {
+  dim3 grid(static_cast<unsigned>(grid_x), static_cast<unsigned>(n_split));
+  bm25_topk_kernel<<<grid, TOPK_THREADS, TOPK_SMEM, st>>>(ix, d_terms, max_qt, k, id_base, blocks_per_split, nq,
+                                                          flag_list, flag_count, part_scores, part_ids);
+  ARB_LAUNCH_OK();
+  return ARB_OK;
+}
 
-static int bm25_set_smem_attrs() {
+int arb::bm25_set_smem_attrs() {
   static std::once_flag once;
   static cudaError_t err = cudaSuccess;
   std::call_once(once, [] {
@@ -599,6 +593,41 @@ extern "C" int arb_bm25_create(arb_bm25** out, int64_t n_docs, int64_t n_terms, 
       bm->dev.n_slices = n_slices;
       bm->dev.n_dense = static_cast<int>(dterms.size());
     }
+    // doc-major planes for the densest terms (df >= n_docs/frac, at most MAX_PLANES of them, largest df first)
+    {
+      int frac = 32, max_planes = MAX_PLANES;
+      if (const char* v = std::getenv("ARB_BM25_PLANE_FRAC")) frac = std::max(1, atoi(v));
+      if (const char* v = std::getenv("ARB_BM25_MAX_PLANES")) max_planes = std::max(0, std::min(MAX_PLANES, atoi(v)));
+      const int64_t min_df = std::max<int64_t>(1, (n_docs + frac - 1) / frac);
+      std::vector<std::pair<int64_t, int32_t>> cand;
+      for (int64_t t = 0; t < n_terms; ++t) {
+        const int64_t f = term_ptr[t + 1] - term_ptr[t];
+        if (f >= min_df && idf[t] != 0.0) cand.emplace_back(-f, static_cast<int32_t>(t));
+      }
+      std::sort(cand.begin(), cand.end());
+      if (static_cast<int>(cand.size()) > max_planes) cand.resize(max_planes);
+      const int n_planes = static_cast<int>(cand.size());
+      const int64_t n_tiles = std::max<int64_t>(1, (n_docs + PLANE_TILE - 1) / PLANE_TILE);
+      std::vector<int32_t> pslot(std::max<int64_t>(n_terms, 1), -1);
+      for (int s2 = 0; s2 < n_planes; ++s2) pslot[cand[s2].second] = s2;
+      const size_t plane_bytes = std::max<size_t>(16, static_cast<size_t>(n_tiles) * n_planes * PLANE_TILE * 8);
+      if (cudaMalloc(&bm->plane_slot, pslot.size() * 4) != cudaSuccess || cudaMalloc(&bm->planes, plane_bytes) != cudaSuccess) {
+        cudaGetLastError(); set_error("arb_bm25_create: out of device memory (term planes)"); return fail(ARB_ENOMEM);
+      }
+      e = cudaMemcpyAsync(bm->plane_slot, pslot.data(), pslot.size() * 4, cudaMemcpyHostToDevice, st);
+      if (e == cudaSuccess) e = cudaMemsetAsync(bm->planes, 0, plane_bytes, st);
+      for (int s2 = 0; s2 < n_planes && e == cudaSuccess; ++s2) {
+        const int32_t t = cand[s2].second;
+        const int64_t lo = term_ptr[t], hi = term_ptr[t + 1];
+        bm25_plane_fill_kernel<<<static_cast<unsigned>((hi - lo + 255) / 256), 256, 0, st>>>(
+            d_doc.as<int32_t>(), d_code.as<int32_t>(), lo, hi, idf[t], bm->gtab, s2, n_planes, bm->planes);
+        count_launch();
+      }
+      if (e == cudaSuccess) e = cudaStreamSynchronize(st);       // pslot dies at scope end
+      if (e != cudaSuccess) return fail(cuda_fail(e, "bm25 term planes", __FILE__, __LINE__));
+      bm->dev.n_planes = n_planes;
+      bm->dev.n_tiles = n_tiles;
+    }
     e = cudaGetLastError();
     if (e == cudaSuccess) e = cudaStreamSynchronize(st);
     if (e != cudaSuccess) return fail(cuda_fail(e, "bm25 build kernels", __FILE__, __LINE__));
@@ -609,6 +638,7 @@ extern "C" int arb_bm25_create(arb_bm25** out, int64_t n_docs, int64_t n_terms, 
   bm->dev.nb = nb; bm->dev.n_g = static_cast<int>(n_g);
   bm->dev.blk_off = bm->blk_off; bm->dev.post = bm->post; bm->dev.idf = bm->idf; bm->dev.gtab = bm->gtab;
   bm->dev.dense_slot = bm->dense_slot; bm->dev.fine_off = bm->fine_off;
+  bm->dev.plane_slot = bm->plane_slot; bm->dev.planes = bm->planes;
   *out = bm;
   return ARB_OK;
 }
@@ -621,6 +651,8 @@ extern "C" int arb_bm25_destroy(arb_bm25* bm) {
   if (bm->gtab) cudaFree(bm->gtab);
   if (bm->dense_slot) cudaFree(bm->dense_slot);
   if (bm->fine_off) cudaFree(bm->fine_off);
+  if (bm->plane_slot) cudaFree(bm->plane_slot);
+  if (bm->planes) cudaFree(bm->planes);
   delete bm;
   return ARB_OK;
 }
@@ -665,14 +697,6 @@ extern "C" int arb_bm25_search(const arb_bm25* bm, const int32_t* q_terms, int64
   rc = stage_terms(q_terms, nq, max_qt, q_is_device, tbuf, &d_terms, st);
   if (rc) return rc;
 
-  // few queries: cut the doc blocks over several CTAs per query and merge
-  const int sms = num_sms();
-  int n_split = 1;
-  if (nq < sms) n_split = static_cast<int>(std::min<int64_t>(bm->dev.nb, (sms + nq - 1) / nq));
-  n_split = std::max(1, std::min(n_split, 8192 / k));
-  const int bps = (bm->dev.nb + n_split - 1) / n_split;
-  n_split = (bm->dev.nb + bps - 1) / bps;
-
   double* d_scores = out_scores;
   int64_t* d_ids = out_ids;
   if (!out_is_device) {
@@ -681,23 +705,45 @@ extern "C" int arb_bm25_search(const arb_bm25* bm, const int32_t* q_terms, int64
     d_scores = oscores.as<double>();
     d_ids = oids.as<int64_t>();
   }
-  double* ps = d_scores;
-  int64_t* pi = d_ids;
-  if (n_split > 1) {
-    ARB_CUDA(pscores.alloc(static_cast<size_t>(n_split) * nq * k * 8, st));
-    ARB_CUDA(pids.alloc(static_cast<size_t>(n_split) * nq * k * 8, st));
-    ps = pscores.as<double>();
-    pi = pids.as<int64_t>();
+
+  // Batches go through the plane/sparse pipeline (bm25_batch.cu); small batches and long queries use the
+  // per-query kernel.  ARB_BM25_MODE=query|batch forces one of them (tests exercise both).
+  int64_t batch_min = 64;
+  bool force_query = false;
+  if (const char* v = std::getenv("ARB_BM25_MODE")) {
+    if (!strcmp(v, "query")) force_query = true;
+    else if (!strcmp(v, "batch")) batch_min = 1;
   }
-  dim3 grid(static_cast<unsigned>(nq), static_cast<unsigned>(n_split));
-  {
+  if (!force_query && nq >= batch_min && max_qt <= 32 && bm->dev.n_docs > 0) {
     ProfileScope pscope(PROF_BM25_TOPK, st);
-    bm25_topk_kernel<<<grid, TOPK_THREADS, TOPK_SMEM, st>>>(bm->dev, d_terms, max_qt, k, id_base, bps, nq, ps, pi);
-  }
-  ARB_LAUNCH_OK();
-  if (n_split > 1) {
-    rc = merge_topk_device(ARB_F64, ps, pi, n_split, nq, k, d_scores, d_ids, st);
+    rc = bm25_batch_search(bm->dev, d_terms, nq, max_qt, k, id_base, d_scores, d_ids, st);
     if (rc) return rc;
+  } else {
+    // few queries: cut the doc blocks over several CTAs per query and merge
+    const int sms = num_sms();
+    int n_split = 1;
+    if (nq < sms) n_split = static_cast<int>(std::min<int64_t>(bm->dev.nb, (sms + nq - 1) / nq));
+    n_split = std::max(1, std::min(n_split, 8192 / k));
+    const int bps = (bm->dev.nb + n_split - 1) / n_split;
+    n_split = (bm->dev.nb + bps - 1) / bps;
+    double* ps = d_scores;
+    int64_t* pi = d_ids;
+    if (n_split > 1) {
+      ARB_CUDA(pscores.alloc(static_cast<size_t>(n_split) * nq * k * 8, st));
+      ARB_CUDA(pids.alloc(static_cast<size_t>(n_split) * nq * k * 8, st));
+      ps = pscores.as<double>();
+      pi = pids.as<int64_t>();
+    }
+    {
+      ProfileScope pscope(PROF_BM25_TOPK, st);
+      rc = launch_bm25_topk(bm->dev, d_terms, max_qt, k, id_base, nq, n_split, bps, nullptr, nullptr,
+                            static_cast<int>(nq), ps, pi, st);
+      if (rc) return rc;
+    }
+    if (n_split > 1) {
+      rc = merge_topk_device(ARB_F64, ps, pi, n_split, nq, k, d_scores, d_ids, st);
+      if (rc) return rc;
+    }
   }
   if (!out_is_device) {
     ARB_CUDA(cudaMemcpyAsync(out_scores, d_scores, static_cast<size_t>(nq) * k * 8, cudaMemcpyDeviceToHost, st));

@@ -1,0 +1,78 @@
+// Declarations shared by the BM25 kernels (bm25.cu: index build, per-query kernel,
+// full score vectors; bm25_batch.cu: the batched plane/sparse pipeline).
+#pragma once
+
+#include "common.cuh"
+
+#include <vector>
+
+namespace arb {
+
+constexpr int DOC_BLOCK_LOG2 = 14;
+constexpr int DOC_BLOCK = 1 << DOC_BLOCK_LOG2;       // docs per posting block (blk_off granularity)
+constexpr int GCODE_BITS = 18;
+constexpr uint32_t GCODE_MASK = (1u << GCODE_BITS) - 1u;
+__host__ __device__ __forceinline__ uint32_t post_doc(uint32_t u) { return u & (DOC_BLOCK - 1); }
+__host__ __device__ __forceinline__ uint32_t post_code(uint32_t u) { return u >> DOC_BLOCK_LOG2; }
+
+constexpr int SLICE_LOG2 = DOC_BLOCK_LOG2 - 5;       // 512 docs: fine_off granularity
+constexpr int SLICE = 1 << SLICE_LOG2;
+
+// Doc-major "planes" of the densest terms (batched pipeline): plane s holds, for every doc,
+// the term's whole contribution idf*g as fp64 (+0.0 where the term is absent), stored
+// tile-major: planes[(doc >> 8) * n_planes + s][plane_pos(doc & 255)].
+constexpr int PLANE_TILE_LOG2 = 8;
+constexpr int PLANE_TILE = 1 << PLANE_TILE_LOG2;
+constexpr int MAX_PLANES = 64;
+// Position of doc d (0..255) inside a 256-entry plane-tile row.  The plane pass gives lane l the eight
+// docs 8l .. 8l+7 and reads them as four 16-byte chunks; chunk j of all lanes is contiguous, so every
+// LDS.128 of a warp is conflict free:  d = 8l + 2j + h  ->  (j*32 + l)*2 + h.
+__host__ __device__ __forceinline__ uint32_t plane_pos(uint32_t d) {
+  return ((((d >> 1) & 3u) * 32u + (d >> 3)) << 1) | (d & 1u);
+}
+
+struct Bm25Dev {
+  int64_t n_docs, n_terms, n_post;
+  int nb;                       // 16K-doc posting blocks
+  int n_g;
+  const uint32_t* blk_off;      // [n_terms*nb + 1]
+  const uint32_t* post;         // [n_post]  gcode << 14 | doc % 16384
+  const double* idf;            // [n_terms]
+  const double* gtab;           // [n_g]
+  int n_slices;                 // 512-doc slices
+  int n_dense;                  // terms with per-slice offsets
+  const int* dense_slot;        // [n_terms] index into fine_off or -1
+  const uint32_t* fine_off;     // [n_dense * (n_slices + 1)]
+  int n_planes;                 // terms stored as doc-major planes (<= MAX_PLANES)
+  const int* plane_slot;        // [n_terms] plane index or -1
+  const double* planes;         // [n_tiles * n_planes * 256]
+  int64_t n_tiles;              // 256-doc tiles
+};
+
+int merge_topk_device(int score_dtype, const void* scores, const int64_t* ids, int parts, int64_t nq, int k,
+                      void* out_scores, int64_t* out_ids, cudaStream_t st);   // fuse.cu
+
+// per-query kernel (bm25.cu) over the queries listed in flag_list[0 .. *flag_count) (NULL = all nq queries)
+int launch_bm25_topk(const Bm25Dev& ix, const int32_t* d_terms, int max_qt, int k, int64_t id_base, int64_t nq,
+                     int n_split, int blocks_per_split, const int* flag_list, const int* flag_count, int grid_x,
+                     double* part_scores, int64_t* part_ids, cudaStream_t st);
+int bm25_set_smem_attrs();
+
+// batched pipeline (bm25_batch.cu); returns ARB_OK after enqueueing everything on `st`
+int bm25_batch_search(const Bm25Dev& ix, const int32_t* d_terms, int64_t nq, int max_qt, int k, int64_t id_base,
+                      double* d_scores, int64_t* d_ids, cudaStream_t st);
+
+}  // namespace arb
+
+struct arb_bm25 {
+  arb::Bm25Dev dev;
+  uint32_t* blk_off = nullptr;
+  uint32_t* post = nullptr;
+  double* idf = nullptr;
+  double* gtab = nullptr;
+  int* dense_slot = nullptr;
+  uint32_t* fine_off = nullptr;
+  int* plane_slot = nullptr;
+  double* planes = nullptr;
+  std::vector<int64_t> df;      // host copy of per-term df (roofline accounting)
+};

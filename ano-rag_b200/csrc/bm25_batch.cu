@@ -1,0 +1,827 @@
+// Batched BM25 top-k (sm_100a): the plane / sparse pipeline behind arb_bm25_search.
+//
+// Replaces corpus.get_scores() + top-k for a whole query batch (reference
+// utils/bm25_search.py:309 -> rank_bm25 BM25Okapi.get_scores / SimpleBM25.get_scores :43-63).
+//
+// Why two passes.  In a Zipf corpus a few dozen terms own almost all postings (cfg3: the 64
+// densest terms carry 98 % of the postings a query touches).  Scatter-adding those postings
+// into shared-memory accumulators costs three 64-bit shared accesses each; instead every such
+// term is stored as a doc-major fp64 "plane" of its finished contributions idf*g (+0.0 where
+// the term is absent), and a CTA that has staged one 256-doc tile of all planes in shared
+// memory scores that tile for EVERY query of the batch with register accumulators:
+// one conflict-free LDS + one DADD per (query token, doc).  The fp64 addition order of the
+// reference (query-token order per doc) is kept exactly:
+//
+//   1. sparse pass   (one warp per query)  docs that match at least one non-plane token
+//      ("members") get their complete score in query-token order: postings of the sparse tokens
+//      are scattered into a per-warp 1024-doc accumulator tile, plane tokens are looked up for the
+//      members only.  The members are recorded in a per-query bitmap; their top-k (list A) gives
+//      a lower bound on the final k-th score.
+//   2. plane pass    (one CTA per 256-doc tile, all queries)  every other doc has plane tokens
+//      only, so its score is the in-order sum of plane values; docs that reach A's k-th score
+//      and are not members are appended to the query's list E.
+//   3. final merge   A + E -> top-k by (score desc, doc asc).
+//   4. fallback      queries whose A holds fewer than k docs while they have plane tokens (no
+//      usable bound), or whose E overflowed, are re-scored by the per-query kernel (bm25.cu).
+//
+// Adding +0.0 for absent terms is what the reference itself does (score += idf * 0), and an
+// accumulator that starts at +0.0 can never become -0.0, so the result is bit-identical.
+#include "bm25.cuh"
+
+#include <algorithm>
+#include <cstdlib>
+#include <mutex>
+
+namespace arb {
+
+constexpr int SP_MIN_BLOCK_LOG2 = 10;                // sparse-pass doc blocks: 1024 .. 8192 docs, chosen per query
+constexpr int SP_MAX_BLOCK_LOG2 = 13;
+constexpr int SP_MAXB = 1 << SP_MAX_BLOCK_LOG2;
+constexpr int SP_MAXM = 1024;                       // members per block visit (rank-compact accumulators)
+constexpr int SP_TARGET_M = 384;                    // block size aims at this many members per visit
+constexpr int SP_POOL = 1920;                       // fp64 pool: M accumulators + staged plane values
+constexpr int SP_PCAP = 1024;                       // postings staged per visit
+constexpr int SP_STAGED_PLANES = 4;                 // plane tokens whose member values are staged by cp.async
+constexpr int PL_WARPS = 16;
+constexpr int PL_SMEM_MAX = 227 * 1024;             // planes tile + per-query records
+constexpr int E_CAP = 1024;                         // plane-pass emissions kept per query
+constexpr unsigned long long THR_SKIP = ~0ull;
+static_assert(SP_POOL >= SP_MAXM, "the pool holds at least the accumulators");
+
+// per-warp state of the sparse pass; CAP = candidate buffer (>= 2k + 32)
+template <int CAP>
+struct SpWarp {
+  double pool[SP_POOL];                  // [0, M): accumulator of member r (ranked by doc id inside the block);
+                                         // [M, ...): plane values of the members, staged by cp.async
+  unsigned long long ckey[CAP];
+  uint32_t cdoc[CAP];
+  uint32_t post[SP_PCAP];                // this visit's postings of all sparse tokens, staged by cp.async
+  uint32_t bm[SP_MAXB / 32];             // member bitmap of the block being visited
+  uint16_t prk[SP_PCAP];                 // member rank of each staged posting (0xFFFF: other sub-block)
+  uint16_t pref[SP_MAXB / 32];           // rank of the first member of each bitmap word
+  uint16_t mdoc[SP_MAXM];                // doc offset (inside the block) of member r
+};
+template <int CAP> constexpr int sp_warps() { return CAP <= 256 ? 8 : 7; }
+
+__device__ __forceinline__ void cp_async_4(void* smem_dst, const void* gsrc) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" :: "r"(static_cast<uint32_t>(__cvta_generic_to_shared(smem_dst))), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_8(void* smem_dst, const void* gsrc) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" :: "r"(static_cast<uint32_t>(__cvta_generic_to_shared(smem_dst))), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() {
+  asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
+}
+
+struct BatchScratch {
+  unsigned long long* a_key;   // [nq, k]  sparse-pass top-k (list A), sorted
+  uint32_t* a_doc;             // [nq, k]
+  int* a_cnt;                  // [nq]
+  unsigned long long* thr;     // [nq]  key of A's k-th score, or THR_SKIP
+  uint8_t* state;              // [nq]  0 = plane pass runs, 1 = no plane tokens (A is final), 2 = fallback
+  uint8_t* qd;                 // [nq, qd_stride] the query's plane slots in token order, 0xFF terminated/padded
+  int qd_stride;               // mq rounded up to a multiple of 8 (<= 32)
+  uint32_t* bitmap;            // [bm_tiles, nq, 8] member bitmap, tile-major: the plane pass streams one tile's
+                               // 32-byte records of consecutive queries (NULL when the index has no planes)
+  int64_t bm_tiles;            // 256-doc tiles covered (whole 16K-doc blocks)
+  int64_t nq;
+  unsigned long long* e_key;   // [nq, E_CAP]
+  uint32_t* e_doc;             // [nq, E_CAP]
+  int* e_cnt;                  // [nq]
+  int* flag_list;              // [nq]
+  // the sparse pass cuts every query into `parts` doc ranges (whole 16K-doc blocks) scored by different
+  // warps, so that one heavy query cannot become the tail of the kernel; part lists are merged into A
+  int parts;
+  unsigned long long* pa_key;  // [nq, parts, k]
+  uint32_t* pa_doc;            // [nq, parts, k]
+  int* pa_cnt;                 // [nq, parts]  entries, or -1 if the part overflowed its staging areas
+  int* counters;               // [0] next query of the sparse pass, [1] number of flagged queries
+};
+
+// bitonic sort of n_pow2 (key, doc) pairs by (key desc, doc asc); one warp
+__device__ __forceinline__ void warp_sort_desc(unsigned long long* key, uint32_t* doc, int n_pow2, int lane) {
+  for (int size = 2; size <= n_pow2; size <<= 1) {
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+      __syncwarp();
+      for (int i = lane; i < n_pow2 / 2; i += 32) {
+        const int lo = 2 * i - (i & (stride - 1));
+        const int hi = lo + stride;
+        const bool best_first = ((lo & size) == 0);
+        const unsigned long long ka = key[lo], kb = key[hi];
+        const uint32_t da = doc[lo], db = doc[hi];
+        const bool a_before_b = (ka > kb) || (ka == kb && da < db);
+        if (a_before_b != best_first) { key[lo] = kb; key[hi] = ka; doc[lo] = db; doc[hi] = da; }
+      }
+    }
+  }
+  __syncwarp();
+}
+
+// same, whole CTA
+template <class IdT>
+__device__ __forceinline__ void cta_sort_desc(unsigned long long* key, IdT* id, int n_pow2) {
+  for (int size = 2; size <= n_pow2; size <<= 1) {
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+      __syncthreads();
+      for (int i = threadIdx.x; i < n_pow2 / 2; i += blockDim.x) {
+        const int lo = 2 * i - (i & (stride - 1));
+        const int hi = lo + stride;
+        const bool best_first = ((lo & size) == 0);
+        const unsigned long long ka = key[lo], kb = key[hi];
+        const IdT da = id[lo], db = id[hi];
+        const bool a_before_b = (ka > kb) || (ka == kb && da < db);
+        if (a_before_b != best_first) { key[lo] = kb; key[hi] = ka; id[lo] = db; id[hi] = da; }
+      }
+    }
+  }
+  __syncthreads();
+}
+
+// ----------------------------------------------------------------------------
+// 1. sparse pass: one warp per query (queries handed out by an atomic counter).
+//
+// The warp walks the corpus in doc blocks of B = 1024 .. 8192 docs (B chosen per query so that a
+// block holds ~SP_TARGET_M members on average).  The pass is bound by memory latency (a few hundred
+// scattered postings and plane values per visit), so every global read of a visit is issued as one
+// burst of cp.async copies into the warp's shared-memory staging areas:
+//  (1) the postings of all the query's sparse tokens in this block are staged, then mark the member
+//      bitmap;
+//  (2) members are ranked (bitmap word prefix sums): the fp64 accumulators are indexed by rank, so
+//      their footprint does not depend on B; every staged posting records its member's rank;
+//  (3) the plane values of the members are staged in one burst (member-major: one address
+//      computation per member);
+//  (4) tokens are applied in QUERY ORDER: a sparse token adds idf*g at the rank of each of its docs,
+//      a plane token adds its staged value for every member;
+//  (5) members are harvested in ascending doc order.
+// ----------------------------------------------------------------------------
+template <int CAP>
+__global__ void __launch_bounds__(sp_warps<CAP>() * 32, 1)
+bm25_sparse_pass_kernel(const Bm25Dev ix, const int32_t* __restrict__ q_terms_all, int mq, int64_t nq, int k,
+                        const BatchScratch sc) {
+  extern __shared__ __align__(16) uint8_t sp_smem[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  SpWarp<CAP>& W = reinterpret_cast<SpWarp<CAP>*>(sp_smem)[warp];
+  for (int i = lane; i < SP_MAXB / 32; i += 32) W.bm[i] = 0u;    // restored to zero after every block
+  __syncwarp();
+  const int nsl = ix.n_slices;
+  const uint32_t lt = (1u << lane) - 1u;
+  const unsigned long long key_zero = f64_key(0.0);
+  const int64_t tile_stride = static_cast<int64_t>(ix.n_planes) * PLANE_TILE;
+
+  while (true) {
+    int ui = 0;
+    if (lane == 0) ui = atomicAdd(&sc.counters[0], 1);
+    const int64_t unit = __shfl_sync(0xffffffffu, ui, 0);
+    if (unit >= nq * sc.parts) break;
+    const int64_t q = unit / sc.parts;
+    const int part = static_cast<int>(unit - q * sc.parts);
+
+    // one query token per lane: kind 1 = plane term, 2 = sparse term with per-512-doc offsets,
+    // 3 = sparse term with per-16K-block offsets only, 0 = contributes nothing
+    int t = -1, kind = 0, slot = -1;
+    double idf = 0.0;
+    long long df = 0;
+    if (lane < mq) {
+      t = q_terms_all[q * mq + lane];
+      if (t >= 0 && t < ix.n_terms) {
+        idf = __ldg(ix.idf + t);
+        if (idf != 0.0) {                                      // (idf.get(q) or 0) == 0 adds +0.0: a no-op
+          const int ps = ix.n_planes > 0 ? __ldg(ix.plane_slot + t) : -1;
+          if (ps >= 0) { kind = 1; slot = ps; }
+          else {
+            const int fs = __ldg(ix.dense_slot + t);
+            if (fs >= 0) { kind = 2; slot = fs; } else kind = 3;
+            df = static_cast<long long>(__ldg(ix.blk_off + static_cast<int64_t>(t + 1) * ix.nb)) -
+                 static_cast<long long>(__ldg(ix.blk_off + static_cast<int64_t>(t) * ix.nb));
+          }
+        }
+      }
+    }
+    const uint32_t plane_mask = __ballot_sync(0xffffffffu, kind == 1);
+    const uint32_t sparse_mask = __ballot_sync(0xffffffffu, kind >= 2);
+    const int np = __popc(plane_mask);
+    // the plane pass reads the query's plane slots in token order, packed at the front of an 8-byte-aligned row
+    if (part == 0) {
+      if (kind == 1) sc.qd[q * sc.qd_stride + __popc(plane_mask & lt)] = static_cast<uint8_t>(slot);
+      if (lane >= np && lane < sc.qd_stride) sc.qd[q * sc.qd_stride + lane] = 0xFF;
+    }
+    // plane offsets (slot * 256) of the first plane tokens, for the member-major staging loop
+    int64_t pso[SP_STAGED_PLANES];
+#pragma unroll
+    for (int p = 0; p < SP_STAGED_PLANES; ++p) {
+      const int jl = p < np ? static_cast<int>(__fns(plane_mask, 0, p + 1)) : 0;
+      pso[p] = static_cast<int64_t>(__shfl_sync(0xffffffffu, slot, jl)) * PLANE_TILE;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) df += __shfl_xor_sync(0xffffffffu, df, o);
+    // block size: the largest power of two in [1024, 8192] with (expected members per block) <= SP_TARGET_M
+    int bl2 = SP_MAX_BLOCK_LOG2;
+    while (bl2 > SP_MIN_BLOCK_LOG2 && (df << bl2) > static_cast<long long>(SP_TARGET_M) * ix.n_docs) --bl2;
+    const int nblk_all = static_cast<int>((ix.n_docs + (int64_t(1) << bl2) - 1) >> bl2);
+    // this part's blocks: 16K-doc blocks [part * nb / parts, (part + 1) * nb / parts)
+    const int b_first = static_cast<int>((static_cast<int64_t>(part) * ix.nb / sc.parts) << (DOC_BLOCK_LOG2 - bl2));
+    const int nblk = min(nblk_all, static_cast<int>((static_cast<int64_t>(part + 1) * ix.nb / sc.parts) << (DOC_BLOCK_LOG2 - bl2)));
+    const int nwords = 1 << (bl2 - 5);
+    const int wpl = nwords >> 5;                               // bitmap words ranked by each lane (contiguous)
+    const uint32_t sub_mask = (1u << (DOC_BLOCK_LOG2 - bl2)) - 1u;
+    const uint32_t in_mask = (1u << bl2) - 1u;
+    const int spb = 1 << (bl2 - SLICE_LOG2);                   // 512-doc slices per block
+
+    unsigned long long thr_key = key_zero;                     // only positive scores are candidates
+    int cnt = 0;
+    bool overflow = false;
+    // word w of this query's member bitmap lives at bitmap[((w >> 3) * nq + q) * 8 + (w & 7)]
+    uint32_t* bm_row = sc.bitmap ? sc.bitmap + q * 8 : nullptr;
+    const int64_t bm_tile_stride = sc.nq * 8;
+
+    auto compact = [&]() {
+      __syncwarp();
+      int n2 = 32;
+      while (n2 < cnt) n2 <<= 1;
+      for (int i = cnt + lane; i < n2; i += 32) { W.ckey[i] = 0ull; W.cdoc[i] = 0xFFFFFFFFu; }
+      warp_sort_desc(W.ckey, W.cdoc, n2, lane);
+      if (cnt >= k) { cnt = k; thr_key = W.ckey[k - 1]; }
+      __syncwarp();
+    };
+    // posting range of this lane's token in block b (kind 3: the enclosing 16K block, fetched once per 16K docs)
+    auto fetch_range = [&](int b, uint32_t& lo, uint32_t& hi) {
+      if (b >= nblk) return;
+      if (kind == 2) {
+        const uint32_t* fo = ix.fine_off + static_cast<int64_t>(slot) * (nsl + 1);
+        lo = __ldg(fo + min(b * spb, nsl));
+        hi = __ldg(fo + min(b * spb + spb, nsl));
+      } else if (kind == 3 && (static_cast<uint32_t>(b) & sub_mask) == 0u) {
+        const int64_t o = static_cast<int64_t>(t) * ix.nb + (b >> (DOC_BLOCK_LOG2 - bl2));
+        lo = __ldg(ix.blk_off + o);
+        hi = __ldg(ix.blk_off + o + 1);
+      }
+    };
+
+    uint32_t lo = 0u, hi = 0u, nlo = 0u, nhi = 0u;
+    if (sparse_mask) fetch_range(b_first, nlo, nhi);
+    for (int b = b_first; b < nblk && sparse_mask; ++b) {
+      lo = nlo; hi = nhi;
+      fetch_range(b + 1, nlo, nhi);                            // in flight during this visit
+      const uint32_t sub = static_cast<uint32_t>(b) & sub_mask;
+      const uint32_t ne = __ballot_sync(0xffffffffu, hi > lo) & sparse_mask;
+      if (ne == 0u) {
+        if (bm_row)
+          for (int i = lane; i < nwords; i += 32) {
+            const int64_t w = static_cast<int64_t>(b) * nwords + i;
+            bm_row[(w >> 3) * bm_tile_stride + (w & 7)] = 0u;
+          }
+        continue;
+      }
+
+      // ---- (1) the active tokens are packed into lanes 0..na-1; their postings are staged back to back
+      const int na = __popc(ne);
+      const int src = lane < na ? static_cast<int>(__fns(ne, 0, lane + 1)) : 0;
+      const uint32_t c_lo = __shfl_sync(0xffffffffu, lo, src);
+      const uint32_t c_hi = __shfl_sync(0xffffffffu, hi, src);
+      const uint32_t c_len = lane < na ? c_hi - c_lo : 0u;
+      uint32_t c_end = c_len;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t v = __shfl_up_sync(0xffffffffu, c_end, o);
+        if (lane >= o) c_end += v;
+      }
+      const uint32_t c_st = c_end - c_len;
+      const uint32_t L = __shfl_sync(0xffffffffu, c_end, 31);
+      if (L > SP_PCAP) { overflow = true; break; }
+      for (int a = 0; a < na; ++a) {
+        const uint32_t l = __shfl_sync(0xffffffffu, c_lo, a), n = __shfl_sync(0xffffffffu, c_len, a);
+        const uint32_t st = __shfl_sync(0xffffffffu, c_st, a);
+#pragma unroll 2
+        for (uint32_t i = lane; i < n; i += 32) cp_async_4(&W.post[st + i], ix.post + l + i);
+      }
+      cp_async_wait_all();
+      __syncwarp();
+      for (uint32_t f = lane; f < L; f += 32) {
+        const uint32_t d16 = post_doc(W.post[f]);
+        if ((d16 >> bl2) == sub) atomicOr(&W.bm[(d16 & in_mask) >> 5], 1u << (d16 & 31));
+      }
+      __syncwarp();
+
+      // ---- (2) rank the members
+      int c = 0;
+      for (int i = 0; i < wpl; ++i) c += __popc(W.bm[lane * wpl + i]);
+      int incl = c;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int v = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += v;
+      }
+      const int M = __shfl_sync(0xffffffffu, incl, 31);
+      if (bm_row)
+        for (int i = lane; i < nwords; i += 32) {
+          const int64_t w = static_cast<int64_t>(b) * nwords + i;
+          bm_row[(w >> 3) * bm_tile_stride + (w & 7)] = W.bm[i];
+        }
+      if (M == 0) continue;                                    // the 16K block's postings lie in other sub-blocks
+      if (M > SP_MAXM) {                                       // denser than the staging areas allow: fallback
+        overflow = true;
+        for (int i = lane; i < nwords; i += 32) W.bm[i] = 0u;
+        __syncwarp();
+        break;
+      }
+      {
+        int r = incl - c;
+        for (int i = 0; i < wpl; ++i) {
+          const int wi = lane * wpl + i;
+          W.pref[wi] = static_cast<uint16_t>(r);
+          r += __popc(W.bm[wi]);
+        }
+      }
+      __syncwarp();
+      for (uint32_t f = lane; f < L; f += 32) {
+        const uint32_t d16 = post_doc(W.post[f]);
+        uint32_t rk = 0xFFFFu;
+        if ((d16 >> bl2) == sub) {
+          const uint32_t d = d16 & in_mask;
+          rk = W.pref[d >> 5] + __popc(W.bm[d >> 5] & ((1u << (d & 31)) - 1u));
+          W.mdoc[rk] = static_cast<uint16_t>(d);               // every posting of the doc writes the same value
+        }
+        W.prk[f] = static_cast<uint16_t>(rk);
+      }
+      for (int i = lane; i < M; i += 32) W.pool[i] = 0.0;
+      __syncwarp();
+      const int64_t doc0 = static_cast<int64_t>(b) << bl2;
+
+      // ---- (3) stage the plane values of the members (first SP_STAGED_PLANES plane tokens, pool permitting)
+      const int n_staged = min(min(np, SP_STAGED_PLANES), (SP_POOL - M) / M);
+      if (n_staged > 0) {
+#pragma unroll 2
+        for (int i = lane; i < M; i += 32) {
+          const int64_t doc = doc0 + W.mdoc[i];
+          const double* src_p = ix.planes + (doc >> PLANE_TILE_LOG2) * tile_stride + plane_pos(static_cast<uint32_t>(doc) & (PLANE_TILE - 1));
+          double* dst = W.pool + M + i;
+#pragma unroll
+          for (int p = 0; p < SP_STAGED_PLANES; ++p)
+            if (p < n_staged) cp_async_8(dst + p * M, src_p + pso[p]);
+        }
+        cp_async_wait_all();
+        __syncwarp();
+      }
+
+      // ---- (4) accumulate in query-token order
+      int p_seen = 0;
+      for (uint32_t m = ne | plane_mask; m; m &= m - 1) {
+        const int jl = __ffs(m) - 1;
+        if ((plane_mask >> jl) & 1u) {
+          if (p_seen < n_staged) {
+            const double* stg = W.pool + static_cast<size_t>(p_seen + 1) * M;
+            for (int i = lane; i < M; i += 32) W.pool[i] = __dadd_rn(W.pool[i], stg[i]);
+          } else {
+            const double* pp = ix.planes + static_cast<int64_t>(__shfl_sync(0xffffffffu, slot, jl)) * PLANE_TILE;
+            for (int i0 = 0; i0 < M; i0 += 128) {
+              double v[4];
+#pragma unroll
+              for (int r = 0; r < 4; ++r) {
+                const int i = i0 + r * 32 + lane;
+                v[r] = 0.0;
+                if (i < M) {
+                  const int64_t doc = doc0 + W.mdoc[i];
+                  v[r] = __ldg(pp + (doc >> PLANE_TILE_LOG2) * tile_stride + plane_pos(static_cast<uint32_t>(doc) & (PLANE_TILE - 1)));
+                }
+              }
+#pragma unroll
+              for (int r = 0; r < 4; ++r) {
+                const int i = i0 + r * 32 + lane;
+                if (i < M) W.pool[i] = __dadd_rn(W.pool[i], v[r]);
+              }
+            }
+          }
+          ++p_seen;
+        } else {
+          const int a = __popc(ne & ((1u << jl) - 1u));         // index of this token among the active ones
+          const uint32_t st = __shfl_sync(0xffffffffu, c_st, a), en = __shfl_sync(0xffffffffu, c_end, a);
+          const double w_idf = __shfl_sync(0xffffffffu, idf, jl);
+          for (uint32_t f = st + lane; f < en; f += 32) {
+            const uint32_t rk = W.prk[f];
+            if (rk != 0xFFFFu)
+              W.pool[rk] = __dadd_rn(W.pool[rk], __dmul_rn(w_idf, __ldg(ix.gtab + post_code(W.post[f]))));
+          }
+        }
+        __syncwarp();
+      }
+
+      // ---- (5) harvest the members (ascending doc id, so a tie with the k-th score loses: strict >)
+      for (int i0 = 0; i0 < M; i0 += 32) {
+        const int i = i0 + lane;
+        const bool valid = i < M;
+        double v = 0.0;
+        uint32_t d = 0u;
+        if (valid) { v = W.pool[i]; d = W.mdoc[i]; }
+        const unsigned long long key = f64_key(v);
+        const bool pass = valid && key > thr_key;
+        const uint32_t pm = __ballot_sync(0xffffffffu, pass);
+        if (pass) {
+          const int pos = cnt + __popc(pm & lt);
+          W.ckey[pos] = key;
+          W.cdoc[pos] = static_cast<uint32_t>(doc0) + d;
+        }
+        cnt += __popc(pm);
+        if (cnt > CAP - 32) compact();
+      }
+      for (int i = lane; i < nwords; i += 32) W.bm[i] = 0u;
+      __syncwarp();
+    }
+    if (bm_row && !sparse_mask)
+      for (int64_t w = static_cast<int64_t>(b_first) * nwords + lane; w < static_cast<int64_t>(nblk) * nwords; w += 32)
+        bm_row[(w >> 3) * bm_tile_stride + (w & 7)] = 0u;
+
+    compact();
+    cnt = min(cnt, k);
+    const int64_t po = (q * sc.parts + part) * k;
+    for (int i = lane; i < cnt; i += 32) { sc.pa_key[po + i] = W.ckey[i]; sc.pa_doc[po + i] = W.cdoc[i]; }
+    if (lane == 0) sc.pa_cnt[q * sc.parts + part] = overflow ? -1 : cnt;
+    __syncwarp();
+  }
+}
+
+// ----------------------------------------------------------------------------
+// 1b. merge the part lists of every query into list A (sorted top-k of the members), and derive the
+// plane-pass threshold / the query's state.  One CTA per query.
+// ----------------------------------------------------------------------------
+__global__ void __launch_bounds__(128)
+bm25_a_merge_kernel(int64_t nq, int k, const BatchScratch sc) {
+  extern __shared__ __align__(16) uint8_t am_smem[];
+  const int64_t q = blockIdx.x;
+  const int tid = threadIdx.x;
+  __shared__ int s_off[33];
+  __shared__ int s_ovf;
+  if (tid == 0) {
+    int o = 0, ovf = 0;
+    for (int p = 0; p < sc.parts; ++p) {
+      s_off[p] = o;
+      const int c = sc.pa_cnt[q * sc.parts + p];
+      if (c < 0) ovf = 1; else o += c;
+    }
+    s_off[sc.parts] = o;
+    s_ovf = ovf;
+  }
+  __syncthreads();
+  const int n = s_off[sc.parts];
+  int n2 = 2;
+  while (n2 < n) n2 <<= 1;
+  unsigned long long* key = reinterpret_cast<unsigned long long*>(am_smem);
+  uint32_t* doc = reinterpret_cast<uint32_t*>(am_smem + static_cast<size_t>(n2) * 8);
+  for (int i = tid; i < n2; i += blockDim.x) { key[i] = 0ull; doc[i] = 0xFFFFFFFFu; }
+  __syncthreads();
+  for (int p = 0; p < sc.parts; ++p) {
+    const int c = s_off[p + 1] - s_off[p];
+    const int64_t po = (q * sc.parts + p) * k;
+    for (int i = tid; i < c; i += blockDim.x) { key[s_off[p] + i] = sc.pa_key[po + i]; doc[s_off[p] + i] = sc.pa_doc[po + i]; }
+  }
+  cta_sort_desc(key, doc, n2);
+  const int cnt = min(n, k);
+  for (int i = tid; i < k; i += blockDim.x) {
+    sc.a_key[q * k + i] = i < cnt ? key[i] : 0ull;
+    sc.a_doc[q * k + i] = i < cnt ? doc[i] : 0xFFFFFFFFu;
+  }
+  if (tid == 0) {
+    const bool has_planes = sc.qd[q * sc.qd_stride] != 0xFF;
+    sc.a_cnt[q] = cnt;
+    if (!has_planes && !s_ovf)   { sc.state[q] = 1; sc.thr[q] = THR_SKIP; }
+    else if (cnt >= k && !s_ovf) { sc.state[q] = 0; sc.thr[q] = key[k - 1]; }
+    else {
+      sc.state[q] = 2; sc.thr[q] = THR_SKIP;
+      sc.flag_list[atomicAdd(&sc.counters[1], 1)] = static_cast<int>(q);
+    }
+  }
+}
+
+// ----------------------------------------------------------------------------
+// 2. plane pass: grid (tile sets, query groups).  The CTA stages one 256-doc tile of every
+// plane in shared memory; each warp then scores that tile for its queries with 8 register
+// accumulators per lane (lane l owns docs 8l .. 8l+7; see plane_pos()).
+// ----------------------------------------------------------------------------
+__global__ void __launch_bounds__(PL_WARPS * 32, 1)
+bm25_plane_pass_kernel(const Bm25Dev ix, int64_t nq, int64_t q_per_group, const BatchScratch sc) {
+  extern __shared__ __align__(16) double pl_smem[];            // [n_planes][256]
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int P = ix.n_planes;
+  const int64_t q0 = blockIdx.y * q_per_group;
+  const int64_t q1 = min(nq, q0 + q_per_group);
+  const uint32_t lt = (1u << lane) - 1u;
+  const int qw = sc.qd_stride >> 3;                            // 8-byte words of packed plane slots per query
+  const unsigned long long* qd64 = reinterpret_cast<const unsigned long long*>(sc.qd);
+  const uint8_t* bm_bytes = reinterpret_cast<const uint8_t*>(sc.bitmap);
+  ulonglong2* qrec = reinterpret_cast<ulonglong2*>(pl_smem + static_cast<size_t>(P) * PLANE_TILE);   // [q_per_group]
+  for (int64_t q = q0 + threadIdx.x; q < q1; q += PL_WARPS * 32)
+    qrec[q - q0] = make_ulonglong2(__ldg(sc.thr + q), __ldg(qd64 + q * qw));
+  for (int64_t tile = blockIdx.x; tile < ix.n_tiles; tile += gridDim.x) {
+    __syncthreads();
+    {
+      const double2* src = reinterpret_cast<const double2*>(ix.planes + tile * P * PLANE_TILE);
+      double2* dst = reinterpret_cast<double2*>(pl_smem);
+      const int n16 = P * (PLANE_TILE / 2);
+      for (int i0 = threadIdx.x; i0 < n16; i0 += PL_WARPS * 32 * 4) {
+        double2 v[4];
+#pragma unroll
+        for (int r = 0; r < 4; ++r) { const int i = i0 + r * PL_WARPS * 32; if (i < n16) v[r] = __ldg(src + i); }
+#pragma unroll
+        for (int r = 0; r < 4; ++r) { const int i = i0 + r * PL_WARPS * 32; if (i < n16) dst[i] = v[r]; }
+      }
+    }
+    __syncthreads();
+    // Per-query inputs: {threshold, packed plane slots} come from shared memory (staged once per CTA), the
+    // member byte is streamed from HBM (this tile's 32-byte records of consecutive queries) two iterations ahead.
+    const uint8_t* bm_tile = bm_bytes + tile * sc.nq * (PLANE_TILE / 8) + lane;   // + q * 32: this lane's 8 member bits
+    uint32_t mb_n = 0u, mb_nn = 0u;
+    {
+      const int64_t q = q0 + warp;
+      if (q < q1) mb_n = __ldg(bm_tile + q * 32);
+      if (q + PL_WARPS < q1) mb_nn = __ldg(bm_tile + (q + PL_WARPS) * 32);
+    }
+    for (int64_t q = q0 + warp; q < q1; q += PL_WARPS) {
+      const ulonglong2 rec = qrec[q - q0];
+      const unsigned long long thr = rec.x;
+      unsigned long long pk = rec.y;
+      const uint32_t mb = mb_n;
+      mb_n = mb_nn;
+      if (q + 2 * PL_WARPS < q1) mb_nn = __ldg(bm_tile + (q + 2 * PL_WARPS) * 32);
+      if (thr == THR_SKIP) continue;
+      double acc[8];
+#pragma unroll
+      for (int r = 0; r < 8; ++r) acc[r] = 0.0;
+      for (int w = 0; w < qw; ++w) {
+        if (w) pk = __ldg(qd64 + q * qw + w);
+        uint32_t ps = static_cast<uint32_t>(pk) & 0xFFu;
+#pragma unroll 1
+        for (int i = 0; i < 8 && ps != 0xFFu; ++i) {
+          const double2* row = reinterpret_cast<const double2*>(pl_smem + ps * PLANE_TILE) + lane;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const double2 v = row[j * 32];
+            acc[2 * j] = __dadd_rn(acc[2 * j], v.x);
+            acc[2 * j + 1] = __dadd_rn(acc[2 * j + 1], v.y);
+          }
+          pk >>= 8;
+          ps = static_cast<uint32_t>(pk) & 0xFFu;
+        }
+        if (ps == 0xFFu) break;
+      }
+      // docs that reach A's k-th score (a positive fp64, so the comparison of doubles is the comparison of
+      // keys) and are not members of the sparse pass
+      const double thr_d = key_f64(thr);
+      uint32_t pass = 0u;
+#pragma unroll
+      for (int r = 0; r < 8; ++r) pass |= (acc[r] >= thr_d ? 1u : 0u) << r;
+      pass &= ~mb;
+      if (__ballot_sync(0xffffffffu, pass != 0u) == 0u) continue;
+#pragma unroll
+      for (int r = 0; r < 8; ++r) {
+        const bool p = (pass >> r) & 1u;
+        const uint32_t m = __ballot_sync(0xffffffffu, p);
+        if (m == 0u) continue;
+        int base = 0;
+        if (lane == 0) base = atomicAdd(&sc.e_cnt[q], __popc(m));
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (p) {
+          const int pos = base + __popc(m & lt);
+          if (pos < E_CAP) {
+            sc.e_key[q * E_CAP + pos] = f64_key(acc[r]);
+            sc.e_doc[q * E_CAP + pos] = static_cast<uint32_t>(tile * PLANE_TILE + 8 * lane + r);
+          }
+        }
+      }
+    }
+  }
+}
+
+// ----------------------------------------------------------------------------
+// 3. final merge: one CTA per query.
+// ----------------------------------------------------------------------------
+__global__ void __launch_bounds__(128)
+bm25_final_merge_kernel(int64_t nq, int k, int64_t id_base, const BatchScratch sc, double* __restrict__ out_scores,
+                        int64_t* __restrict__ out_ids) {
+  extern __shared__ __align__(16) uint8_t fm_smem[];
+  const int64_t q = blockIdx.x;
+  const int tid = threadIdx.x;
+  const int st = sc.state[q];
+  if (st == 2) return;                                         // the fallback writes this row
+  const int ne = st == 0 ? sc.e_cnt[q] : 0;
+  if (ne > E_CAP) {                                            // emissions overflowed (mass ties): fallback
+    if (tid == 0) { sc.state[q] = 2; sc.flag_list[atomicAdd(&sc.counters[1], 1)] = static_cast<int>(q); }
+    return;
+  }
+  const int na = sc.a_cnt[q];
+  if (ne == 0) {
+    for (int i = tid; i < k; i += blockDim.x) {
+      const bool ok = i < na;
+      out_scores[q * k + i] = ok ? key_f64(sc.a_key[q * k + i]) : 0.0;
+      out_ids[q * k + i] = ok ? id_base + static_cast<int64_t>(sc.a_doc[q * k + i]) : -1;
+    }
+    return;
+  }
+  const int n = na + ne;
+  int n2 = 2;
+  while (n2 < n) n2 <<= 1;
+  unsigned long long* key = reinterpret_cast<unsigned long long*>(fm_smem);
+  uint32_t* doc = reinterpret_cast<uint32_t*>(fm_smem + static_cast<size_t>(ARB_MAX_TOPK + E_CAP) * 2 * 8);
+  for (int i = tid; i < n2; i += blockDim.x) {
+    unsigned long long kk = 0ull; uint32_t dd = 0xFFFFFFFFu;
+    if (i < na) { kk = sc.a_key[q * k + i]; dd = sc.a_doc[q * k + i]; }
+    else if (i < n) { kk = sc.e_key[q * E_CAP + (i - na)]; dd = sc.e_doc[q * E_CAP + (i - na)]; }
+    key[i] = kk; doc[i] = dd;
+  }
+  cta_sort_desc(key, doc, n2);
+  for (int i = tid; i < k; i += blockDim.x) {
+    const bool ok = i < n;
+    out_scores[q * k + i] = ok ? key_f64(key[i]) : 0.0;
+    out_ids[q * k + i] = ok ? id_base + static_cast<int64_t>(doc[i]) : -1;
+  }
+}
+constexpr int FM_SMEM = (ARB_MAX_TOPK + E_CAP) * 2 * 12;
+
+// merge the per-split part lists of the fallback for the flagged queries
+__global__ void __launch_bounds__(256)
+bm25_flag_merge_kernel(const double* __restrict__ ps, const int64_t* __restrict__ pi, int n_split, int64_t nq, int k,
+                       const int* __restrict__ flag_list, const int* __restrict__ flag_count, int n_pow2,
+                       double* __restrict__ out_scores, int64_t* __restrict__ out_ids) {
+  extern __shared__ __align__(16) uint8_t gm_smem[];
+  unsigned long long* key = reinterpret_cast<unsigned long long*>(gm_smem);
+  int64_t* id = reinterpret_cast<int64_t*>(gm_smem + static_cast<size_t>(n_pow2) * 8);
+  const int n_listed = *flag_count;
+  const int m = n_split * k;
+  for (int slot = blockIdx.x; slot < n_listed; slot += gridDim.x) {
+    const int64_t q = flag_list[slot];
+    __syncthreads();
+    for (int i = threadIdx.x; i < n_pow2; i += blockDim.x) {
+      unsigned long long kk = 0ull; int64_t ii = 0x7fffffffffffffffll;
+      if (i < m) {
+        const int64_t o = (static_cast<int64_t>(i / k) * nq + q) * k + (i % k);
+        const int64_t v = pi[o];
+        if (v >= 0) { ii = v; kk = f64_key(ps[o]); }
+      }
+      key[i] = kk; id[i] = ii;
+    }
+    cta_sort_desc(key, id, n_pow2);
+    for (int i = threadIdx.x; i < k; i += blockDim.x) {
+      const bool ok = i < n_pow2 && key[i] != 0ull;
+      out_scores[q * k + i] = ok ? key_f64(key[i]) : 0.0;
+      out_ids[q * k + i] = ok ? id[i] : -1;
+    }
+  }
+}
+
+static thread_local int64_t g_stats[4] = {0, 0, 0, 0};
+
+static int batch_set_attrs() {
+  static std::once_flag once;
+  static cudaError_t err = cudaSuccess;
+  std::call_once(once, [] {
+    err = cudaFuncSetAttribute(bm25_sparse_pass_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               sp_warps<256>() * static_cast<int>(sizeof(SpWarp<256>)));
+    if (err == cudaSuccess)
+      err = cudaFuncSetAttribute(bm25_sparse_pass_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 sp_warps<512>() * static_cast<int>(sizeof(SpWarp<512>)));
+    if (err == cudaSuccess)
+      err = cudaFuncSetAttribute(bm25_plane_pass_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PL_SMEM_MAX);
+    if (err == cudaSuccess)
+      err = cudaFuncSetAttribute(bm25_flag_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 4096 * 16);
+    if (err == cudaSuccess)
+      err = cudaFuncSetAttribute(bm25_a_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 8192 * 12);
+  });
+  ARB_CUDA(err);
+  return bm25_set_smem_attrs();
+}
+
+static int batch_chunk(const Bm25Dev& ix, const int32_t* d_terms, int64_t nq, int mq, int k, int64_t id_base,
+                       double* d_scores, int64_t* d_ids, cudaStream_t st) {
+  const int sms = num_sms();
+  const bool planes = ix.n_planes > 0;
+  BatchScratch sc{};
+  sc.bm_tiles = static_cast<int64_t>(ix.nb) * (DOC_BLOCK / PLANE_TILE);  // whole 16K-doc blocks
+  sc.nq = nq;
+  AsyncBuf b_akey, b_adoc, b_i32, b_thr, b_u8, b_bitmap, b_ekey, b_edoc, b_pakey, b_padoc, b_pacnt;
+  sc.parts = static_cast<int>(std::min<int64_t>(ix.nb, 16));
+  if (const char* v = std::getenv("ARB_BM25_PARTS")) sc.parts = std::max(1, std::min<int>(std::min<int64_t>(ix.nb, 32), atoi(v)));
+  ARB_CUDA(b_pakey.alloc(static_cast<size_t>(nq) * sc.parts * k * 8, st));
+  ARB_CUDA(b_padoc.alloc(static_cast<size_t>(nq) * sc.parts * k * 4, st));
+  ARB_CUDA(b_pacnt.alloc(static_cast<size_t>(nq) * sc.parts * 4, st));
+  sc.pa_key = b_pakey.as<unsigned long long>();
+  sc.pa_doc = b_padoc.as<uint32_t>();
+  sc.pa_cnt = b_pacnt.as<int>();
+  ARB_CUDA(b_akey.alloc(static_cast<size_t>(nq) * k * 8, st));
+  ARB_CUDA(b_adoc.alloc(static_cast<size_t>(nq) * k * 4, st));
+  ARB_CUDA(b_i32.alloc((static_cast<size_t>(nq) * 3 + 2) * 4, st));       // e_cnt | counters | a_cnt | flag_list
+  ARB_CUDA(b_thr.alloc(static_cast<size_t>(nq) * 8, st));
+  sc.qd_stride = (mq + 7) & ~7;
+  ARB_CUDA(b_u8.alloc(static_cast<size_t>(nq) * (sc.qd_stride + 8) + 16, st));
+  if (planes) {
+    ARB_CUDA(b_bitmap.alloc(static_cast<size_t>(nq) * sc.bm_tiles * 32, st));
+    ARB_CUDA(b_ekey.alloc(static_cast<size_t>(nq) * E_CAP * 8, st));
+    ARB_CUDA(b_edoc.alloc(static_cast<size_t>(nq) * E_CAP * 4, st));
+  }
+  sc.a_key = b_akey.as<unsigned long long>();
+  sc.a_doc = b_adoc.as<uint32_t>();
+  sc.e_cnt = b_i32.as<int>();
+  sc.counters = sc.e_cnt + nq;
+  sc.a_cnt = sc.counters + 2;
+  sc.flag_list = sc.a_cnt + nq;
+  sc.thr = b_thr.as<unsigned long long>();
+  sc.qd = b_u8.as<uint8_t>();                                   // 8-byte aligned rows first
+  sc.state = sc.qd + static_cast<size_t>(nq) * sc.qd_stride;
+  sc.bitmap = planes ? b_bitmap.as<uint32_t>() : nullptr;
+  sc.e_key = planes ? b_ekey.as<unsigned long long>() : nullptr;
+  sc.e_doc = planes ? b_edoc.as<uint32_t>() : nullptr;
+  ARB_CUDA(cudaMemsetAsync(sc.e_cnt, 0, (static_cast<size_t>(nq) + 2) * 4, st));
+
+  {
+    ProfileScope ps(PROF_BM25_SPARSE, st);
+    if (2 * k + 32 <= 256) {
+      constexpr int W = sp_warps<256>();
+      const unsigned grid = static_cast<unsigned>(std::min<int64_t>(sms, (nq * sc.parts + W - 1) / W));
+      bm25_sparse_pass_kernel<256><<<grid, W * 32, W * sizeof(SpWarp<256>), st>>>(ix, d_terms, mq, nq, k, sc);
+    } else {
+      constexpr int W = sp_warps<512>();
+      const unsigned grid = static_cast<unsigned>(std::min<int64_t>(sms, (nq * sc.parts + W - 1) / W));
+      bm25_sparse_pass_kernel<512><<<grid, W * 32, W * sizeof(SpWarp<512>), st>>>(ix, d_terms, mq, nq, k, sc);
+    }
+    ARB_LAUNCH_OK();
+    int n2 = 2;
+    while (n2 < sc.parts * k) n2 <<= 1;
+    bm25_a_merge_kernel<<<static_cast<unsigned>(nq), 128, static_cast<size_t>(n2) * 12, st>>>(nq, k, sc);
+    ARB_LAUNCH_OK();
+  }
+  if (planes) {
+    ProfileScope ps(PROF_BM25_PLANES, st);
+    // enough CTAs to fill the GPU: tile sets first, query groups when the corpus has few tiles
+    const int64_t sets = std::min<int64_t>(ix.n_tiles, sms);
+    const size_t plane_smem = static_cast<size_t>(ix.n_planes) * PLANE_TILE * 8;
+    const int64_t max_qpg = static_cast<int64_t>((PL_SMEM_MAX - plane_smem) / 16);   // {thr, slots} records per CTA
+    int64_t groups = std::max<int64_t>(1, std::min<int64_t>(sms / sets, (nq + 4 * PL_WARPS - 1) / (4 * PL_WARPS)));
+    groups = std::max<int64_t>(groups, (nq + max_qpg - 1) / max_qpg);
+    const int64_t qpg = (nq + groups - 1) / groups;
+    groups = (nq + qpg - 1) / qpg;
+    dim3 grid(static_cast<unsigned>(sets), static_cast<unsigned>(groups));
+    bm25_plane_pass_kernel<<<grid, PL_WARPS * 32, plane_smem + static_cast<size_t>(qpg) * 16, st>>>(ix, nq, qpg, sc);
+    ARB_LAUNCH_OK();
+  }
+  {
+    ProfileScope ps(PROF_BM25_FINAL, st);
+    bm25_final_merge_kernel<<<static_cast<unsigned>(nq), 128, FM_SMEM, st>>>(nq, k, id_base, sc, d_scores, d_ids);
+    ARB_LAUNCH_OK();
+    if (planes) {
+      // fallback for the flagged queries (the count lives on the device; CTAs with nothing to do exit)
+      int n_split = static_cast<int>(std::min<int64_t>(ix.nb, 8));
+      n_split = std::max(1, std::min(n_split, 4096 / k));
+      const int bps = (ix.nb + n_split - 1) / n_split;
+      n_split = (ix.nb + bps - 1) / bps;
+      const int grid_x = static_cast<int>(std::min<int64_t>(nq, std::max(1, 2 * sms / n_split)));
+      AsyncBuf pscores, pids;
+      double* ps_ = d_scores;
+      int64_t* pi_ = d_ids;
+      if (n_split > 1) {
+        ARB_CUDA(pscores.alloc(static_cast<size_t>(n_split) * nq * k * 8, st));
+        ARB_CUDA(pids.alloc(static_cast<size_t>(n_split) * nq * k * 8, st));
+        ps_ = pscores.as<double>();
+        pi_ = pids.as<int64_t>();
+      }
+      int rc = launch_bm25_topk(ix, d_terms, mq, k, id_base, nq, n_split, bps, sc.flag_list, sc.counters + 1, grid_x,
+                                ps_, pi_, st);
+      if (rc) return rc;
+      if (n_split > 1) {
+        int n_pow2 = 2;
+        while (n_pow2 < n_split * k) n_pow2 <<= 1;
+        bm25_flag_merge_kernel<<<static_cast<unsigned>(grid_x), 256, static_cast<size_t>(n_pow2) * 16, st>>>(
+            ps_, pi_, n_split, nq, k, sc.flag_list, sc.counters + 1, n_pow2, d_scores, d_ids);
+        ARB_LAUNCH_OK();
+      }
+    }
+  }
+  if (std::getenv("ARB_BM25_STATS")) {                           // diagnostics only: synchronises
+    std::vector<int> h(static_cast<size_t>(nq) + 2);
+    ARB_CUDA(cudaMemcpyAsync(h.data(), sc.e_cnt, h.size() * 4, cudaMemcpyDeviceToHost, st));
+    ARB_CUDA(cudaStreamSynchronize(st));
+    g_stats[0] += nq;
+    g_stats[1] += h[nq + 1];
+    for (int64_t i = 0; i < nq; ++i) { g_stats[2] += h[i]; g_stats[3] = std::max<int64_t>(g_stats[3], h[i]); }
+  }
+  return ARB_OK;
+}
+
+int bm25_batch_search(const Bm25Dev& ix, const int32_t* d_terms, int64_t nq, int max_qt, int k, int64_t id_base,
+                      double* d_scores, int64_t* d_ids, cudaStream_t st) {
+  int rc = batch_set_attrs();
+  if (rc) return rc;
+  // the member bitmap is nq x n_docs bits: cut the batch so that it stays under ~2 GB
+  const int64_t row_bytes = std::max<int64_t>(1, static_cast<int64_t>(ix.nb) * (DOC_BLOCK / 8));
+  int64_t chunk = std::max<int64_t>(64, (int64_t(2) << 30) / row_bytes);
+  if (const char* v = std::getenv("ARB_BM25_CHUNK")) chunk = std::max<int64_t>(1, atoll(v));
+  for (int64_t q0 = 0; q0 < nq; q0 += chunk) {
+    const int64_t n = std::min(chunk, nq - q0);
+    rc = batch_chunk(ix, d_terms + q0 * max_qt, n, max_qt, k, id_base, d_scores + q0 * k, d_ids + q0 * k, st);
+    if (rc) return rc;
+  }
+  return ARB_OK;
+}
+
+}  // namespace arb
+
+extern "C" int arb_bm25_batch_stats(int64_t out[4], int reset) {
+  for (int i = 0; i < 4; ++i) { if (out) out[i] = arb::g_stats[i]; if (reset) arb::g_stats[i] = 0; }
+  return ARB_OK;
+}

@@ -13,8 +13,8 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
-SOURCES = ["common.cu", "dense.cu", "bm25.cu", "fuse.cu"]
-HEADERS = ["common.cuh", "ptx.cuh", os.path.join(ROOT, "include", "anorag_b200.h")]
+SOURCES = ["common.cu", "dense.cu", "bm25.cu", "bm25_batch.cu", "fuse.cu"]
+HEADERS = ["common.cuh", "ptx.cuh", "bm25.cuh", os.path.join(ROOT, "include", "anorag_b200.h")]
 LIB = os.path.join(HERE, "libanorag_b200.so")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 FLAGS = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden",

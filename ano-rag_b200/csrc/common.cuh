@@ -61,7 +61,8 @@ int num_sms();
 
 // Optional per-thread kernel timing (bench.py roofline): when enabled, the dominant
 // kernels are bracketed by CUDA events on their launch stream.
-enum { PROF_DENSE_TOPK = 0, PROF_BM25_TOPK = 1, PROF_FUSE = 2, PROF_DENSE_MERGE = 3, PROF_KINDS = 4 };
+enum { PROF_DENSE_TOPK = 0, PROF_BM25_TOPK = 1, PROF_FUSE = 2, PROF_DENSE_MERGE = 3, PROF_BM25_SPARSE = 4,
+       PROF_BM25_PLANES = 5, PROF_BM25_FINAL = 6, PROF_IVF_COARSE = 7, PROF_KINDS = 8 };
 struct ProfileScope {
   int kind; cudaStream_t st; cudaEvent_t e0 = nullptr, e1 = nullptr; bool on;
   ProfileScope(int kind, cudaStream_t st);

@@ -81,9 +81,11 @@ ARB_API int64_t     arb_launch_count(int reset);
 /* Per-thread kernel timing for the roofline report: while enabled, the dominant
  * kernels are bracketed by CUDA events on their launch stream.  collect() waits for
  * them and returns summed milliseconds / launch counts per kind, then clears:
- * [0] dense GEMM+select  [1] BM25 top-k  [2] fusion  [3] dense list merge. */
+ * [0] dense GEMM+select  [1] BM25 top-k (whole arb_bm25_search)  [2] fusion  [3] dense list merge
+ * [4] BM25 sparse pass  [5] BM25 plane pass  [6] BM25 final merge + fallback  [7] IVF coarse probe. */
+#define ARB_PROFILE_KINDS 8
 ARB_API int         arb_profile(int enable);
-ARB_API int         arb_profile_collect(double out_ms[4], int64_t out_count[4]);
+ARB_API int         arb_profile_collect(double out_ms[ARB_PROFILE_KINDS], int64_t out_count[ARB_PROFILE_KINDS]);
 
 /* ------------------------------------------------------------------------- *
  * Dense: exact inner-product top-k (replaces faiss.IndexFlatIP behind
@@ -154,6 +156,11 @@ ARB_API int arb_bm25_search(const arb_bm25* bm, const int32_t* q_terms, int64_t 
 ARB_API int arb_bm25_scores(const arb_bm25* bm, const int32_t* q_terms, int64_t nq, int max_qt,
                     int q_is_device, int normalise, int64_t n_out, double* out,
                     int out_is_device, void* stream);
+
+/* Diagnostics of the batched pipeline, collected only while the environment variable ARB_BM25_STATS is
+ * set (each search then synchronises): [0] queries scored, [1] queries re-scored by the per-query
+ * fallback, [2] plane-pass emissions in total, [3] most emissions for one query.  Per calling thread. */
+ARB_API int arb_bm25_batch_stats(int64_t out[4], int reset);
 
 /* FieldWeightedBM25.get_scores combination (utils/bm25_search.py:117-145):
  * out[i] = ((0.0 + w[0]*s[0][i]) + w[1]*s[1][i]) + ... in fp64, fields in the given order; then, if

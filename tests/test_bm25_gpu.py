@@ -74,7 +74,10 @@ def test_degenerate_corpora_fall_back_to_simple():
 
 @pytest.mark.parametrize("variant,n,v,nq,k", [("okapi", 50_000, 4000, 300, 100), ("simple", 20_000, 500, 8, 40),
                                               ("okapi", 16_385, 50, 3, 256), ("okapi", 100, 10, 2, 100)])
-def test_topk_and_full_scores_match_array_oracle(variant, n, v, nq, k):
+@pytest.mark.parametrize("mode", ["query", "batch"])
+def test_topk_and_full_scores_match_array_oracle(variant, n, v, nq, k, mode, monkeypatch):
+    """Both device paths (per-query kernel, batched plane/sparse pipeline) against the restated reference."""
+    monkeypatch.setenv("ARB_BM25_MODE", mode)
     import ano_rag_b200  # noqa: F401
     from ano_rag_b200.utils.bm25_search import GpuBM25
     from oracle import bm25 as obm
@@ -123,3 +126,38 @@ def test_reference_golden_field_weighted_bm25(golden_dir):
                 assert corpus.get_scores(toks) == [fh(v) for v in q["raw"]], (case["name"], q["query"])
             assert field_weighted_bm25_scores(corpus, case["notes"], q["query"]) == [fh(v) for v in q["normalised"]]
         corpus.close()
+
+
+@pytest.mark.parametrize("n,v,nq,k,mean_len,planes", [(200_000, 20_000, 512, 100, 40, None), (30_000, 300, 257, 10, 12, None),
+                                                      (70_000, 5000, 300, 256, 30, "3"), (5_000, 40, 100, 100, 6, None),
+                                                      (120_000, 2000, 200, 50, 40, "0")])
+def test_batched_pipeline_equals_per_query_kernel(n, v, nq, k, mean_len, planes, monkeypatch):
+    """Every query of a batch: the plane/sparse pipeline (incl. its fallback and emission paths) returns
+    bit-identical scores and ids to the per-query kernel, which the tests above pin to the oracle."""
+    import ano_rag_b200  # noqa: F401
+    from ano_rag_b200 import synth, _native as nat
+    from ano_rag_b200.utils.bm25_search import GpuBM25
+    from oracle import bm25 as obm
+    if planes is not None:
+        monkeypatch.setenv("ARB_BM25_MAX_PLANES", planes)
+    monkeypatch.setenv("ARB_BM25_STATS", "1")
+    ptr, tok = synth.bm25_corpus(n, v, mean_len, seed=n + v)
+    qt = synth.bm25_queries(nq, ptr, tok, v, seed=7)
+    qt[3, :] = qt[3, 0]                       # one term eight times
+    qt[4, 1:] = -1
+    qt[5, :] = 0                              # the densest term only (no sparse members: fallback path)
+    qt[6, :4] = np.arange(4)                  # mostly plane terms
+    gpu = GpuBM25.from_token_ids(ptr, tok, v, variant="okapi")
+    monkeypatch.setenv("ARB_BM25_MODE", "query")
+    s0, i0 = gpu.search_terms(qt, k)
+    monkeypatch.setenv("ARB_BM25_MODE", "batch")
+    nat.bm25_batch_stats(reset=True)
+    s1, i1 = gpu.search_terms(qt, k)
+    stats = nat.bm25_batch_stats()
+    assert stats["queries"] == nq
+    assert np.array_equal(i0, i1) and np.array_equal(s0, s1), stats
+    ora = obm.ArrayBM25Oracle(ptr, tok, variant="okapi")
+    for r in (0, 3, 4, 5, 6, nq - 1):
+        ws, wi = obm.topk_positive(ora.get_scores([t for t in qt[r] if t >= 0]), k)
+        assert np.array_equal(i1[r], wi) and np.array_equal(s1[r], ws), f"query {r}"
+    gpu.close()
