@@ -297,8 +297,14 @@ def run_b200(a):
     b_ms = prof["bm25_topk"][0] / max(1, prof["bm25_topk"][1])
     n_local = row1 - row0
     dense_tflops = 2.0 * a.queries * n_local * a.dim / (d_ms * 1e-3) / 1e12 if d_ms > 0 else 0.0
-    bm25_bytes = local_postings * 4 + a.queries * a.topk * 16
+    # bytes/query = sum over query tokens of df(t) * (4 B doc id + 4 B impact) + k * 8 B of output.
+    # (The index itself stores 4 B per posting and the batched pipeline re-uses term planes across the
+    # queries of a batch from shared memory, so DRAM traffic is far below this figure: see `traffic`.)
+    bm25_bytes = local_postings * 8 + a.queries * a.topk * 8
     bm25_gbs = bm25_bytes / (b_ms * 1e-3) / 1e9 if b_ms > 0 else 0.0
+
+    def per_launch(kind):
+        return prof[kind][0] / max(1, prof[kind][1]) if kind in prof else 0.0
     traffic = {}
     tpath = os.path.join(ROOT, "profiles", "dram_traffic.json")
     if os.path.exists(tpath):
@@ -309,7 +315,9 @@ def run_b200(a):
                        "frac": dense_tflops / peaks["tflops"], "algorithmic_flops": 2.0 * a.queries * n_local * a.dim},
         "bm25_topk": {"ms": b_ms, "bound": "hbm", "achieved": bm25_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                       "frac": bm25_gbs / peaks["hbm_gbs"], "algorithmic_bytes": bm25_bytes,
-                      "postings_per_query": local_postings / a.queries},
+                      "postings_per_query": local_postings / a.queries,
+                      "kernels_ms": {"sparse_pass": per_launch("bm25_sparse"), "plane_pass": per_launch("bm25_planes"),
+                                     "final_merge_and_fallback": per_launch("bm25_final")}},
         "fuse": {"ms": prof["fuse"][0] / max(1, prof["fuse"][1])},
         "dense_merge": {"ms": prof["dense_merge"][0] / max(1, prof["dense_merge"][1])},
     }
