@@ -23,7 +23,7 @@ constexpr int SLICE = 1 << SLICE_LOG2;
 // tile-major: planes[(doc >> 8) * n_planes + s][plane_pos(doc & 255)].
 constexpr int PLANE_TILE_LOG2 = 8;
 constexpr int PLANE_TILE = 1 << PLANE_TILE_LOG2;
-constexpr int MAX_PLANES = 64;
+constexpr int MAX_PLANES = 96;
 // Position of doc d (0..255) inside a 256-entry plane-tile row.  The plane pass gives lane l the eight
 // docs 8l .. 8l+7 and reads them as four 16-byte chunks; chunk j of all lanes is contiguous, so every
 // LDS.128 of a warp is conflict free:  d = 8l + 2j + h  ->  (j*32 + l)*2 + h.

@@ -34,12 +34,12 @@
 
 namespace arb {
 
-constexpr int SP_MIN_BLOCK_LOG2 = 10;                // sparse-pass doc blocks: 1024 .. 8192 docs, chosen per query
-constexpr int SP_MAX_BLOCK_LOG2 = 13;
+constexpr int SP_MIN_BLOCK_LOG2 = 10;                // sparse-pass doc blocks: 1024 .. 16384 docs, chosen per query
+constexpr int SP_MAX_BLOCK_LOG2 = 14;
 constexpr int SP_MAXB = 1 << SP_MAX_BLOCK_LOG2;
 constexpr int SP_MAXM = 1024;                       // members per block visit (rank-compact accumulators)
-constexpr int SP_TARGET_M = 384;                    // block size aims at this many members per visit
-constexpr int SP_POOL = 1920;                       // fp64 pool: M accumulators + staged plane values
+constexpr int SP_TARGET_M = 448;                    // block size aims at this many members per visit
+constexpr int SP_POOL = 1728;                       // fp64 pool: M accumulators + staged plane values
 constexpr int SP_PCAP = 1024;                       // postings staged per visit
 constexpr int SP_STAGED_PLANES = 4;                 // plane tokens whose member values are staged by cp.async
 constexpr int PL_WARPS = 16;
