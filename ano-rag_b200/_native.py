@@ -59,6 +59,12 @@ _SIGS = {
     "arb_index_reconstruct": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_int, c_void_p]),
     "arb_index_search": (c_int, [c_void_p, c_void_p, c_int, c_int64, c_int, c_int, c_int, c_int64,
                                  c_void_p, c_void_p, c_int, c_void_p]),
+    "arb_index_ivf_set_centroids": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p]),
+    "arb_index_ivf_train": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int64, c_int, c_int, c_int, c_void_p]),
+    "arb_index_ivf_nlist": (c_int, [c_void_p]),
+    "arb_index_ivf_export": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p]),
+    "arb_index_ivf_search": (c_int, [c_void_p, c_void_p, c_int, c_int64, c_int, c_int, c_int, c_int, c_int64, c_void_p,
+                                     c_void_p, c_int, c_void_p]),
     "arb_bm25_create": (c_int, [POINTER(c_void_p), c_int64, c_int64, c_void_p, c_void_p, c_void_p,
                                 c_void_p, c_void_p, c_int64, c_void_p]),
     "arb_bm25_destroy": (c_int, [c_void_p]),

@@ -36,6 +36,8 @@ DEFAULTS: Dict[str, Any] = {
     },
     "b200": {
         "storage": "fp32",                  # 'fp32' (exact, 3 bf16 planes) | 'bf16'
+        "ivf": "exact",                     # 'exact': every index_type is the flat kernel | 'lists': IVFFlat is a real IVF
+        "ivf_niter": 25,                    # k-means iterations of train_index (faiss default)
         "bm25_backend": "okapi",            # what runs wherever rank_bm25 is installed (bm25_search.py:271-275)
     },
 }

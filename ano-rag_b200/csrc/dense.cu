@@ -18,6 +18,8 @@
 // the fp32 value); the six largest cross terms are accumulated in fp32 on the
 // tensor cores, smallest first.
 #include "common.cuh"
+
+#include <cub/cub.cuh>
 #include "ptx.cuh"
 
 #include <algorithm>
@@ -339,7 +341,10 @@ dense_merge_kernel(const DenseParams p, int64_t id_base, float* __restrict__ out
     const int n = p.counts[slot];
     for (int b = 0; b < n; b += 32) {
       uint2 e = make_uint2(0u, 0u);
-      if (b + lane < n) e = L[b + lane];
+      if (b + lane < n) {
+        e = L[b + lane];
+        if (IVF) e.x = static_cast<uint32_t>(p.row_ids[e.x]);   // rank and tie-break by the original row, not the list slot
+      }
       const bool pass = (b + lane < n) && e.y >= thr_key;
       const uint32_t m = __ballot_sync(0xffffffffu, pass);
       if (pass) buf[cnt + __popc(m & lt)] = e;
@@ -363,7 +368,7 @@ dense_merge_kernel(const DenseParams p, int64_t id_base, float* __restrict__ out
       rank += (o.y > e.y || (o.y == e.y && o.x < e.x)) ? 1 : 0;
     }
     out_scores[static_cast<size_t>(q) * p.k + rank] = key_f32(e.y);
-    out_ids[static_cast<size_t>(q) * p.k + rank] = id_base + (IVF ? p.row_ids[e.x] : static_cast<int64_t>(e.x));
+    out_ids[static_cast<size_t>(q) * p.k + rank] = id_base + static_cast<int64_t>(e.x);
   }
   for (int j = cnt + lane; j < p.k; j += 32) {
     out_scores[static_cast<size_t>(q) * p.k + j] = -3.4028234663852886e38f;   // faiss "no result"
@@ -486,6 +491,16 @@ struct arb_index {
   int64_t n = 0, cap = 0;
   __nv_bfloat16* rows = nullptr;       // [cap, planes*d_pad]
   size_t row_elems() const { return static_cast<size_t>(planes) * d_pad; }
+  // IVF (IndexIVFFlat, inner-product coarse quantiser; vector_index.py:85-91): nlist > 0 once centroids exist
+  int nlist = 0;
+  arb_index* coarse = nullptr;         // the centroids as a small flat index (same storage mode, no normalisation)
+  float* centroids = nullptr;          // [nlist, dim] fp32
+  int32_t* assign = nullptr;           // [cap] list of each row (add order)
+  bool grouped_dirty = true;
+  int64_t g_n = 0, g_cap = 0;
+  __nv_bfloat16* g_rows = nullptr;     // rows regrouped list-major
+  int64_t* g_ids = nullptr;            // [g_n] add-order position of each regrouped row
+  uint32_t* list_off = nullptr;        // [nlist + 1]
 };
 
 static int launch_prep(const void* src_dev, int dtype, int64_t n, int d, int d_pad, int planes, int normalize,
@@ -500,6 +515,8 @@ static int launch_prep(const void* src_dev, int dtype, int64_t n, int d, int d_p
   ARB_LAUNCH_OK();
   return ARB_OK;
 }
+
+static int ivf_assign_rows(arb_index* ix, int64_t row0, int64_t n, cudaStream_t st);
 
 extern "C" int arb_index_create(arb_index** out, int dim, int storage, int normalize) {
   ARB_CHECK(out != nullptr, ARB_EINVAL, "arb_index_create: out is NULL");
@@ -521,6 +538,12 @@ extern "C" int arb_index_create(arb_index** out, int dim, int storage, int norma
 extern "C" int arb_index_destroy(arb_index* ix) {
   if (!ix) return ARB_OK;
   if (ix->rows) cudaFree(ix->rows);
+  if (ix->coarse) arb_index_destroy(ix->coarse);
+  if (ix->centroids) cudaFree(ix->centroids);
+  if (ix->assign) cudaFree(ix->assign);
+  if (ix->g_rows) cudaFree(ix->g_rows);
+  if (ix->g_ids) cudaFree(ix->g_ids);
+  if (ix->list_off) cudaFree(ix->list_off);
   delete ix;
   return ARB_OK;
 }
@@ -528,6 +551,8 @@ extern "C" int arb_index_destroy(arb_index* ix) {
 extern "C" int arb_index_reset(arb_index* ix) {
   ARB_CHECK(ix != nullptr, ARB_EINVAL, "arb_index_reset: NULL index");
   ix->n = 0;
+  ix->g_n = 0;
+  ix->grouped_dirty = true;
   return ARB_OK;
 }
 
@@ -553,6 +578,15 @@ extern "C" int arb_index_add(arb_index* ix, const void* rows, int dtype, int64_t
     }
     if (ix->rows) cudaFree(ix->rows);
     ix->rows = nr;
+    int32_t* na = nullptr;
+    e = cudaMalloc(&na, static_cast<size_t>(ncap) * 4);
+    if (e != cudaSuccess) { cudaGetLastError(); set_error("arb_index_add: out of device memory"); return ARB_ENOMEM; }
+    if (ix->n > 0 && ix->assign) {
+      ARB_CUDA(cudaMemcpyAsync(na, ix->assign, static_cast<size_t>(ix->n) * 4, cudaMemcpyDeviceToDevice, st));
+      ARB_CUDA(cudaStreamSynchronize(st));
+    }
+    if (ix->assign) cudaFree(ix->assign);
+    ix->assign = na;
     ix->cap = ncap;
   }
   const size_t esz = dtype == ARB_F32 ? 4 : 2;
@@ -575,7 +609,12 @@ extern "C" int arb_index_add(arb_index* ix, const void* rows, int dtype, int64_t
     }
     ARB_CUDA(cudaStreamSynchronize(st));
   }
+  if (ix->nlist > 0) {                                   // IVF: quantise the new rows (add_with_ids, :187-193)
+    int rc = ivf_assign_rows(ix, ix->n, n, st);
+    if (rc) return rc;
+  }
   ix->n += n;
+  ix->grouped_dirty = true;
   return ARB_OK;
 }
 
@@ -616,6 +655,20 @@ static void plan_splits(int n_qtiles, int n_ntiles, int grid, int* n_splits, int
   *n_splits = (n_ntiles + *tiles_per_split - 1) / *tiles_per_split;
 }
 
+// (query plane, corpus plane) pairs, smallest magnitude first
+static void setup_terms(DenseParams& p, int q_planes, int planes, int d_pad) {
+  int terms[MAX_TERMS][2]; int nt = 0;
+  if (q_planes == 1 && planes == 1) { terms[nt][0] = 0; terms[nt++][1] = 0; }
+  else if (q_planes == 3 && planes == 1) { for (int a = 2; a >= 0; --a) { terms[nt][0] = a; terms[nt++][1] = 0; } }
+  else if (q_planes == 1 && planes == 3) { for (int b = 2; b >= 0; --b) { terms[nt][0] = 0; terms[nt++][1] = b; } }
+  else {
+    const int order[6][2] = {{2, 0}, {0, 2}, {1, 1}, {1, 0}, {0, 1}, {0, 0}};
+    for (int i = 0; i < 6; ++i) { terms[nt][0] = order[i][0]; terms[nt++][1] = order[i][1]; }
+  }
+  p.n_terms = nt;
+  for (int i = 0; i < nt; ++i) { p.a_col[i] = terms[i][0] * d_pad; p.b_col[i] = terms[i][1] * d_pad; }
+}
+
 template <int EPL>
 static int run_dense(const arb_index* ix, const __nv_bfloat16* qplanes, int q_planes, int64_t nq, int k,
                      int64_t id_base, float* d_scores, int64_t* d_ids, cudaStream_t st) {
@@ -626,17 +679,7 @@ static int run_dense(const arb_index* ix, const __nv_bfloat16* qplanes, int q_pl
   p.n_rows = static_cast<uint32_t>(ix->n);
   p.k = k;
   p.kb_per_term = ix->d_pad / BLOCK_K;
-  // (query plane, corpus plane) pairs, smallest magnitude first
-  int terms[MAX_TERMS][2]; int nt = 0;
-  if (q_planes == 1 && ix->planes == 1) { terms[nt][0] = 0; terms[nt++][1] = 0; }
-  else if (q_planes == 3 && ix->planes == 1) { for (int a = 2; a >= 0; --a) { terms[nt][0] = a; terms[nt++][1] = 0; } }
-  else if (q_planes == 1 && ix->planes == 3) { for (int b = 2; b >= 0; --b) { terms[nt][0] = 0; terms[nt++][1] = b; } }
-  else {
-    const int order[6][2] = {{2, 0}, {0, 2}, {1, 1}, {1, 0}, {0, 1}, {0, 0}};
-    for (int i = 0; i < 6; ++i) { terms[nt][0] = order[i][0]; terms[nt++][1] = order[i][1]; }
-  }
-  p.n_terms = nt;
-  for (int i = 0; i < nt; ++i) { p.a_col[i] = terms[i][0] * ix->d_pad; p.b_col[i] = terms[i][1] * ix->d_pad; }
+  setup_terms(p, q_planes, ix->planes, ix->d_pad);
   p.n_qtiles = static_cast<int>((nq + BLOCK_M - 1) / BLOCK_M);
   p.n_ntiles = static_cast<int>((ix->n + BLOCK_N - 1) / BLOCK_N);
   const int sms = num_sms();
@@ -718,6 +761,467 @@ extern "C" int arb_index_search(const arb_index* ix, const void* queries, int dt
   }
   if (k <= 128) rc = run_dense<16>(ix, qplanes.as<__nv_bfloat16>(), query_planes, nq, k, id_base, d_scores, d_ids, st);
   else          rc = run_dense<32>(ix, qplanes.as<__nv_bfloat16>(), query_planes, nq, k, id_base, d_scores, d_ids, st);
+  if (rc) return rc;
+  if (!out_is_device) {
+    ARB_CUDA(cudaMemcpyAsync(out_scores, d_scores, static_cast<size_t>(nq) * k * 4, cudaMemcpyDeviceToHost, st));
+    ARB_CUDA(cudaMemcpyAsync(out_ids, d_ids, static_cast<size_t>(nq) * k * 8, cudaMemcpyDeviceToHost, st));
+    ARB_CUDA(cudaStreamSynchronize(st));
+  }
+  return ARB_OK;
+}
+
+// ============================================================================
+// IVF (replaces faiss.IndexIVFFlat(IndexFlatIP(d), d, nlist, METRIC_INNER_PRODUCT) behind
+// VectorIndex: vector_index.py:85-91 create, :126-169 train, :187-193 add_with_ids, :223 search).
+//
+// Build: the coarse quantiser is the exact top-1 inner-product search over the centroids (the same
+// tcgen05 kernel with k = 1); rows are regrouped list-major on the device (stable radix sort by
+// list, so a list keeps ascending ids) the first time a search follows an add.
+// Search: top-nprobe centroids per query (same kernel, k = nprobe); the (query, probed list) pairs
+// are bucketed by list on the device and the queries of each list are gathered into 128-row A
+// tiles; one work item of the GEMM+select kernel = one A tile x the rows of its list, so a list
+// is streamed once for all the queries probing it and the score block never reaches HBM.
+// ============================================================================
+namespace arb {
+
+__global__ void ivf_ids_to_assign_kernel(const int64_t* __restrict__ ids, int64_t n, int32_t* __restrict__ assign) {
+  const int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  if (i < n) assign[i] = static_cast<int32_t>(ids[i] < 0 ? 0 : ids[i]);
+}
+__global__ void ivf_iota_kernel(int32_t* __restrict__ v, int64_t n) {
+  const int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  if (i < n) v[i] = static_cast<int32_t>(i);
+}
+// list_off[l] = first sorted position whose list >= l  (one thread per list boundary)
+__global__ void ivf_listoff_kernel(const int32_t* __restrict__ sorted_list, int64_t n, int nlist, uint32_t* __restrict__ list_off) {
+  const int l = blockIdx.x * blockDim.x + threadIdx.x;
+  if (l > nlist) return;
+  int64_t lo = 0, hi = n;
+  while (lo < hi) { const int64_t mid = (lo + hi) >> 1; if (sorted_list[mid] < l) lo = mid + 1; else hi = mid; }
+  list_off[l] = static_cast<uint32_t>(lo);
+}
+// regroup rows list-major: one warp per destination row
+__global__ void __launch_bounds__(256)
+ivf_regroup_kernel(const __nv_bfloat16* __restrict__ rows, const int32_t* __restrict__ perm, int64_t n, int row_elems,
+                   __nv_bfloat16* __restrict__ g_rows, int64_t* __restrict__ g_ids) {
+  const int lane = threadIdx.x & 31;
+  const int64_t r = blockIdx.x * static_cast<int64_t>(blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (r >= n) return;
+  const int64_t src = perm[r];
+  if (lane == 0) g_ids[r] = src;
+  const uint4* s4 = reinterpret_cast<const uint4*>(rows + src * row_elems);
+  uint4* d4 = reinterpret_cast<uint4*>(g_rows + r * row_elems);
+  for (int i = lane; i < row_elems / 8; i += 32) d4[i] = s4[i];
+}
+
+// ---- search-time planning -------------------------------------------------
+__global__ void ivf_count_kernel(const int64_t* __restrict__ probe, int64_t n_pairs, int* __restrict__ cnt, int* __restrict__ slot) {
+  const int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  if (i >= n_pairs) return;
+  const int64_t l = probe[i];
+  slot[i] = l >= 0 ? atomicAdd(&cnt[l], 1) : -1;
+}
+// one block: items per list -> exclusive scan -> item table
+__global__ void __launch_bounds__(1024)
+ivf_plan_kernel(const int* __restrict__ cnt, int nlist, const uint32_t* __restrict__ list_off, int* __restrict__ item_start,
+                int* __restrict__ n_items, IvfItem* __restrict__ items) {
+  __shared__ int warp_sum[32];
+  __shared__ int carry_s;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid == 0) carry_s = 0;
+  __syncthreads();
+  for (int base = 0; base < nlist; base += 1024) {
+    const int l = base + tid;
+    const int mine = l < nlist ? (cnt[l] + BLOCK_M - 1) / BLOCK_M : 0;
+    int incl = mine;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
+    if (lane == 31) warp_sum[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+      int w = warp_sum[lane];
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, w, o); if (lane >= o) w += v; }
+      warp_sum[lane] = w;
+    }
+    __syncthreads();
+    const int carry = carry_s;
+    const int start = carry + (warp ? warp_sum[warp - 1] : 0) + incl - mine;
+    if (l < nlist) {
+      item_start[l] = start;
+      const IvfItem it = {list_off[l], list_off[l + 1]};
+      for (int i = 0; i < mine; ++i) items[start + i] = it;
+    }
+    __syncthreads();
+    if (tid == 1023) carry_s = carry + warp_sum[31];
+    __syncthreads();
+  }
+  if (tid == 0) *n_items = carry_s;
+}
+__global__ void ivf_place_kernel(const int64_t* __restrict__ probe, const int* __restrict__ slot, const int* __restrict__ item_start,
+                                 int64_t n_pairs, int nprobe, int* __restrict__ row_query, int* __restrict__ pair_pos) {
+  const int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  if (i >= n_pairs) return;
+  const int64_t l = probe[i];
+  int pos = -1;
+  if (l >= 0) {
+    pos = item_start[l] * BLOCK_M + slot[i];
+    row_query[pos] = static_cast<int>(i / nprobe);
+  }
+  pair_pos[i] = pos;
+}
+// gathered A matrix: row pos <- query planes of row_query[pos] (zeros for padding rows); one warp per row
+__global__ void __launch_bounds__(256)
+ivf_gather_kernel(const __nv_bfloat16* __restrict__ qplanes, const int* __restrict__ row_query, const int* __restrict__ n_items,
+                  int row_elems, __nv_bfloat16* __restrict__ ag) {
+  const int lane = threadIdx.x & 31;
+  const int64_t r = blockIdx.x * static_cast<int64_t>(blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (r >= static_cast<int64_t>(*n_items) * BLOCK_M) return;
+  const int q = row_query[r];
+  uint4* d4 = reinterpret_cast<uint4*>(ag + r * row_elems);
+  if (q < 0) { for (int i = lane; i < row_elems / 8; i += 32) d4[i] = make_uint4(0u, 0u, 0u, 0u); return; }
+  const uint4* s4 = reinterpret_cast<const uint4*>(qplanes + static_cast<int64_t>(q) * row_elems);
+  for (int i = lane; i < row_elems / 8; i += 32) d4[i] = s4[i];
+}
+
+// ---- k-means (train_index) --------------------------------------------------
+// new centroid = mean of the rows assigned to it (rows are visited in sorted order: deterministic);
+// spherical: L2-normalised afterwards (faiss sets cp.spherical for inner-product IVF).  Block per centroid.
+__global__ void __launch_bounds__(256)
+ivf_kmeans_update_kernel(const __nv_bfloat16* __restrict__ rows, const int32_t* __restrict__ perm,
+                         const uint32_t* __restrict__ list_off, int dim, int d_pad, int planes, int spherical,
+                         float* __restrict__ centroids) {
+  __shared__ float red[8];
+  const int c = blockIdx.x;
+  const uint32_t lo = list_off[c], hi = list_off[c + 1];
+  if (lo == hi) return;                                   // empty cluster keeps its centroid
+  const float inv = 1.0f / static_cast<float>(hi - lo);
+  float ss = 0.f;
+  for (int j = threadIdx.x; j < dim; j += blockDim.x) {
+    float acc = 0.f;
+    for (uint32_t i = lo; i < hi; ++i) {
+      const __nv_bfloat16* src = rows + static_cast<int64_t>(perm[i]) * planes * d_pad;
+      float v = 0.f;
+      for (int pl = planes - 1; pl >= 0; --pl) v = __fadd_rn(v, __bfloat162float(src[pl * d_pad + j]));
+      acc = __fadd_rn(acc, v);
+    }
+    acc = __fmul_rn(acc, inv);
+    centroids[static_cast<int64_t>(c) * dim + j] = acc;
+    ss = fmaf(acc, acc, ss);
+  }
+  if (!spherical) return;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = ss;
+  __syncthreads();
+  float tot = 0.f;
+  for (int w = 0; w < 8; ++w) tot += red[w];
+  const float nrm = sqrtf(tot);
+  if (nrm > 0.f)
+    for (int j = threadIdx.x; j < dim; j += blockDim.x)
+      centroids[static_cast<int64_t>(c) * dim + j] = __fdiv_rn(centroids[static_cast<int64_t>(c) * dim + j], nrm);
+}
+__global__ void ivf_pick_rows_kernel(const __nv_bfloat16* __restrict__ rows, int64_t n, int nlist, int dim, int d_pad, int planes,
+                                     float* __restrict__ centroids) {
+  const int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  if (i >= static_cast<int64_t>(nlist) * dim) return;
+  const int c = static_cast<int>(i / dim), j = static_cast<int>(i % dim);
+  const int64_t r = static_cast<int64_t>(c) * n / nlist;                 // evenly spaced training rows as seeds
+  const __nv_bfloat16* src = rows + r * planes * d_pad;
+  float v = 0.f;
+  for (int pl = planes - 1; pl >= 0; --pl) v = __fadd_rn(v, __bfloat162float(src[pl * d_pad + j]));
+  centroids[i] = v;
+}
+
+}  // namespace arb
+
+// rows in storage layout -> nearest centroid (max inner product), written to assign_out[0..n)
+static int ivf_quantise(const arb_index* ix, const __nv_bfloat16* rows_storage, int64_t n, int32_t* assign_out, cudaStream_t st) {
+  AsyncBuf sc, id;
+  const int64_t chunk = int64_t(1) << 22;
+  ARB_CUDA(sc.alloc(static_cast<size_t>(std::min(n, chunk)) * 4, st));
+  ARB_CUDA(id.alloc(static_cast<size_t>(std::min(n, chunk)) * 8, st));
+  for (int64_t off = 0; off < n; off += chunk) {
+    const int64_t m = std::min(chunk, n - off);
+    int rc = run_dense<16>(ix->coarse, rows_storage + static_cast<size_t>(off) * ix->row_elems(), ix->planes, m, 1, 0,
+                           sc.as<float>(), id.as<int64_t>(), st);
+    if (rc) return rc;
+    ivf_ids_to_assign_kernel<<<static_cast<unsigned>((m + 255) / 256), 256, 0, st>>>(id.as<int64_t>(), m, assign_out + off);
+    ARB_LAUNCH_OK();
+  }
+  return ARB_OK;
+}
+
+static int ivf_assign_rows(arb_index* ix, int64_t row0, int64_t n, cudaStream_t st) {
+  return ivf_quantise(ix, ix->rows + static_cast<size_t>(row0) * ix->row_elems(), n, ix->assign + row0, st);
+}
+
+// (list, add-order position) stable sort -> perm (sorted positions) and list offsets
+static int ivf_sort_by_list(const int32_t* assign, int64_t n, int nlist, AsyncBuf& perm, uint32_t* list_off, cudaStream_t st) {
+  AsyncBuf keys_out, idx_in, tmp;
+  ARB_CUDA(keys_out.alloc(static_cast<size_t>(n) * 4, st));
+  ARB_CUDA(idx_in.alloc(static_cast<size_t>(n) * 4, st));
+  ARB_CUDA(perm.alloc(static_cast<size_t>(n) * 4, st));
+  ivf_iota_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, st>>>(idx_in.as<int32_t>(), n);
+  ARB_LAUNCH_OK();
+  size_t tmp_bytes = 0;
+  int end_bit = 1;
+  while ((1 << end_bit) < nlist && end_bit < 31) ++end_bit;
+  ARB_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, assign, keys_out.as<int32_t>(), idx_in.as<int32_t>(),
+                                           perm.as<int32_t>(), static_cast<int>(n), 0, end_bit, st));
+  ARB_CUDA(tmp.alloc(tmp_bytes, st));
+  ARB_CUDA(cub::DeviceRadixSort::SortPairs(tmp.p, tmp_bytes, assign, keys_out.as<int32_t>(), idx_in.as<int32_t>(),
+                                           perm.as<int32_t>(), static_cast<int>(n), 0, end_bit, st));
+  count_launch(4);
+  ivf_listoff_kernel<<<static_cast<unsigned>((nlist + 1 + 255) / 256), 256, 0, st>>>(keys_out.as<int32_t>(), n, nlist, list_off);
+  ARB_LAUNCH_OK();
+  return ARB_OK;
+}
+
+static int ivf_regroup(arb_index* ix, cudaStream_t st) {
+  if (!ix->grouped_dirty) return ARB_OK;
+  ARB_CHECK(ix->n < (int64_t(1) << 31), ARB_ELIMIT, "IVF: at most 2^31 rows per shard");
+  if (ix->g_cap < ix->n) {
+    if (ix->g_rows) cudaFree(ix->g_rows);
+    if (ix->g_ids) cudaFree(ix->g_ids);
+    ix->g_rows = nullptr; ix->g_ids = nullptr; ix->g_cap = 0;
+    if (cudaMalloc(&ix->g_rows, static_cast<size_t>(ix->n) * ix->row_elems() * 2) != cudaSuccess ||
+        cudaMalloc(&ix->g_ids, static_cast<size_t>(ix->n) * 8) != cudaSuccess) {
+      cudaGetLastError(); set_error("IVF regroup: out of device memory"); return ARB_ENOMEM;
+    }
+    ix->g_cap = ix->n;
+  }
+  AsyncBuf perm;
+  int rc = ivf_sort_by_list(ix->assign, ix->n, ix->nlist, perm, ix->list_off, st);
+  if (rc) return rc;
+  ivf_regroup_kernel<<<static_cast<unsigned>((ix->n + 7) / 8), 256, 0, st>>>(ix->rows, perm.as<int32_t>(), ix->n,
+                                                                            static_cast<int>(ix->row_elems()), ix->g_rows, ix->g_ids);
+  ARB_LAUNCH_OK();
+  ARB_CUDA(cudaStreamSynchronize(st));
+  ix->g_n = ix->n;
+  ix->grouped_dirty = false;
+  return ARB_OK;
+}
+
+// centroids (fp32, device) -> coarse index; re-quantise the rows already stored
+static int ivf_install_centroids(arb_index* ix, int nlist, cudaStream_t st) {
+  if (ix->coarse) { arb_index_destroy(ix->coarse); ix->coarse = nullptr; }
+  int rc = arb_index_create(&ix->coarse, ix->dim, ix->storage, 0);
+  if (rc) return rc;
+  rc = arb_index_add(ix->coarse, ix->centroids, ARB_F32, nlist, 1, st);
+  if (rc) return rc;
+  if (ix->list_off) cudaFree(ix->list_off);
+  ix->list_off = nullptr;
+  ARB_CUDA(cudaMalloc(&ix->list_off, static_cast<size_t>(nlist + 1) * 4));
+  ix->nlist = nlist;
+  ix->grouped_dirty = true;
+  if (ix->n > 0) return ivf_assign_rows(ix, 0, ix->n, st);
+  return ARB_OK;
+}
+
+extern "C" int arb_index_ivf_set_centroids(arb_index* ix, int nlist, const float* centroids, int is_device, void* stream) {
+  ARB_CHECK(ix != nullptr && centroids != nullptr, ARB_EINVAL, "arb_index_ivf_set_centroids: NULL argument");
+  ARB_CHECK(nlist >= 1 && nlist <= (1 << 20), ARB_ELIMIT, "arb_index_ivf_set_centroids: nlist must be in [1, 2^20]");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (ix->centroids) { cudaFree(ix->centroids); ix->centroids = nullptr; }
+  ARB_CUDA(cudaMalloc(&ix->centroids, static_cast<size_t>(nlist) * ix->dim * 4));
+  ARB_CUDA(cudaMemcpyAsync(ix->centroids, centroids, static_cast<size_t>(nlist) * ix->dim * 4,
+                           is_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, st));
+  int rc = ivf_install_centroids(ix, nlist, st);
+  if (rc) return rc;
+  ARB_CUDA(cudaStreamSynchronize(st));
+  return ARB_OK;
+}
+
+extern "C" int arb_index_ivf_train(arb_index* ix, int nlist, const void* rows, int dtype, int64_t n, int rows_is_device,
+                                   int niter, int spherical, void* stream) {
+  ARB_CHECK(ix != nullptr && rows != nullptr, ARB_EINVAL, "arb_index_ivf_train: NULL argument");
+  ARB_CHECK(nlist >= 1 && nlist <= (1 << 20), ARB_ELIMIT, "arb_index_ivf_train: nlist must be in [1, 2^20]");
+  ARB_CHECK(n >= nlist, ARB_EINVAL, "arb_index_ivf_train: fewer training rows than lists");
+  ARB_CHECK(n < (int64_t(1) << 31), ARB_ELIMIT, "arb_index_ivf_train: at most 2^31 training rows");
+  ARB_CHECK(dtype == ARB_F32 || dtype == ARB_BF16, ARB_EINVAL, "arb_index_ivf_train: dtype must be ARB_F32 or ARB_BF16");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  // the training rows, pre-processed exactly like added rows, in a scratch index
+  arb_index* tr = nullptr;
+  int rc = arb_index_create(&tr, ix->dim, ix->storage, ix->normalize);
+  if (rc) return rc;
+  struct Guard { arb_index* p; ~Guard() { arb_index_destroy(p); } } guard{tr};
+  rc = arb_index_add(tr, rows, dtype, n, rows_is_device, st);
+  if (rc) return rc;
+  if (ix->centroids) { cudaFree(ix->centroids); ix->centroids = nullptr; }
+  ARB_CUDA(cudaMalloc(&ix->centroids, static_cast<size_t>(nlist) * ix->dim * 4));
+  const int64_t nc = static_cast<int64_t>(nlist) * ix->dim;
+  ivf_pick_rows_kernel<<<static_cast<unsigned>((nc + 255) / 256), 256, 0, st>>>(tr->rows, n, nlist, ix->dim, ix->d_pad, ix->planes, ix->centroids);
+  ARB_LAUNCH_OK();
+  AsyncBuf assign, loff;
+  ARB_CUDA(assign.alloc(static_cast<size_t>(n) * 4, st));
+  ARB_CUDA(loff.alloc(static_cast<size_t>(nlist + 1) * 4, st));
+  for (int it = 0; it < niter; ++it) {
+    // quantise with the current centroids, then move every centroid to the mean of its rows
+    arb_index* coarse = nullptr;
+    rc = arb_index_create(&coarse, ix->dim, ix->storage, 0);
+    if (rc) return rc;
+    Guard cg{coarse};
+    rc = arb_index_add(coarse, ix->centroids, ARB_F32, nlist, 1, st);
+    if (rc) return rc;
+    arb_index view = *tr;                      // borrow tr's rows with this iteration's quantiser
+    view.coarse = coarse;
+    rc = ivf_quantise(&view, tr->rows, n, assign.as<int32_t>(), st);
+    view.coarse = nullptr; view.rows = nullptr;
+    if (rc) return rc;
+    AsyncBuf perm;
+    rc = ivf_sort_by_list(assign.as<int32_t>(), n, nlist, perm, loff.as<uint32_t>(), st);
+    if (rc) return rc;
+    ivf_kmeans_update_kernel<<<nlist, 256, 0, st>>>(tr->rows, perm.as<int32_t>(), loff.as<uint32_t>(), ix->dim, ix->d_pad,
+                                                     ix->planes, spherical, ix->centroids);
+    ARB_LAUNCH_OK();
+    ARB_CUDA(cudaStreamSynchronize(st));       // coarse dies at scope end
+  }
+  rc = ivf_install_centroids(ix, nlist, st);
+  if (rc) return rc;
+  ARB_CUDA(cudaStreamSynchronize(st));
+  return ARB_OK;
+}
+
+extern "C" int arb_index_ivf_nlist(const arb_index* ix) { return ix ? ix->nlist : 0; }
+
+extern "C" int arb_index_ivf_export(const arb_index* ix, float* centroids_out, int32_t* assign_out, void* stream) {
+  ARB_CHECK(ix != nullptr && ix->nlist > 0, ARB_EINVAL, "arb_index_ivf_export: index has no IVF state");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (centroids_out) ARB_CUDA(cudaMemcpyAsync(centroids_out, ix->centroids, static_cast<size_t>(ix->nlist) * ix->dim * 4, cudaMemcpyDeviceToHost, st));
+  if (assign_out && ix->n) ARB_CUDA(cudaMemcpyAsync(assign_out, ix->assign, static_cast<size_t>(ix->n) * 4, cudaMemcpyDeviceToHost, st));
+  ARB_CUDA(cudaStreamSynchronize(st));
+  return ARB_OK;
+}
+
+template <int EPL>
+static int run_ivf(arb_index* ix, const __nv_bfloat16* qplanes, int q_planes, int64_t nq, int k, int nprobe,
+                   int64_t id_base, float* d_scores, int64_t* d_ids, cudaStream_t st) {
+  constexpr int C = 32 * EPL;
+  const int sms = num_sms();
+  const int64_t n_pairs = nq * nprobe;
+  const int64_t max_items = n_pairs / BLOCK_M + std::min<int64_t>(ix->nlist, n_pairs) + 1;
+  ARB_CHECK(max_items * BLOCK_M < (int64_t(1) << 31), ARB_ELIMIT, "arb_index_ivf_search: nq * nprobe too large for one call");
+  AsyncBuf pscore, pids, cnt, slot, item_start, n_items, items, row_query, pair_pos, ag, lists, counts, gthr;
+  ARB_CUDA(pscore.alloc(static_cast<size_t>(n_pairs) * 4, st));
+  ARB_CUDA(pids.alloc(static_cast<size_t>(n_pairs) * 8, st));
+  {
+    ProfileScope ps(PROF_IVF_COARSE, st);
+    int rc = nprobe <= 128 ? run_dense<16>(ix->coarse, qplanes, q_planes, nq, nprobe, 0, pscore.as<float>(), pids.as<int64_t>(), st)
+                           : run_dense<32>(ix->coarse, qplanes, q_planes, nq, nprobe, 0, pscore.as<float>(), pids.as<int64_t>(), st);
+    if (rc) return rc;
+  }
+  ARB_CUDA(cnt.alloc(static_cast<size_t>(ix->nlist) * 4, st));
+  ARB_CUDA(slot.alloc(static_cast<size_t>(n_pairs) * 4, st));
+  ARB_CUDA(item_start.alloc(static_cast<size_t>(ix->nlist) * 4, st));
+  ARB_CUDA(n_items.alloc(4, st));
+  ARB_CUDA(items.alloc(static_cast<size_t>(max_items) * sizeof(IvfItem), st));
+  ARB_CUDA(row_query.alloc(static_cast<size_t>(max_items) * BLOCK_M * 4, st));
+  ARB_CUDA(pair_pos.alloc(static_cast<size_t>(n_pairs) * 4, st));
+  const size_t q_row = static_cast<size_t>(q_planes) * ix->d_pad;
+  ARB_CUDA(ag.alloc(static_cast<size_t>(max_items) * BLOCK_M * q_row * 2, st));
+  ARB_CUDA(cudaMemsetAsync(cnt.p, 0, static_cast<size_t>(ix->nlist) * 4, st));
+  ARB_CUDA(cudaMemsetAsync(row_query.p, 0xFF, static_cast<size_t>(max_items) * BLOCK_M * 4, st));
+  ivf_count_kernel<<<static_cast<unsigned>((n_pairs + 255) / 256), 256, 0, st>>>(pids.as<int64_t>(), n_pairs, cnt.as<int>(), slot.as<int>());
+  ARB_LAUNCH_OK();
+  ivf_plan_kernel<<<1, 1024, 0, st>>>(cnt.as<int>(), ix->nlist, ix->list_off, item_start.as<int>(), n_items.as<int>(), items.as<IvfItem>());
+  ARB_LAUNCH_OK();
+  ivf_place_kernel<<<static_cast<unsigned>((n_pairs + 255) / 256), 256, 0, st>>>(pids.as<int64_t>(), slot.as<int>(), item_start.as<int>(), n_pairs,
+                                                                                  nprobe, row_query.as<int>(), pair_pos.as<int>());
+  ARB_LAUNCH_OK();
+  ivf_gather_kernel<<<static_cast<unsigned>((max_items * BLOCK_M + 7) / 8), 256, 0, st>>>(qplanes, row_query.as<int>(), n_items.as<int>(),
+                                                                                           static_cast<int>(q_row), ag.as<__nv_bfloat16>());
+  ARB_LAUNCH_OK();
+
+  DenseParams p;
+  memset(&p, 0, sizeof(p));
+  p.nq = static_cast<int>(nq);
+  p.n_rows = static_cast<uint32_t>(ix->g_n);
+  p.k = k;
+  p.kb_per_term = ix->d_pad / BLOCK_K;
+  setup_terms(p, q_planes, ix->planes, ix->d_pad);
+  p.n_qtiles = static_cast<int>((nq + BLOCK_M - 1) / BLOCK_M);
+  p.items = items.as<IvfItem>();
+  p.n_items_ptr = n_items.as<int>();
+  p.row_query = row_query.as<int>();
+  p.pair_pos = pair_pos.as<int>();
+  p.nprobe = nprobe;
+  p.row_ids = ix->g_ids;
+  ARB_CUDA(lists.alloc(static_cast<size_t>(max_items) * BLOCK_M * C * sizeof(uint2), st));
+  ARB_CUDA(counts.alloc(static_cast<size_t>(max_items) * BLOCK_M * sizeof(int), st));
+  ARB_CUDA(gthr.alloc(static_cast<size_t>(p.n_qtiles) * BLOCK_M * sizeof(uint32_t), st));
+  p.lists = lists.as<uint2>();
+  p.counts = counts.as<int>();
+  p.gthr = gthr.as<uint32_t>();
+  const size_t ng = static_cast<size_t>(p.n_qtiles) * BLOCK_M;
+  fill_u32_kernel<<<static_cast<unsigned>((ng + 255) / 256), 256, 0, st>>>(p.gthr, KEY_NEG_INF, ng);
+  ARB_LAUNCH_OK();
+
+  CUtensorMap ta, tb;
+  int rc = make_tmap(&ta, ag.p, static_cast<uint64_t>(max_items) * BLOCK_M, q_row, BLOCK_M);
+  if (rc) return rc;
+  rc = make_tmap(&tb, ix->g_rows, static_cast<uint64_t>(ix->g_n), static_cast<uint64_t>(ix->planes) * ix->d_pad, BLOCK_N);
+  if (rc) return rc;
+  static std::once_flag attr_once;
+  static cudaError_t attr_err = cudaSuccess;
+  std::call_once(attr_once, [] {
+    attr_err = cudaFuncSetAttribute(dense_topk_kernel<EPL, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, DENSE_SMEM);
+  });
+  ARB_CUDA(attr_err);
+  const int grid = static_cast<int>(std::min<int64_t>(sms, max_items));
+  {
+    ProfileScope ps(PROF_DENSE_TOPK, st);
+    dense_topk_kernel<EPL, true><<<grid, DENSE_THREADS, DENSE_SMEM, st>>>(ta, tb, p);
+  }
+  ARB_LAUNCH_OK();
+  const int wpb = 4;
+  {
+    ProfileScope ps(PROF_DENSE_MERGE, st);
+    dense_merge_kernel<EPL, true><<<static_cast<unsigned>((nq + wpb - 1) / wpb), wpb * 32, wpb * C * sizeof(uint2), st>>>(
+        p, id_base, d_scores, d_ids);
+  }
+  ARB_LAUNCH_OK();
+  return ARB_OK;
+}
+
+extern "C" int arb_index_ivf_search(arb_index* ix, const void* queries, int dtype, int64_t nq, int queries_is_device,
+                                    int k, int nprobe, int query_planes, int64_t id_base, float* out_scores,
+                                    int64_t* out_ids, int out_is_device, void* stream) {
+  ARB_CHECK(ix != nullptr, ARB_EINVAL, "arb_index_ivf_search: NULL index");
+  ARB_CHECK(ix->nlist > 0, ARB_EINVAL, "arb_index_ivf_search: index is not trained (no centroids)");
+  ARB_CHECK(nq >= 0 && (queries != nullptr || nq == 0), ARB_EINVAL, "arb_index_ivf_search: bad queries/nq");
+  ARB_CHECK(out_scores != nullptr && out_ids != nullptr, ARB_EINVAL, "arb_index_ivf_search: NULL output");
+  ARB_CHECK(dtype == ARB_F32 || dtype == ARB_BF16, ARB_EINVAL, "arb_index_ivf_search: dtype must be ARB_F32 or ARB_BF16");
+  ARB_CHECK(k >= 1 && k <= ARB_MAX_TOPK, ARB_ELIMIT, "arb_index_ivf_search: k must be in [1, 256]");
+  ARB_CHECK(nprobe >= 1, ARB_EINVAL, "arb_index_ivf_search: nprobe must be >= 1");
+  ARB_CHECK(query_planes == 1 || query_planes == 3, ARB_EINVAL, "arb_index_ivf_search: query_planes must be 1 or 3");
+  ARB_CHECK(ix->n > 0, ARB_EINVAL, "arb_index_ivf_search: index is empty");
+  if (nq == 0) return ARB_OK;
+  nprobe = std::min(nprobe, std::min(ix->nlist, ARB_MAX_TOPK));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  int rc = ivf_regroup(ix, st);
+  if (rc) return rc;
+  const size_t esz = dtype == ARB_F32 ? 4 : 2;
+  AsyncBuf qstage, qplanes, oscores, oids;
+  const void* q_dev = queries;
+  if (!queries_is_device) {
+    ARB_CUDA(qstage.alloc(static_cast<size_t>(nq) * ix->dim * esz, st));
+    ARB_CUDA(cudaMemcpyAsync(qstage.p, queries, static_cast<size_t>(nq) * ix->dim * esz, cudaMemcpyHostToDevice, st));
+    q_dev = qstage.p;
+  }
+  ARB_CUDA(qplanes.alloc(static_cast<size_t>(nq) * query_planes * ix->d_pad * 2, st));
+  rc = launch_prep(q_dev, dtype, nq, ix->dim, ix->d_pad, query_planes, ix->normalize, qplanes.as<__nv_bfloat16>(), st);
+  if (rc) return rc;
+  float* d_scores = out_scores;
+  int64_t* d_ids = out_ids;
+  if (!out_is_device) {
+    ARB_CUDA(oscores.alloc(static_cast<size_t>(nq) * k * 4, st));
+    ARB_CUDA(oids.alloc(static_cast<size_t>(nq) * k * 8, st));
+    d_scores = oscores.as<float>();
+    d_ids = oids.as<int64_t>();
+  }
+  if (k <= 128) rc = run_ivf<16>(ix, qplanes.as<__nv_bfloat16>(), query_planes, nq, k, nprobe, id_base, d_scores, d_ids, st);
+  else          rc = run_ivf<32>(ix, qplanes.as<__nv_bfloat16>(), query_planes, nq, k, nprobe, id_base, d_scores, d_ids, st);
   if (rc) return rc;
   if (!out_is_device) {
     ARB_CUDA(cudaMemcpyAsync(out_scores, d_scores, static_cast<size_t>(nq) * k * 4, cudaMemcpyDeviceToHost, st));

@@ -134,6 +134,53 @@ class DenseIndex:
         return scores, ids
 
 
+    # -- IVF (IndexIVFFlat): the same handle, once it has centroids
+    @property
+    def nlist(self) -> int:
+        return int(nat.lib.arb_index_ivf_nlist(self._h))
+
+    def set_centroids(self, centroids) -> None:
+        b = _Buf(centroids, (np.dtype(np.float32),), (torch.float32,) if torch is not None else (), "centroids")
+        if len(b.shape) != 2 or b.shape[1] != self.dim:
+            raise ValueError(f"centroids must be [nlist, {self.dim}], got {b.shape}")
+        nat.check(nat.lib.arb_index_ivf_set_centroids(self._h, b.shape[0], b.ptr, b.is_device, _stream_ptr(b.device)))
+
+    def train(self, rows, nlist: int, niter: int = 25, spherical: bool = True) -> None:
+        b = _Buf(rows, (np.dtype(np.float32),), (torch.float32, torch.bfloat16) if torch is not None else (), "rows")
+        if len(b.shape) != 2 or b.shape[1] != self.dim:
+            raise ValueError(f"rows must be [n, {self.dim}], got {b.shape}")
+        nat.check(nat.lib.arb_index_ivf_train(self._h, int(nlist), b.ptr, b.code, b.shape[0], b.is_device, int(niter),
+                                              1 if spherical else 0, _stream_ptr(b.device)))
+
+    def ivf_export(self):
+        """-> (centroids fp32 [nlist, dim], list of every row int32 [ntotal])"""
+        cent = np.empty((self.nlist, self.dim), dtype=np.float32)
+        assign = np.empty(self.ntotal, dtype=np.int32)
+        nat.check(nat.lib.arb_index_ivf_export(self._h, cent.ctypes.data, assign.ctypes.data, _stream_ptr()))
+        return cent, assign
+
+    def ivf_search(self, queries, k: int, nprobe: int, query_planes: Optional[int] = None, id_base: int = 0):
+        """Same contract as search(), restricted to the nprobe lists nearest to each query."""
+        if query_planes is None:
+            query_planes = 3 if self.storage == "fp32" else 1
+        b = _Buf(queries, (np.dtype(np.float32),), (torch.float32, torch.bfloat16) if torch is not None else (), "queries")
+        if len(b.shape) != 2 or b.shape[1] != self.dim:
+            raise ValueError(f"queries must be [nq, {self.dim}], got {b.shape}")
+        nq = b.shape[0]
+        if b.is_device:
+            with torch.cuda.device(b.device):
+                scores = torch.empty((nq, k), dtype=torch.float32, device=b.device)
+                ids = torch.empty((nq, k), dtype=torch.int64, device=b.device)
+                nat.check(nat.lib.arb_index_ivf_search(self._h, b.ptr, b.code, nq, 1, k, int(nprobe), query_planes, id_base,
+                                                       scores.data_ptr(), ids.data_ptr(), 1, _stream_ptr(b.device)))
+            return scores, ids
+        scores = np.empty((nq, k), dtype=np.float32)
+        ids = np.empty((nq, k), dtype=np.int64)
+        nat.check(nat.lib.arb_index_ivf_search(self._h, b.ptr, b.code, nq, 0, k, int(nprobe), query_planes, id_base,
+                                               scores.ctypes.data, ids.ctypes.data, 0, _stream_ptr()))
+        return scores, ids
+
+
 class BM25Index:
     """Device-resident block-partitioned inverted index (see csrc/bm25.cu)."""
 

@@ -7,9 +7,12 @@ Same constructor, attributes, method names, return shapes and error convention
 path -- without a CUDA device ``create_index`` fails and logs.
 
 Differences, all stated in DESIGN.md:
-  * every ``index_type`` is served by the exact flat kernel (recall 1.0); ``nlist`` /
-    ``nprobe`` are kept as attributes, including the nlist shrink of ``train_index``
-    (:140-155), but do not approximate the search.
+  * ``b200.ivf = "exact"`` (default): every ``index_type`` is served by the exact flat kernel
+    (recall 1.0); ``nlist`` / ``nprobe`` are kept as attributes, including the nlist shrink of
+    ``train_index`` (:140-155), but do not approximate the search.
+    ``b200.ivf = "lists"``: 'IVFFlat' is a real inverted-file index on the device -- ``train_index``
+    runs k-means for ``nlist`` centroids (or ``set_centroids`` installs given ones), ``add_vectors``
+    quantises rows to the centroid of largest inner product, ``search`` scans ``nprobe`` lists.
   * ``similarity_metric`` other than 'cosine' (L2) is not on the north-star path and
     is rejected by ``create_index``.
   * ``search_tensors`` is an addition: the batched tensor-returning fast path.
@@ -51,6 +54,8 @@ class VectorIndex:
         self.nprobe = config.get("vector_store.nprobe", 10)                                 # :21
         self.m = config.get("vector_store.pq_m", 8)                                         # :22
         self.storage = config.get("b200.storage", "fp32")
+        self.ivf_mode = config.get("b200.ivf", "exact")                                     # 'exact' | 'lists'
+        self.ivf_niter = config.get("b200.ivf_niter", 25)                                   # faiss ClusteringParameters.niter
         self.index: Optional[engine.DenseIndex] = None
         self.is_trained = False
         self.total_vectors = 0
@@ -103,6 +108,8 @@ class VectorIndex:
                     if not self.create_index(self.index_type):
                         self.nlist = old_nlist
                         return False
+            if self._ivf_lists():
+                self.index.train(self._as_rows(training_vectors), self.nlist, niter=self.ivf_niter)   # index.train (:158)
             self.is_trained = True      # exact search: nothing to learn
             logger.info("Index training completed")
             return True
@@ -134,6 +141,24 @@ class VectorIndex:
             logger.error(f"Failed to add vectors to index: {e}")
             return False
 
+    def _ivf_lists(self) -> bool:
+        return self.ivf_mode == "lists" and self.index_type == "IVFFlat"
+
+    def set_centroids(self, centroids) -> bool:
+        """Addition (BASELINE cfg5): install given coarse centroids, e.g. the topic-cluster means of
+        doc/clustering.py:194, instead of training; cosine metric -> they are L2-normalised first."""
+        if self.index is None:
+            logger.error("Index not created yet")
+            return False
+        try:
+            self.index.set_centroids(self._preprocess_vectors(np.asarray(centroids)))
+            self.nlist = self.index.nlist
+            self.is_trained = True
+            return True
+        except Exception as e:
+            logger.error(f"Failed to set centroids: {e}")
+            return False
+
     @staticmethod
     def _as_rows(vectors):
         """fp32 cast + contiguity of _preprocess_vectors (:268-273); the L2
@@ -152,6 +177,8 @@ class VectorIndex:
     # ------------------------------------------------------------------ search
     def search_tensors(self, query_vectors, top_k: int = 10):
         """(scores fp32 [nq,k], ids int64 [nq,k]); numpy in -> numpy out, CUDA in -> CUDA out."""
+        if self._ivf_lists() and self.index.nlist > 0:
+            return self.index.ivf_search(self._as_rows(query_vectors), top_k, self.nprobe)   # index.nprobe (:91)
         return self.index.search(self._as_rows(query_vectors), top_k)
 
     def search(self, query_vectors, top_k: int = 10, return_vectors: bool = False) -> List[Dict[str, Any]]:
@@ -209,8 +236,11 @@ class VectorIndex:
             filepath = os.path.join(self.index_dir, filename)
             rows = self.index.reconstruct(0, self.index.ntotal) if self.index.ntotal else \
                 np.zeros((0, self.embedding_dim), np.float32)
+            extra = {}
+            if self.index.nlist > 0:
+                extra["centroids"] = self.index.ivf_export()[0]
             with open(filepath, "wb") as f:
-                np.savez(f, rows=rows, storage=np.array(self.storage))
+                np.savez(f, rows=rows, storage=np.array(self.storage), **extra)
             metadata = {                                                                    # :303-311
                 "index_type": self.index_type, "embedding_dim": self.embedding_dim,
                 "similarity_metric": self.similarity_metric, "total_vectors": self.total_vectors,
@@ -242,10 +272,13 @@ class VectorIndex:
             with np.load(filepath, allow_pickle=False) as z:
                 rows = z["rows"]
                 self.storage = str(z["storage"])
+                centroids = z["centroids"] if "centroids" in z.files else None
             if self.index is not None:
                 self.index.close()
             # stored rows are already normalised; normalising again on add is idempotent to 1 ulp
             self.index = engine.DenseIndex(self.embedding_dim, storage=self.storage, normalize=True)
+            if centroids is not None:
+                self.index.set_centroids(centroids)
             if len(rows):
                 self.index.add(rows)
             self.total_vectors = len(rows)
@@ -301,13 +334,23 @@ class VectorIndex:
         if self.index_type not in ("IVFFlat", "IVFPQ"):
             logger.warning("Search parameter optimization only supported for IVF indices")
             return {}
-        # exact search: every nprobe gives the same (full) recall; keep the reference's sweep shape (:437-470)
-        results = self.search(query_vectors, top_k=len(ground_truth_indices[0]))
-        if results and isinstance(results[0], dict):
-            results = [results]
-        recall = self._calculate_recall(results, ground_truth_indices)
-        best = {"nprobe": 1 if 1 <= self.nlist else self.nprobe, "recall": recall}
-        self.nprobe = best["nprobe"]
+        best = {"nprobe": self.nprobe, "recall": 0.0}                                       # :434
+        for nprobe in [1, 5, 10, 20, 50, 100]:                                              # :437-462
+            if nprobe > self.nlist:
+                break
+            original = self.nprobe
+            self.nprobe = nprobe
+            results = self.search(query_vectors, top_k=len(ground_truth_indices[0]))
+            if results and isinstance(results[0], dict):
+                results = [results]
+            recall = self._calculate_recall(results, ground_truth_indices)
+            logger.info(f"nprobe={nprobe}, recall={recall:.3f}")
+            if recall > best["recall"]:
+                best = {"nprobe": nprobe, "recall": recall}
+            if recall >= target_recall:
+                break
+            self.nprobe = original
+        self.nprobe = best["nprobe"]                                                        # :465-466
         logger.info(f"Optimized search params: nprobe={best['nprobe']}, recall={best['recall']:.3f}")
         return best
 

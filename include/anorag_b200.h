@@ -121,6 +121,29 @@ ARB_API int arb_index_search(const arb_index* index, const void* queries, int dt
                      float* out_scores, int64_t* out_ids, int out_is_device, void* stream);
 
 /* ------------------------------------------------------------------------- *
+ * IVF: faiss.IndexIVFFlat(IndexFlatIP(d), d, nlist, METRIC_INNER_PRODUCT) behind VectorIndex
+ * (vector_index.py:85-91 create, :126-169 train_index, :187-193 add_with_ids, :223 search with
+ * index.nprobe).  An index becomes an IVF index once it has centroids; rows added before or after
+ * are quantised to the centroid of largest inner product (IndexFlatIP quantiser), ids stay the add
+ * order.  The flat search (arb_index_search) keeps working on the same handle.
+ * ------------------------------------------------------------------------- */
+/* install `nlist` centroids [nlist, dim] fp32 as given (e.g. topic-cluster means, doc/clustering.py:194) */
+ARB_API int arb_index_ivf_set_centroids(arb_index* index, int nlist, const float* centroids,
+                                int centroids_is_device, void* stream);
+/* index.train(x) (:158): k-means on the device -- seeds = evenly spaced training rows, `niter` Lloyd
+ * iterations (faiss default 25), `spherical` != 0 re-normalises the centroids (faiss does for IP). */
+ARB_API int arb_index_ivf_train(arb_index* index, int nlist, const void* rows, int dtype, int64_t n,
+                        int rows_is_device, int niter, int spherical, void* stream);
+ARB_API int arb_index_ivf_nlist(const arb_index* index);                /* 0 = not trained */
+/* centroids [nlist, dim] fp32 and/or the list of every stored row int32 [ntotal] (either may be NULL); host */
+ARB_API int arb_index_ivf_export(const arb_index* index, float* centroids_out, int32_t* assign_out, void* stream);
+/* search the `nprobe` lists of largest centroid inner product; same outputs as arb_index_search
+ * (rows outside the probed lists are not seen: slots stay -1 / -3.4028235e38 when fewer than k). */
+ARB_API int arb_index_ivf_search(arb_index* index, const void* queries, int dtype, int64_t nq,
+                         int queries_is_device, int k, int nprobe, int query_planes, int64_t id_base,
+                         float* out_scores, int64_t* out_ids, int out_is_device, void* stream);
+
+/* ------------------------------------------------------------------------- *
  * BM25 (replaces corpus.get_scores at utils/bm25_search.py:309 /
  * SimpleBM25.get_scores :43-63, and the max-normalisation :329-333).
  *

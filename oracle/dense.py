@@ -196,3 +196,45 @@ def compare_topk(ids_a, sc_a, ids_b, sc_b, tol: float = 1e-5):
             if abs(s - kth_a) > tol:
                 ok = False
     return ok, n_match, int(ids_a.size), worst
+
+
+# --------------------------------------------------------------------------------------
+# IVF (PARITY UNPINNED: faiss.IndexIVFFlat is external and absent, see the module header)
+# --------------------------------------------------------------------------------------
+def ivf_assign(x: np.ndarray, centroids: np.ndarray) -> np.ndarray:
+    """Coarse quantiser of ``faiss.IndexIVFFlat(IndexFlatIP(d), d, nlist, METRIC_INNER_PRODUCT)``
+    (created at vector_store/vector_index.py:85-91): a row goes to the list whose centroid has the
+    largest inner product with it (lowest list id on exact ties)."""
+    x = np.ascontiguousarray(x, dtype=np.float32)
+    c = np.ascontiguousarray(centroids, dtype=np.float32)
+    out = np.empty(len(x), dtype=np.int32)
+    for lo in range(0, len(x), 65536):
+        out[lo:lo + 65536] = np.argmax(x[lo:lo + 65536] @ c.T, axis=1)
+    return out
+
+
+def ivf_search(q: np.ndarray, x: np.ndarray, centroids: np.ndarray, assign: np.ndarray, k: int, nprobe: int):
+    """``index.search(q, k)`` of an IndexIVFFlat with ``index.nprobe = nprobe`` (vector_index.py:91,:223):
+    the ``nprobe`` lists of largest centroid inner product are scanned exhaustively, exact fp32 inner
+    products, k best in descending order (ascending id on ties), ``-1`` / lowest float when the probed
+    lists hold fewer than k rows.  Returns (scores [nq,k], ids [nq,k], probed lists [nq,nprobe])."""
+    q = np.ascontiguousarray(q, dtype=np.float32)
+    x = np.ascontiguousarray(x, dtype=np.float32)
+    c = np.ascontiguousarray(centroids, dtype=np.float32)
+    nprobe = min(nprobe, len(c))
+    _, probes = topk_desc(q @ c.T, nprobe)
+    order = np.argsort(assign, kind="stable")
+    starts = np.searchsorted(assign[order], np.arange(len(c) + 1))
+    scores = np.full((len(q), k), LOWEST_F32, dtype=np.float32)
+    ids = np.full((len(q), k), -1, dtype=np.int64)
+    for r in range(len(q)):
+        rows = np.concatenate([order[starts[l]:starts[l + 1]] for l in probes[r]]) if nprobe else np.zeros(0, np.int64)
+        if len(rows) == 0:
+            continue
+        rows = np.sort(rows)
+        s = x[rows] @ q[r]
+        ss, ii = topk_desc(s[None, :], min(k, len(rows)))
+        n = ss.shape[1]
+        scores[r, :n] = ss[0]
+        ids[r, :n] = rows[ii[0]]
+    return scores, ids, probes
