@@ -509,7 +509,11 @@ bm25_plane_pass_kernel(const Bm25Dev ix, int64_t nq, int64_t q_per_group, const 
   const uint8_t* bm_bytes = reinterpret_cast<const uint8_t*>(sc.bitmap);
   ulonglong2* qrec = reinterpret_cast<ulonglong2*>(pl_smem + static_cast<size_t>(P) * PLANE_TILE);   // [q_per_group]
   for (int64_t q = q0 + threadIdx.x; q < q1; q += PL_WARPS * 32)
-    qrec[q - q0] = make_ulonglong2(__ldg(sc.thr + q), __ldg(qd64 + q * qw));
+  {
+    const unsigned long long t = __ldg(sc.thr + q);
+    qrec[q - q0] = t == THR_SKIP ? make_ulonglong2(0ull, ~0ull)
+                                 : make_ulonglong2(static_cast<unsigned long long>(__double_as_longlong(key_f64(t))), __ldg(qd64 + q * qw));
+  }
   for (int64_t tile = blockIdx.x; tile < ix.n_tiles; tile += gridDim.x) {
     __syncthreads();
     {
@@ -535,39 +539,38 @@ bm25_plane_pass_kernel(const Bm25Dev ix, int64_t nq, int64_t q_per_group, const 
       if (q + PL_WARPS < q1) mb_nn = __ldg(bm_tile + (q + PL_WARPS) * 32);
     }
     for (int64_t q = q0 + warp; q < q1; q += PL_WARPS) {
-      const ulonglong2 rec = qrec[q - q0];
-      const unsigned long long thr = rec.x;
+      const ulonglong2 rec = qrec[q - q0];                   // {k-th score of A as fp64 bits, packed plane slots}
       unsigned long long pk = rec.y;
       const uint32_t mb = mb_n;
       mb_n = mb_nn;
       if (q + 2 * PL_WARPS < q1) mb_nn = __ldg(bm_tile + (q + 2 * PL_WARPS) * 32);
-      if (thr == THR_SKIP) continue;
+      uint32_t ps = static_cast<uint32_t>(pk) & 0xFFu;
+      if (ps == 0xFFu) continue;                             // skipped query (no plane tokens / fallback)
+      // first plane token: 0.0 + x == x (plane values are never -0.0), so the accumulators start as its row
       double acc[8];
+      {
+        const double2* row = reinterpret_cast<const double2*>(pl_smem + ps * PLANE_TILE) + lane;
 #pragma unroll
-      for (int r = 0; r < 8; ++r) acc[r] = 0.0;
-      for (int w = 0; w < qw; ++w) {
-        if (w) pk = __ldg(qd64 + q * qw + w);
-        uint32_t ps = static_cast<uint32_t>(pk) & 0xFFu;
-#pragma unroll 1
-        for (int i = 0; i < 8 && ps != 0xFFu; ++i) {
-          const double2* row = reinterpret_cast<const double2*>(pl_smem + ps * PLANE_TILE) + lane;
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const double2 v = row[j * 32];
-            acc[2 * j] = __dadd_rn(acc[2 * j], v.x);
-            acc[2 * j + 1] = __dadd_rn(acc[2 * j + 1], v.y);
-          }
-          pk >>= 8;
-          ps = static_cast<uint32_t>(pk) & 0xFFu;
-        }
-        if (ps == 0xFFu) break;
+        for (int j = 0; j < 4; ++j) { const double2 v = row[j * 32]; acc[2 * j] = v.x; acc[2 * j + 1] = v.y; }
       }
-      // docs that reach A's k-th score (a positive fp64, so the comparison of doubles is the comparison of
-      // keys) and are not members of the sparse pass
-      const double thr_d = key_f64(thr);
+      for (int i = 1; i < sc.qd_stride; ++i) {
+        if ((i & 7) == 0) pk = __ldg(qd64 + q * qw + (i >> 3)); else pk >>= 8;
+        ps = static_cast<uint32_t>(pk) & 0xFFu;
+        if (ps == 0xFFu) break;
+        const double2* row = reinterpret_cast<const double2*>(pl_smem + ps * PLANE_TILE) + lane;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const double2 v = row[j * 32];
+          acc[2 * j] = __dadd_rn(acc[2 * j], v.x);
+          acc[2 * j + 1] = __dadd_rn(acc[2 * j + 1], v.y);
+        }
+      }
+      // docs that reach A's k-th score (a positive fp64, so comparing doubles is comparing keys) and are not
+      // members of the sparse pass
+      const double thr_d = __longlong_as_double(static_cast<long long>(rec.x));
       uint32_t pass = 0u;
 #pragma unroll
-      for (int r = 0; r < 8; ++r) pass |= (acc[r] >= thr_d ? 1u : 0u) << r;
+      for (int r = 0; r < 8; ++r) if (acc[r] >= thr_d) pass |= 1u << r;
       pass &= ~mb;
       if (__ballot_sync(0xffffffffu, pass != 0u) == 0u) continue;
 #pragma unroll

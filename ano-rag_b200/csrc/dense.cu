@@ -938,7 +938,7 @@ __global__ void ivf_pick_rows_kernel(const __nv_bfloat16* __restrict__ rows, int
 // rows in storage layout -> nearest centroid (max inner product), written to assign_out[0..n)
 static int ivf_quantise(const arb_index* ix, const __nv_bfloat16* rows_storage, int64_t n, int32_t* assign_out, cudaStream_t st) {
   AsyncBuf sc, id;
-  const int64_t chunk = int64_t(1) << 22;
+  const int64_t chunk = int64_t(1) << 18;             // candidate lists are 4 KB per query row
   ARB_CUDA(sc.alloc(static_cast<size_t>(std::min(n, chunk)) * 4, st));
   ARB_CUDA(id.alloc(static_cast<size_t>(std::min(n, chunk)) * 8, st));
   for (int64_t off = 0; off < n; off += chunk) {
