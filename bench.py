@@ -39,9 +39,12 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--notes", type=int, default=1_000_000)
-    ap.add_argument("--dim", type=int, default=768)
-    ap.add_argument("--queries", type=int, default=4096)
+    ap.add_argument("--workload", default="cfg3", choices=["cfg3", "cfg4"],
+                    help="cfg3 (default, the driver's line): hybrid over 1M notes, row-sharded when N>1 (strong scaling). "
+                         "cfg4: dense only, 12.5M x 1024-d bf16 notes PER GPU, 8192 queries (N=8 is BASELINE configs[3])")
+    ap.add_argument("--notes", type=int, default=None)
+    ap.add_argument("--dim", type=int, default=None)
+    ap.add_argument("--queries", type=int, default=None)
     ap.add_argument("--topk", type=int, default=100)
     ap.add_argument("--vocab", type=int, default=50_000)
     ap.add_argument("--cpu-sample", type=int, default=64, help="queries per CPU-baseline step")
@@ -49,7 +52,26 @@ def parse_args():
     return ap.parse_args()
 
 
+def resolve_workload(a):
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if a.workload == "cfg4":
+        a.notes = a.notes or 12_500_000 * world
+        a.dim = a.dim or 1024
+        a.queries = a.queries or 8192
+    else:
+        a.notes = a.notes or 1_000_000
+        a.dim = a.dim or 768
+        a.queries = a.queries or 4096
+    return a
+
+
 def workload_config(a, n_gpus):
+    if a.workload == "cfg4":
+        return {"workload": f"cfg4 dense: {a.notes} notes x {a.dim}-d bf16 row-sharded over {n_gpus} GPU(s) "
+                            f"({a.notes // n_gpus} rows each), exact IP local top-{a.topk} + all-gather merge, {a.queries}-query batch",
+                "notes": a.notes, "dim": a.dim, "queries": a.queries, "top_k": a.topk,
+                "sharding": f"rows/{n_gpus}" if n_gpus > 1 else "none",
+                "l2": "inputs larger than L2 (corpus shard 25.6 GB bf16 vs 126 MB L2)"}
     return {
         "workload": f"cfg3 hybrid: {a.notes} notes x {a.dim}-d bf16 flat-IP top-{a.topk} + BM25 (Zipf vocab {a.vocab}, "
                     f"~40 tok/doc, okapi fp64) + RRF k=60 -> fused top-{a.topk}, {a.queries}-query batch",
@@ -221,21 +243,25 @@ def run_b200(a):
     for _, rows in synth.dense_rows(row0, row1 - row0, a.dim, dev):
         dense.add(rows)
     q_emb = synth.dense_queries(a.queries, a.dim, dev, n_rows=a.notes)              # bf16, resident
-    doc_ptr, doc_tok = synth.bm25_corpus(a.notes, a.vocab)
-    q_terms_h = synth.bm25_queries(a.queries, doc_ptr, doc_tok, a.vocab)
-    full = bb.build_arrays(doc_ptr, doc_tok, a.vocab, variant="okapi")
-    if world > 1:
-        sptr = doc_ptr[row0:row1 + 1] - doc_ptr[row0]
-        arr = bb.build_arrays(sptr, doc_tok[doc_ptr[row0]:doc_ptr[row1]], a.vocab, stats=full.stats)
-    else:
-        arr = full
-    bm25 = engine.BM25Index(row1 - row0, arr.term_ptr, arr.post_doc, arr.post_gcode, arr.stats.idf, arr.gtab)
+    hybrid = a.workload == "cfg3"
+    bm25 = None
+    q_terms_h = None
+    if hybrid:
+        doc_ptr, doc_tok = synth.bm25_corpus(a.notes, a.vocab)
+        q_terms_h = synth.bm25_queries(a.queries, doc_ptr, doc_tok, a.vocab)
+        full = bb.build_arrays(doc_ptr, doc_tok, a.vocab, variant="okapi")
+        if world > 1:
+            sptr = doc_ptr[row0:row1 + 1] - doc_ptr[row0]
+            arr = bb.build_arrays(sptr, doc_tok[doc_ptr[row0]:doc_ptr[row1]], a.vocab, stats=full.stats)
+        else:
+            arr = full
+        bm25 = engine.BM25Index(row1 - row0, arr.term_ptr, arr.post_doc, arr.post_gcode, arr.stats.idf, arr.gtab)
     searcher = HybridSearcher({"retrieval": {"candidate_pool": a.topk, "hybrid": {
         "fusion_method": "rrf", "rrf_k": 60, "weights": {"dense": 1.0, "bm25": 1.0}}}})
     pipe = HybridPipeline(dense, bm25, searcher, k_dense=a.topk, k_bm25=a.topk, pool=a.topk, id_base=row0,
                           query_planes=1, device=dev)
-    q_terms = torch.from_numpy(q_terms_h).to(dev)
-    local_postings = bm25.query_postings(q_terms_h)
+    q_terms = torch.from_numpy(q_terms_h).to(dev) if hybrid else None
+    local_postings = bm25.query_postings(q_terms_h) if hybrid else 0
 
     def barrier():
         if world > 1:
@@ -274,7 +300,7 @@ def run_b200(a):
 
     # ---- end to end: pinned host inputs, host outputs
     q_emb_h = q_emb.to(torch.float32).cpu().pin_memory()                              # encoder output is fp32 on the host
-    q_terms_p = torch.from_numpy(q_terms_h).pin_memory()
+    q_terms_p = torch.from_numpy(q_terms_h).pin_memory() if hybrid else None
     for _ in range(3):
         pipe.search_host(q_emb_h, q_terms_p)
     barrier()
@@ -286,7 +312,7 @@ def run_b200(a):
     barrier()
     e2e_ms = max_over_ranks(e0.elapsed_time(e1)) / a.steps
     lo, hi = pipe.query_slice(a.queries)
-    h2d = q_emb_h.numel() * 4 + q_terms_p.numel() * 4
+    h2d = q_emb_h.numel() * 4 + (q_terms_p.numel() * 4 if hybrid else 0)
     d2h = sum(int(r.nbytes) for r in res)
     e2e = {"value": a.queries / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
            "ms_per_step": e2e_ms}
@@ -328,7 +354,7 @@ def run_b200(a):
 
     # ---- CPU baseline beside it (rank 0, N=1, bounded sample)
     cpu_baseline = None
-    if rank == 0 and world == 1 and not a.no_cpu_baseline:
+    if rank == 0 and world == 1 and not a.no_cpu_baseline and hybrid:
         xs = np.concatenate([r.to(torch.float32).cpu().numpy() for _, r in synth.dense_rows(0, a.notes, a.dim, dev)])
         cpu = CpuPath(a, xs, q_emb.to(torch.float32).cpu().numpy(), doc_ptr, doc_tok, q_terms_h)
         n = min(a.cpu_sample, a.queries)
@@ -348,8 +374,8 @@ def run_b200(a):
         cpu_baseline["fused_top100_agreement_with_oracle"] = agree / max(1, min(n, hi - lo))
 
     if rank == 0:
-        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": n_gpus, "steps": a.steps, "warmup": max(3, a.warmup),
-                "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        line = {"metric": METRIC if hybrid else "dense_queries_per_sec_top100", "value": value, "unit": UNIT, "n_gpus": n_gpus, "steps": a.steps, "warmup": max(3, a.warmup),
+                "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong" if hybrid else "weak", "vs_baseline": None,
                 "dtype": "bf16", "data": "synthetic", "config": workload_config(a, n_gpus), "e2e": e2e,
                 "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "stages": stages,
                 "cpu_baseline": cpu_baseline, "impl": "b200",
@@ -361,7 +387,7 @@ def run_b200(a):
 
 
 def main():
-    a = parse_args()
+    a = resolve_workload(parse_args())
     if a.impl == "reference":
         return run_reference(a)
     return run_b200(a)
