@@ -232,6 +232,10 @@ def run_b200(a):
         raise SystemExit("bench.py: no CUDA device -- the B200 arm has no CPU fallback")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    # stdout carries exactly one JSON line: anything libraries print meanwhile (NCCL's version banner ...) goes to stderr
+    sys.stdout.flush()
+    saved_stdout = os.dup(1)
+    os.dup2(2, 1)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     n_gpus = world
@@ -380,6 +384,8 @@ def run_b200(a):
                 "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "stages": stages,
                 "cpu_baseline": cpu_baseline, "impl": "b200",
                 "dtype_note": "dense: bf16 operands, fp32 accumulate on tcgen05; BM25 and fusion: fp64"}
+        sys.stdout.flush()
+        os.dup2(saved_stdout, 1)
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
