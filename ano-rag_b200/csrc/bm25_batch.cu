@@ -173,8 +173,10 @@ bm25_sparse_pass_kernel(const Bm25Dev ix, const int32_t* __restrict__ q_terms_al
     if (lane == 0) ui = atomicAdd(&sc.counters[0], 1);
     const int64_t unit = __shfl_sync(0xffffffffu, ui, 0);
     if (unit >= nq * sc.parts) break;
-    const int64_t q = unit / sc.parts;
-    const int part = static_cast<int>(unit - q * sc.parts);
+    // part-major order: the warps in flight work on the same doc range of different queries, so the term planes
+    // of that range (n_planes * 8 B per doc) stay in L2 for the scattered member look-ups
+    const int part = static_cast<int>(unit / nq);
+    const int64_t q = unit - static_cast<int64_t>(part) * nq;
 
     // one query token per lane: kind 1 = plane term, 2 = sparse term with per-512-doc offsets,
     // 3 = sparse term with per-16K-block offsets only, 0 = contributes nothing
