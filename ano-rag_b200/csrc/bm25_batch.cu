@@ -450,31 +450,39 @@ bm25_a_merge_kernel(int64_t nq, int k, const BatchScratch sc) {
   extern __shared__ __align__(16) uint8_t am_smem[];
   const int64_t q = blockIdx.x;
   const int tid = threadIdx.x;
-  __shared__ int s_off[33];
-  __shared__ int s_ovf;
+  __shared__ int s_n, s_ovf, s_total;
+  __shared__ unsigned long long s_floor;
   if (tid == 0) {
-    int o = 0, ovf = 0;
+    // Every part list is sorted; a full part's k-th key is a lower bound of the merged k-th key, so only
+    // entries at or above the largest such bound can be in the merged top-k.
+    int ovf = 0, total = 0;
+    unsigned long long fl = 0ull;
     for (int p = 0; p < sc.parts; ++p) {
-      s_off[p] = o;
       const int c = sc.pa_cnt[q * sc.parts + p];
-      if (c < 0) ovf = 1; else o += c;
+      if (c < 0) { ovf = 1; continue; }
+      total += c;
+      if (c >= k) fl = max(fl, sc.pa_key[(q * sc.parts + p) * k + k - 1]);
     }
-    s_off[sc.parts] = o;
-    s_ovf = ovf;
+    s_n = 0; s_ovf = ovf; s_floor = fl; s_total = total;
   }
   __syncthreads();
-  const int n = s_off[sc.parts];
+  const unsigned long long fl = s_floor;
+  unsigned long long* key = reinterpret_cast<unsigned long long*>(am_smem);
+  int n2max = 2;                                               // the launch reserves 12 B x this many slots
+  while (n2max < sc.parts * k) n2max <<= 1;
+  uint32_t* doc = reinterpret_cast<uint32_t*>(am_smem + static_cast<size_t>(n2max) * 8);
+  for (int i = tid; i < sc.parts * k; i += blockDim.x) {
+    const int p = i / k, j = i - p * k;
+    if (j < sc.pa_cnt[q * sc.parts + p]) {
+      const unsigned long long kk = sc.pa_key[(q * sc.parts + p) * k + j];
+      if (kk >= fl) { const int pos = atomicAdd(&s_n, 1); key[pos] = kk; doc[pos] = sc.pa_doc[(q * sc.parts + p) * k + j]; }
+    }
+  }
+  __syncthreads();
+  const int n = s_n;
   int n2 = 2;
   while (n2 < n) n2 <<= 1;
-  unsigned long long* key = reinterpret_cast<unsigned long long*>(am_smem);
-  uint32_t* doc = reinterpret_cast<uint32_t*>(am_smem + static_cast<size_t>(n2) * 8);
-  for (int i = tid; i < n2; i += blockDim.x) { key[i] = 0ull; doc[i] = 0xFFFFFFFFu; }
-  __syncthreads();
-  for (int p = 0; p < sc.parts; ++p) {
-    const int c = s_off[p + 1] - s_off[p];
-    const int64_t po = (q * sc.parts + p) * k;
-    for (int i = tid; i < c; i += blockDim.x) { key[s_off[p] + i] = sc.pa_key[po + i]; doc[s_off[p] + i] = sc.pa_doc[po + i]; }
-  }
+  for (int i = n + tid; i < n2; i += blockDim.x) { key[i] = 0ull; doc[i] = 0xFFFFFFFFu; }
   cta_sort_desc(key, doc, n2);
   const int cnt = min(n, k);
   for (int i = tid; i < k; i += blockDim.x) {
