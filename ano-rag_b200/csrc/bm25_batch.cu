@@ -95,6 +95,8 @@ struct BatchScratch {
   unsigned long long* pa_key;  // [nq, parts, k]
   uint32_t* pa_doc;            // [nq, parts, k]
   int* pa_cnt;                 // [nq, parts]  entries, or -1 if the part overflowed its staging areas
+  unsigned long long* gthr;    // [nq] largest k-th key any part of the query has reached so far (0 = none): a doc
+                               // strictly below it cannot be in the query's top-k, whichever part it lies in
   int* counters;               // [0] next query of the sparse pass, [1] number of flagged queries
 };
 
@@ -230,6 +232,7 @@ bm25_sparse_pass_kernel(const Bm25Dev ix, const int32_t* __restrict__ q_terms_al
     const int spb = 1 << (bl2 - SLICE_LOG2);                   // 512-doc slices per block
 
     unsigned long long thr_key = key_zero;                     // only positive scores are candidates
+    unsigned long long floor_key = *reinterpret_cast<volatile unsigned long long*>(sc.gthr + q);   // other parts' bound
     int cnt = 0;
     bool overflow = false;
     // word w of this query's member bitmap lives at bitmap[((w >> 3) * nq + q) * 8 + (w & 7)]
@@ -242,7 +245,10 @@ bm25_sparse_pass_kernel(const Bm25Dev ix, const int32_t* __restrict__ q_terms_al
       while (n2 < cnt) n2 <<= 1;
       for (int i = cnt + lane; i < n2; i += 32) { W.ckey[i] = 0ull; W.cdoc[i] = 0xFFFFFFFFu; }
       warp_sort_desc(W.ckey, W.cdoc, n2, lane);
-      if (cnt >= k) { cnt = k; thr_key = W.ckey[k - 1]; }
+      if (cnt >= k) {
+        cnt = k; thr_key = W.ckey[k - 1];
+        if (lane == 0 && thr_key > floor_key) atomicMax(sc.gthr + q, thr_key);
+      }
       __syncwarp();
     };
     // posting range of this lane's token in block b (kind 3: the enclosing 16K block, fetched once per 16K docs)
@@ -274,6 +280,8 @@ bm25_sparse_pass_kernel(const Bm25Dev ix, const int32_t* __restrict__ q_terms_al
           }
         continue;
       }
+
+      floor_key = max(floor_key, *reinterpret_cast<volatile unsigned long long*>(sc.gthr + q));
 
       // ---- (1) the active tokens are packed into lanes 0..na-1; their postings are staged back to back
       const int na = __popc(ne);
@@ -415,7 +423,7 @@ bm25_sparse_pass_kernel(const Bm25Dev ix, const int32_t* __restrict__ q_terms_al
         uint32_t d = 0u;
         if (valid) { v = W.pool[i]; d = W.mdoc[i]; }
         const unsigned long long key = f64_key(v);
-        const bool pass = valid && key > thr_key;
+        const bool pass = valid && key > thr_key && key >= floor_key;
         const uint32_t pm = __ballot_sync(0xffffffffu, pass);
         if (pass) {
           const int pos = cnt + __popc(pm & lt);
@@ -708,12 +716,15 @@ static int batch_chunk(const Bm25Dev& ix, const int32_t* d_terms, int64_t nq, in
   BatchScratch sc{};
   sc.bm_tiles = static_cast<int64_t>(ix.nb) * (DOC_BLOCK / PLANE_TILE);  // whole 16K-doc blocks
   sc.nq = nq;
-  AsyncBuf b_akey, b_adoc, b_i32, b_thr, b_u8, b_bitmap, b_ekey, b_edoc, b_pakey, b_padoc, b_pacnt;
+  AsyncBuf b_akey, b_adoc, b_i32, b_thr, b_u8, b_bitmap, b_ekey, b_edoc, b_pakey, b_padoc, b_pacnt, b_gthr;
   sc.parts = static_cast<int>(std::min<int64_t>(ix.nb, 16));
   if (const char* v = std::getenv("ARB_BM25_PARTS")) sc.parts = std::max(1, std::min<int>(std::min<int64_t>(ix.nb, 32), atoi(v)));
   ARB_CUDA(b_pakey.alloc(static_cast<size_t>(nq) * sc.parts * k * 8, st));
   ARB_CUDA(b_padoc.alloc(static_cast<size_t>(nq) * sc.parts * k * 4, st));
   ARB_CUDA(b_pacnt.alloc(static_cast<size_t>(nq) * sc.parts * 4, st));
+  ARB_CUDA(b_gthr.alloc(static_cast<size_t>(nq) * 8, st));
+  ARB_CUDA(cudaMemsetAsync(b_gthr.p, 0, static_cast<size_t>(nq) * 8, st));
+  sc.gthr = b_gthr.as<unsigned long long>();
   sc.pa_key = b_pakey.as<unsigned long long>();
   sc.pa_doc = b_padoc.as<uint32_t>();
   sc.pa_cnt = b_pacnt.as<int>();
