@@ -80,6 +80,24 @@ __global__ void bm25_plane_fill_kernel(const int32_t* __restrict__ doc, const in
   planes[((d >> PLANE_TILE_LOG2) * n_planes + slot) * PLANE_TILE + plane_pos(static_cast<uint32_t>(d) & (PLANE_TILE - 1))] = __dmul_rn(idf, gtab[gcode[i]]);
 }
 
+// per-tile and global maxima of every plane (upper bounds the plane pass prunes with); absent docs count as +0.0
+__global__ void bm25_plane_tmax_kernel(const double* __restrict__ planes, int64_t n_tiles, int n_planes,
+                                       double* __restrict__ tmax) {
+  const int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  if (i >= n_tiles * n_planes) return;
+  const double* row = planes + i * PLANE_TILE;
+  double m = 0.0;
+  for (int d = 0; d < PLANE_TILE; ++d) m = fmax(m, row[d]);
+  tmax[i] = m;
+}
+__global__ void bm25_plane_gmax_kernel(const double* __restrict__ tmax, int64_t n_tiles, int n_planes, double* __restrict__ gmax) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= n_planes) return;
+  double m = 0.0;
+  for (int64_t t = 0; t < n_tiles; ++t) m = fmax(m, tmax[t * n_planes + s]);
+  gmax[s] = m;
+}
+
 // ---------------------------------------------------------------- scoring core
 struct Bm25Smem {
   double* acc;                  // [DOC_BLOCK]
@@ -623,6 +641,15 @@ extern "C" int arb_bm25_create(arb_bm25** out, int64_t n_docs, int64_t n_terms, 
             d_doc.as<int32_t>(), d_code.as<int32_t>(), lo, hi, idf[t], bm->gtab, s2, n_planes, bm->planes);
         count_launch();
       }
+      if (e == cudaSuccess && n_planes > 0) {
+        const size_t nt = static_cast<size_t>(n_tiles) * n_planes;
+        if (cudaMalloc(&bm->plane_tmax, (nt + n_planes) * 8) != cudaSuccess) {
+          cudaGetLastError(); set_error("arb_bm25_create: out of device memory (plane maxima)"); return fail(ARB_ENOMEM);
+        }
+        bm25_plane_tmax_kernel<<<static_cast<unsigned>((nt + 255) / 256), 256, 0, st>>>(bm->planes, n_tiles, n_planes, bm->plane_tmax);
+        bm25_plane_gmax_kernel<<<(n_planes + 127) / 128, 128, 0, st>>>(bm->plane_tmax, n_tiles, n_planes, bm->plane_tmax + nt);
+        count_launch(2);
+      }
       if (e == cudaSuccess) e = cudaStreamSynchronize(st);       // pslot dies at scope end
       if (e != cudaSuccess) return fail(cuda_fail(e, "bm25 term planes", __FILE__, __LINE__));
       bm->dev.n_planes = n_planes;
@@ -639,6 +666,8 @@ extern "C" int arb_bm25_create(arb_bm25** out, int64_t n_docs, int64_t n_terms, 
   bm->dev.blk_off = bm->blk_off; bm->dev.post = bm->post; bm->dev.idf = bm->idf; bm->dev.gtab = bm->gtab;
   bm->dev.dense_slot = bm->dense_slot; bm->dev.fine_off = bm->fine_off;
   bm->dev.plane_slot = bm->plane_slot; bm->dev.planes = bm->planes;
+  bm->dev.plane_tmax = bm->plane_tmax;
+  bm->dev.plane_gmax = bm->plane_tmax ? bm->plane_tmax + static_cast<size_t>(bm->dev.n_tiles) * bm->dev.n_planes : nullptr;
   *out = bm;
   return ARB_OK;
 }
@@ -653,6 +682,7 @@ extern "C" int arb_bm25_destroy(arb_bm25* bm) {
   if (bm->fine_off) cudaFree(bm->fine_off);
   if (bm->plane_slot) cudaFree(bm->plane_slot);
   if (bm->planes) cudaFree(bm->planes);
+  if (bm->plane_tmax) cudaFree(bm->plane_tmax);
   delete bm;
   return ARB_OK;
 }

@@ -46,6 +46,8 @@ struct Bm25Dev {
   int n_planes;                 // terms stored as doc-major planes (<= MAX_PLANES)
   const int* plane_slot;        // [n_terms] plane index or -1
   const double* planes;         // [n_tiles * n_planes * 256]
+  const double* plane_tmax;     // [n_tiles * n_planes] largest value of each plane inside each tile (>= +0.0)
+  const double* plane_gmax;     // [n_planes] largest value of each plane
   int64_t n_tiles;              // 256-doc tiles
 };
 
@@ -74,5 +76,6 @@ struct arb_bm25 {
   uint32_t* fine_off = nullptr;
   int* plane_slot = nullptr;
   double* planes = nullptr;
+  double* plane_tmax = nullptr;   // followed by plane_gmax
   std::vector<int64_t> df;      // host copy of per-term df (roofline accounting)
 };

@@ -525,12 +525,25 @@ bm25_plane_pass_kernel(const Bm25Dev ix, int64_t nq, int64_t q_per_group, const 
   const int qw = sc.qd_stride >> 3;                            // 8-byte words of packed plane slots per query
   const unsigned long long* qd64 = reinterpret_cast<const unsigned long long*>(sc.qd);
   const uint8_t* bm_bytes = reinterpret_cast<const uint8_t*>(sc.bitmap);
-  ulonglong2* qrec = reinterpret_cast<ulonglong2*>(pl_smem + static_cast<size_t>(P) * PLANE_TILE);   // [q_per_group]
-  for (int64_t q = q0 + threadIdx.x; q < q1; q += PL_WARPS * 32)
-  {
+  double* tmax_s = pl_smem + static_cast<size_t>(P) * PLANE_TILE;                                    // [P] this tile's plane maxima
+  ulonglong2* qrec = reinterpret_cast<ulonglong2*>(tmax_s + ((P + 1) & ~1));                         // [q_per_group]
+  // Upper bounds: fp64 addition is monotone, so adding the plane maxima in the query's token order bounds the
+  // in-order score of every doc that matches plane tokens only.  A query whose bound over the whole corpus is
+  // below its threshold needs no plane pass at all; the per-tile bound prunes most (query, tile) pairs of the rest.
+  for (int64_t q = q0 + threadIdx.x; q < q1; q += PL_WARPS * 32) {
     const unsigned long long t = __ldg(sc.thr + q);
-    qrec[q - q0] = t == THR_SKIP ? make_ulonglong2(0ull, ~0ull)
-                                 : make_ulonglong2(static_cast<unsigned long long>(__double_as_longlong(key_f64(t))), __ldg(qd64 + q * qw));
+    ulonglong2 rec = make_ulonglong2(0ull, ~0ull);
+    if (t != THR_SKIP) {
+      const double thr_d = key_f64(t);
+      double ub = 0.0;
+      for (int i = 0; i < sc.qd_stride; ++i) {
+        const uint32_t ps = sc.qd[q * sc.qd_stride + i];
+        if (ps == 0xFFu) break;
+        ub = __dadd_rn(ub, __ldg(ix.plane_gmax + ps));
+      }
+      if (ub >= thr_d) rec = make_ulonglong2(static_cast<unsigned long long>(__double_as_longlong(thr_d)), __ldg(qd64 + q * qw));
+    }
+    qrec[q - q0] = rec;
   }
   for (int64_t tile = blockIdx.x; tile < ix.n_tiles; tile += gridDim.x) {
     __syncthreads();
@@ -545,6 +558,7 @@ bm25_plane_pass_kernel(const Bm25Dev ix, int64_t nq, int64_t q_per_group, const 
 #pragma unroll
         for (int r = 0; r < 4; ++r) { const int i = i0 + r * PL_WARPS * 32; if (i < n16) dst[i] = v[r]; }
       }
+      if (threadIdx.x < P) tmax_s[threadIdx.x] = __ldg(ix.plane_tmax + tile * P + threadIdx.x);
     }
     __syncthreads();
     // Per-query inputs: {threshold, packed plane slots} come from shared memory (staged once per CTA), the
@@ -563,7 +577,20 @@ bm25_plane_pass_kernel(const Bm25Dev ix, int64_t nq, int64_t q_per_group, const 
       mb_n = mb_nn;
       if (q + 2 * PL_WARPS < q1) mb_nn = __ldg(bm_tile + (q + 2 * PL_WARPS) * 32);
       uint32_t ps = static_cast<uint32_t>(pk) & 0xFFu;
-      if (ps == 0xFFu) continue;                             // skipped query (no plane tokens / fallback)
+      if (ps == 0xFFu) continue;                             // skipped query (no plane tokens / fallback / bounded out)
+      const double thr_d = __longlong_as_double(static_cast<long long>(rec.x));
+      {
+        // this tile's bound for the query (same token order); all lanes read the same shared-memory words
+        double ub = tmax_s[ps];
+        unsigned long long pb = pk;
+        for (int i = 1; i < sc.qd_stride; ++i) {
+          if ((i & 7) == 0) pb = __ldg(qd64 + q * qw + (i >> 3)); else pb >>= 8;
+          const uint32_t s2 = static_cast<uint32_t>(pb) & 0xFFu;
+          if (s2 == 0xFFu) break;
+          ub = __dadd_rn(ub, tmax_s[s2]);
+        }
+        if (ub < thr_d) continue;
+      }
       // first plane token: 0.0 + x == x (plane values are never -0.0), so the accumulators start as its row
       double acc[8];
       {
@@ -585,7 +612,6 @@ bm25_plane_pass_kernel(const Bm25Dev ix, int64_t nq, int64_t q_per_group, const 
       }
       // docs that reach A's k-th score (a positive fp64, so comparing doubles is comparing keys) and are not
       // members of the sparse pass
-      const double thr_d = __longlong_as_double(static_cast<long long>(rec.x));
       uint32_t pass = 0u;
 #pragma unroll
       for (int r = 0; r < 8; ++r) if (acc[r] >= thr_d) pass |= 1u << r;
@@ -717,7 +743,7 @@ static int batch_chunk(const Bm25Dev& ix, const int32_t* d_terms, int64_t nq, in
   sc.bm_tiles = static_cast<int64_t>(ix.nb) * (DOC_BLOCK / PLANE_TILE);  // whole 16K-doc blocks
   sc.nq = nq;
   AsyncBuf b_akey, b_adoc, b_i32, b_thr, b_u8, b_bitmap, b_ekey, b_edoc, b_pakey, b_padoc, b_pacnt, b_gthr;
-  sc.parts = static_cast<int>(std::min<int64_t>(ix.nb, 16));
+  sc.parts = static_cast<int>(std::min<int64_t>(ix.nb, 24));
   if (const char* v = std::getenv("ARB_BM25_PARTS")) sc.parts = std::max(1, std::min<int>(std::min<int64_t>(ix.nb, 32), atoi(v)));
   ARB_CUDA(b_pakey.alloc(static_cast<size_t>(nq) * sc.parts * k * 8, st));
   ARB_CUDA(b_padoc.alloc(static_cast<size_t>(nq) * sc.parts * k * 4, st));
@@ -775,13 +801,14 @@ static int batch_chunk(const Bm25Dev& ix, const int32_t* d_terms, int64_t nq, in
     // enough CTAs to fill the GPU: tile sets first, query groups when the corpus has few tiles
     const int64_t sets = std::min<int64_t>(ix.n_tiles, sms);
     const size_t plane_smem = static_cast<size_t>(ix.n_planes) * PLANE_TILE * 8;
-    const int64_t max_qpg = static_cast<int64_t>((PL_SMEM_MAX - plane_smem) / 16);   // {thr, slots} records per CTA
+    const size_t tmax_smem = static_cast<size_t>((ix.n_planes + 1) & ~1) * 8;
+    const int64_t max_qpg = static_cast<int64_t>((PL_SMEM_MAX - plane_smem - tmax_smem) / 16);   // {thr, slots} records per CTA
     int64_t groups = std::max<int64_t>(1, std::min<int64_t>(sms / sets, (nq + 4 * PL_WARPS - 1) / (4 * PL_WARPS)));
     groups = std::max<int64_t>(groups, (nq + max_qpg - 1) / max_qpg);
     const int64_t qpg = (nq + groups - 1) / groups;
     groups = (nq + qpg - 1) / qpg;
     dim3 grid(static_cast<unsigned>(sets), static_cast<unsigned>(groups));
-    bm25_plane_pass_kernel<<<grid, PL_WARPS * 32, plane_smem + static_cast<size_t>(qpg) * 16, st>>>(ix, nq, qpg, sc);
+    bm25_plane_pass_kernel<<<grid, PL_WARPS * 32, plane_smem + tmax_smem + static_cast<size_t>(qpg) * 16, st>>>(ix, nq, qpg, sc);
     ARB_LAUNCH_OK();
   }
   {
