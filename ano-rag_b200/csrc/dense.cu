@@ -23,6 +23,7 @@
 #include "ptx.cuh"
 
 #include <algorithm>
+#include <cstdlib>
 #include <mutex>
 #include <vector>
 #include <math.h>
@@ -44,6 +45,9 @@ constexpr int ACC_STAGES = 2;
 constexpr int TMEM_COLS = ACC_STAGES * BLOCK_N;   // 512: the whole TMEM of the SM
 constexpr int DENSE_THREADS = 192;                // warp0 TMA, warp1 MMA, warps2-5 epilogue
 constexpr int DENSE_SMEM = STAGES * STAGE_BYTES + 256 + 1024;
+constexpr int PSTAGES = 6;                        // CTA-pair kernel: A 128 x 64 + half of B (128 x 64) per stage
+constexpr int PSTAGE_BYTES = A_BYTES + B_BYTES / 2;
+constexpr int PAIR_SMEM = PSTAGES * PSTAGE_BYTES + 256 + 1024;
 constexpr int MAX_TERMS = 6;
 
 constexpr uint32_t KEY_NEG_INF = 0x007FFFFFu;     // f32_key(-inf)
@@ -269,10 +273,21 @@ dense_topk_kernel(const __grid_constant__ CUtensorMap tmap_a,
           }
           const uint32_t idx0 = n_base + c * 32;
           if (!tail) {
+            // Once the threshold has warmed up almost no score beats it: a max-reduction per group of 8 columns
+            // decides whether that group's compare-and-append code runs at all (the epilogue warps, one per
+            // scheduler, were the bottleneck of the kernel when every column paid for the append path).
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              float s = __uint_as_float(v[j]);
-              if (s > thr) { list[cnt] = make_uint2(idx0 + j, f32_key(s)); ++cnt; }
+            for (int g8 = 0; g8 < 4; ++g8) {
+              float mx = __uint_as_float(v[8 * g8]);
+#pragma unroll
+              for (int j = 1; j < 8; ++j) mx = fmaxf(mx, __uint_as_float(v[8 * g8 + j]));
+              if (mx > thr) {                                // taken by the whole warp if any of its 32 rows passes
+#pragma unroll
+                for (int j = 8 * g8; j < 8 * g8 + 8; ++j) {
+                  float s = __uint_as_float(v[j]);
+                  if (s > thr) { list[cnt] = make_uint2(idx0 + j, f32_key(s)); ++cnt; }
+                }
+              }
             }
           } else {
 #pragma unroll
@@ -308,6 +323,213 @@ dense_topk_kernel(const __grid_constant__ CUtensorMap tmap_a,
     tmem_dealloc(tmem_base, TMEM_COLS);
   }
 }
+
+// CTA-pair variant (cta_group::2): a cluster of two CTAs owns one 256-query x 256-row tile.  Each CTA stages its own
+// 128 query rows and HALF of the corpus tile (128 rows) per k-block, so a stage is 32 KB instead of 48 KB and six
+// stages fit: 1.5x more k-blocks in flight for the same shared memory, and a third less L2 -> SM traffic per flop.
+// The leader CTA's single MMA thread issues tcgen05.mma.cta_group::2 (M = 256); the accumulator rows of each CTA's
+// queries land in that CTA's own TMEM, so the epilogue is the one of the single-CTA kernel.
+template <int EPL>
+__global__ void __launch_bounds__(DENSE_THREADS, 1)
+dense_topk_pair_kernel(const __grid_constant__ CUtensorMap tmap_a,
+                  const __grid_constant__ CUtensorMap tmap_b, const DenseParams p) {
+  constexpr bool IVF = false;
+  constexpr int C = 32 * EPL;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + PSTAGES * PSTAGE_BYTES);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + PSTAGES;
+  uint64_t* tfull = bars + 2 * PSTAGES;
+  uint64_t* tempty = tfull + ACC_STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + ACC_STAGES);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t cta_rank = cluster_ctarank();
+  const bool leader = cta_rank == 0;
+  const int pair = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tmap_a);
+    prefetch_tmap(&tmap_b);
+    for (int s = 0; s < PSTAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    // the leader's "accumulator drained" barrier collects the epilogue warps of BOTH CTAs
+    for (int a = 0; a < ACC_STAGES; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], 8); }
+    fence_barrier_init();
+  }
+  __syncthreads();
+  cluster_sync_all();                              // barriers of both CTAs exist before anything remote happens
+  if (warp == 1) tmem_alloc_2sm(tmem_slot, TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
+
+  const int kb_total = p.n_terms * p.kb_per_term;
+  const int n_items = IVF ? __ldg(p.n_items_ptr) : p.n_items;
+  // work item -> (A tile row, first B row, n-tile range, end of the valid B rows)
+  auto decode = [&](int item, int& a_row0, uint32_t& b_row0, int& t0, int& t1, uint32_t& b_end) {
+    if (IVF) {
+      const IvfItem it = p.items[item];
+      a_row0 = item * BLOCK_M; b_row0 = it.row_lo; b_end = it.row_hi;
+      t0 = 0; t1 = static_cast<int>((it.row_hi - it.row_lo + BLOCK_N - 1) / BLOCK_N);
+    } else {
+      const int n_qt2 = p.n_qtiles >> 1;             // p.n_qtiles is even in pair mode
+      const int qt = 2 * (item % n_qt2) + static_cast<int>(cta_rank), sp = item / n_qt2;
+      a_row0 = qt * BLOCK_M; b_row0 = 0; b_end = p.n_rows;
+      t0 = sp * p.tiles_per_split; t1 = min(t0 + p.tiles_per_split, p.n_ntiles);
+    }
+  };
+
+  if (warp == 0) {
+    // ------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      for (int item = pair; item < n_items; item += n_pairs) {
+        int a_row0, t0, t1; uint32_t b_row0, b_end;
+        decode(item, a_row0, b_row0, t0, t1, b_end);
+        for (int t = t0; t < t1; ++t) {
+          for (int term = 0; term < p.n_terms; ++term) {
+            for (int kb = 0; kb < p.kb_per_term; ++kb) {
+              mbar_wait(&empty[stage], phase ^ 1u);
+              uint8_t* sa = smem + stage * PSTAGE_BYTES;
+              // both CTAs' bytes are accounted on the leader's barrier (its arrival carries the expected total)
+              if (leader) mbar_expect_tx(&full[stage], 2 * PSTAGE_BYTES);
+              tma_load_2d_2sm(&tmap_a, &full[stage], sa, p.a_col[term] + kb * BLOCK_K, a_row0, EVICT_LAST);
+              tma_load_2d_2sm(&tmap_b, &full[stage], sa + A_BYTES, p.b_col[term] + kb * BLOCK_K,
+                              static_cast<int32_t>(b_row0) + t * BLOCK_N + static_cast<int32_t>(cta_rank) * (BLOCK_N / 2),
+                              EVICT_NORMAL);
+              if (++stage == PSTAGES) { stage = 0; phase ^= 1u; }
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------ MMA issuer (leader CTA only)
+    if (lane == 0 && leader) {
+      constexpr uint32_t idesc = umma_idesc_bf16(2 * BLOCK_M, BLOCK_N);
+      int stage = 0; uint32_t phase = 0;
+      int acc = 0; uint32_t acc_phase = 0;
+      for (int item = pair; item < n_items; item += n_pairs) {
+        int a_row0, t0, t1; uint32_t b_row0, b_end;
+        decode(item, a_row0, b_row0, t0, t1, b_end);
+        for (int t = t0; t < t1; ++t) {
+          mbar_wait(&tempty[acc], acc_phase ^ 1u);
+          tc_fence_after();
+          const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
+          for (int kb = 0; kb < kb_total; ++kb) {
+            mbar_wait(&full[stage], phase);
+            tc_fence_after();
+            const uint32_t sa = smem_u32(smem + stage * PSTAGE_BYTES);
+            const uint64_t a_desc = umma_desc_k_sw128(sa);
+            const uint64_t b_desc = umma_desc_k_sw128(sa + A_BYTES);
+#pragma unroll
+            for (int kk = 0; kk < BLOCK_K / UMMA_K; ++kk) {
+              // +32 B per UMMA_K inside the 128 B swizzle row -> +2 in 16 B units
+              umma_bf16_2sm(d_tmem, a_desc + 2 * kk, b_desc + 2 * kk, idesc, (kb | kk) != 0 ? 1u : 0u);
+            }
+            umma_commit_2sm(&empty[stage]);      // frees the slot in both CTAs when these MMAs retire
+            if (++stage == PSTAGES) { stage = 0; phase ^= 1u; }
+          }
+          umma_commit_2sm(&tfull[acc]);          // accumulator complete -> the epilogues of both CTAs
+          if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1u; }
+        }
+      }
+    }
+  } else {
+    // ------------------------------------------------------------ epilogue (4 warps)
+    const int quad = warp & 3;                   // TMEM lane quadrant this warp may read
+    const int row = quad * 32 + lane;            // query row inside the tile
+    int acc = 0; uint32_t acc_phase = 0;
+    for (int item = pair; item < n_items; item += n_pairs) {
+      int a_row0, t0, t1; uint32_t b_row0, b_end;
+      decode(item, a_row0, b_row0, t0, t1, b_end);
+      const int q = IVF ? __ldg(p.row_query + a_row0 + row) : a_row0 + row;
+      const bool valid = q >= 0 && q < p.nq;
+      // candidate-list slot of this CTA's query tile: same numbering as the single-CTA kernel (split-major)
+      const int n_qt2 = p.n_qtiles >> 1;
+      const size_t list_item = static_cast<size_t>(item / n_qt2) * p.n_qtiles + 2 * (item % n_qt2) + cta_rank;
+      uint2* list = p.lists + (list_item * BLOCK_M + row) * C;
+      int cnt = 0;
+      uint32_t thr_key = KEY_NEG_INF;
+      float thr = valid ? -INFINITY : INFINITY;
+      for (int t = t0; t < t1; ++t) {
+        if (valid) {
+          uint32_t g = __ldcg(p.gthr + q);
+          if (g > thr_key) { thr_key = g; thr = key_f32(g); }
+        }
+        mbar_wait(&tfull[acc], acc_phase);
+        tc_fence_after();
+        const uint32_t n_base = b_row0 + static_cast<uint32_t>(t) * BLOCK_N;
+        const bool tail = n_base + BLOCK_N > b_end;
+        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * BLOCK_N;
+#pragma unroll 1
+        for (int c = 0; c < BLOCK_N / 32; ++c) {
+          uint32_t v[32];
+          tmem_ld_32x32(taddr + c * 32, v);
+          tmem_ld_wait();
+          if (c == BLOCK_N / 32 - 1) {
+            // all of this warp's reads of the accumulator are done: hand it back
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(mapa_u32(&tempty[acc], 0));
+          }
+          const uint32_t idx0 = n_base + c * 32;
+          if (!tail) {
+            // Once the threshold has warmed up almost no score beats it: a max-reduction per group of 8 columns
+            // decides whether that group's compare-and-append code runs at all (the epilogue warps, one per
+            // scheduler, were the bottleneck of the kernel when every column paid for the append path).
+#pragma unroll
+            for (int g8 = 0; g8 < 4; ++g8) {
+              float mx = __uint_as_float(v[8 * g8]);
+#pragma unroll
+              for (int j = 1; j < 8; ++j) mx = fmaxf(mx, __uint_as_float(v[8 * g8 + j]));
+              if (mx > thr) {                                // taken by the whole warp if any of its 32 rows passes
+#pragma unroll
+                for (int j = 8 * g8; j < 8 * g8 + 8; ++j) {
+                  float s = __uint_as_float(v[j]);
+                  if (s > thr) { list[cnt] = make_uint2(idx0 + j, f32_key(s)); ++cnt; }
+                }
+              }
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              float s = __uint_as_float(v[j]);
+              if (s > thr && idx0 + j < b_end) { list[cnt] = make_uint2(idx0 + j, f32_key(s)); ++cnt; }
+            }
+          }
+          uint32_t need = __ballot_sync(0xffffffffu, cnt > C - 32);
+          while (need) {
+            const int r = __ffs(need) - 1;
+            need &= need - 1;
+            uint2* l = reinterpret_cast<uint2*>(__shfl_sync(0xffffffffu, reinterpret_cast<unsigned long long>(list), r));
+            const int c_r = __shfl_sync(0xffffffffu, cnt, r);
+            const uint32_t T = warp_select<EPL, true>(l, c_r, p.k, lane);
+            if (lane == r) {
+              cnt = p.k;
+              if (T > thr_key) { thr_key = T; thr = key_f32(T); }
+              atomicMax(p.gthr + (valid ? q : 0), T);
+            }
+          }
+        }
+        if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1u; }
+      }
+      p.counts[list_item * BLOCK_M + row] = valid ? cnt : 0;
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();                              // the peer may still read this CTA's shared memory / barriers
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc_2sm(tmem_base, TMEM_COLS);
+  }
+}
+
 
 // ----------------------------------------------------------------------------
 // Merge the per-item candidate lists of each query into its final top-k.
@@ -669,60 +891,128 @@ static void setup_terms(DenseParams& p, int q_planes, int planes, int d_pad) {
   for (int i = 0; i < nt; ++i) { p.a_col[i] = terms[i][0] * d_pad; p.b_col[i] = terms[i][1] * d_pad; }
 }
 
+// gthr[i] = thr_init[i] for real queries (pre-pass bound), "-inf" for padding rows
+__global__ void init_gthr_kernel(uint32_t* __restrict__ gthr, const uint32_t* __restrict__ thr_init, int nq, size_t n) {
+  const size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
+  if (i < n) gthr[i] = (thr_init && i < static_cast<size_t>(nq)) ? thr_init[i] : KEY_NEG_INF;
+}
+// bound for the main pass from the pre-pass result: one key below its k-th score, so that the strict
+// "score > threshold" test of the epilogue still admits that row when the main pass meets it again
+__global__ void prepass_bound_kernel(const float* __restrict__ scores, const int64_t* __restrict__ ids, int nq, int k,
+                                     uint32_t* __restrict__ thr) {
+  const int q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= nq) return;
+  thr[q] = ids[static_cast<size_t>(q) * k + k - 1] >= 0 ? f32_key(scores[static_cast<size_t>(q) * k + k - 1]) - 1u : KEY_NEG_INF;
+}
+
+// one scan of rows [0, n_rows) of the index; thr_init (device, [nq] keys or NULL) pre-loads the shared thresholds
 template <int EPL>
-static int run_dense(const arb_index* ix, const __nv_bfloat16* qplanes, int q_planes, int64_t nq, int k,
-                     int64_t id_base, float* d_scores, int64_t* d_ids, cudaStream_t st) {
+static int run_dense_rows(const arb_index* ix, int64_t n_rows, const uint32_t* thr_init, const __nv_bfloat16* qplanes,
+                          int q_planes, int64_t nq, int k, int64_t id_base, float* d_scores, int64_t* d_ids,
+                          cudaStream_t st) {
   constexpr int C = 32 * EPL;
   DenseParams p;
   memset(&p, 0, sizeof(p));
   p.nq = static_cast<int>(nq);
-  p.n_rows = static_cast<uint32_t>(ix->n);
+  p.n_rows = static_cast<uint32_t>(n_rows);
   p.k = k;
   p.kb_per_term = ix->d_pad / BLOCK_K;
   setup_terms(p, q_planes, ix->planes, ix->d_pad);
   p.n_qtiles = static_cast<int>((nq + BLOCK_M - 1) / BLOCK_M);
-  p.n_ntiles = static_cast<int>((ix->n + BLOCK_N - 1) / BLOCK_N);
+  p.n_ntiles = static_cast<int>((n_rows + BLOCK_N - 1) / BLOCK_N);
   const int sms = num_sms();
-  plan_splits(p.n_qtiles, p.n_ntiles, sms, &p.n_splits, &p.tiles_per_split);
-  p.n_items = p.n_splits * p.n_qtiles;
-  const int grid = std::min(sms, p.n_items);
+  // CTA pairs (cta_group::2) for batches of at least 256 queries
+  // (measured slower than the single-CTA kernel on cfg3 -- 6.2 vs 5.9 ms -- so it is opt-in: ARB_DENSE_PAIR=1)
+  bool use_pair = false;
+  if (const char* v = std::getenv("ARB_DENSE_PAIR")) use_pair = atoi(v) != 0 && nq >= 2 * BLOCK_M && sms >= 2;
+  int grid;
+  if (use_pair) {
+    p.n_qtiles = (p.n_qtiles + 1) & ~1;                  // whole 256-query super tiles (the odd one is padding)
+    const int clusters = sms / 2;
+    plan_splits(p.n_qtiles / 2, p.n_ntiles, clusters, &p.n_splits, &p.tiles_per_split);
+    p.n_items = p.n_splits * (p.n_qtiles / 2);
+    grid = 2 * std::min(clusters, p.n_items);
+  } else {
+    plan_splits(p.n_qtiles, p.n_ntiles, sms, &p.n_splits, &p.tiles_per_split);
+    p.n_items = p.n_splits * p.n_qtiles;
+    grid = std::min(sms, p.n_items);
+  }
+  const size_t n_slots = static_cast<size_t>(p.n_splits) * p.n_qtiles;   // candidate lists per query row
 
   AsyncBuf lists, counts, gthr;
-  ARB_CUDA(lists.alloc(static_cast<size_t>(p.n_items) * BLOCK_M * C * sizeof(uint2), st));
-  ARB_CUDA(counts.alloc(static_cast<size_t>(p.n_items) * BLOCK_M * sizeof(int), st));
+  ARB_CUDA(lists.alloc(n_slots * BLOCK_M * C * sizeof(uint2), st));
+  ARB_CUDA(counts.alloc(n_slots * BLOCK_M * sizeof(int), st));
   ARB_CUDA(gthr.alloc(static_cast<size_t>(p.n_qtiles) * BLOCK_M * sizeof(uint32_t), st));
   p.lists = lists.as<uint2>();
   p.counts = counts.as<int>();
   p.gthr = gthr.as<uint32_t>();
   const size_t ng = static_cast<size_t>(p.n_qtiles) * BLOCK_M;
-  fill_u32_kernel<<<static_cast<unsigned>((ng + 255) / 256), 256, 0, st>>>(p.gthr, KEY_NEG_INF, ng);
+  init_gthr_kernel<<<static_cast<unsigned>((ng + 255) / 256), 256, 0, st>>>(p.gthr, thr_init, p.nq, ng);
   ARB_LAUNCH_OK();
 
   CUtensorMap ta, tb;
   int rc = make_tmap(&ta, qplanes, static_cast<uint64_t>(nq), static_cast<uint64_t>(q_planes) * ix->d_pad, BLOCK_M);
   if (rc) return rc;
-  rc = make_tmap(&tb, ix->rows, static_cast<uint64_t>(ix->n), static_cast<uint64_t>(ix->planes) * ix->d_pad, BLOCK_N);
+  rc = make_tmap(&tb, ix->rows, static_cast<uint64_t>(n_rows), static_cast<uint64_t>(ix->planes) * ix->d_pad,
+                 use_pair ? BLOCK_N / 2 : BLOCK_N);              // a pair's CTA stages half of the corpus tile
   if (rc) return rc;
 
   static std::once_flag attr_once;
   static cudaError_t attr_err = cudaSuccess;
   std::call_once(attr_once, [] {
     attr_err = cudaFuncSetAttribute(dense_topk_kernel<EPL, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, DENSE_SMEM);
+    if (attr_err == cudaSuccess)
+      attr_err = cudaFuncSetAttribute(dense_topk_pair_kernel<EPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, PAIR_SMEM);
   });
   ARB_CUDA(attr_err);
   {
-    ProfileScope ps(PROF_DENSE_TOPK, st);
-    dense_topk_kernel<EPL, false><<<grid, DENSE_THREADS, DENSE_SMEM, st>>>(ta, tb, p);
+    if (use_pair) {
+      cudaLaunchConfig_t cfg;
+      memset(&cfg, 0, sizeof(cfg));
+      cfg.gridDim = dim3(static_cast<unsigned>(grid));
+      cfg.blockDim = dim3(DENSE_THREADS);
+      cfg.dynamicSmemBytes = PAIR_SMEM;
+      cfg.stream = st;
+      cudaLaunchAttribute attr[1];
+      attr[0].id = cudaLaunchAttributeClusterDimension;
+      attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+      cfg.attrs = attr;
+      cfg.numAttrs = 1;
+      ARB_CUDA(cudaLaunchKernelEx(&cfg, dense_topk_pair_kernel<EPL>, ta, tb, p));
+    } else {
+      dense_topk_kernel<EPL, false><<<grid, DENSE_THREADS, DENSE_SMEM, st>>>(ta, tb, p);
+    }
   }
   ARB_LAUNCH_OK();
   const int wpb = 4;
   {
-    ProfileScope ps(PROF_DENSE_MERGE, st);
     dense_merge_kernel<EPL, false><<<static_cast<unsigned>((nq + wpb - 1) / wpb), wpb * 32, wpb * C * sizeof(uint2), st>>>(
         p, id_base, d_scores, d_ids);
   }
   ARB_LAUNCH_OK();
   return ARB_OK;
+}
+
+// Exact flat search.  Large corpora are scanned twice: a pre-pass over the first tenth of the rows gives every
+// query the k-th score of that sample, and the full scan starts from that bound instead of -inf.  The epilogue
+// pays ~45 warp instructions whenever any of a warp's 32 queries has a score above its threshold in a group of 8
+// columns; with cold thresholds that is ~17 % of all column steps and the four epilogue warps -- not the tensor
+// pipe -- bound the kernel (6.7 ms vs 4.1 ms for the bare GEMM at cfg3).  The pre-pass costs a tenth of a scan.
+template <int EPL>
+static int run_dense(const arb_index* ix, const __nv_bfloat16* qplanes, int q_planes, int64_t nq, int k,
+                     int64_t id_base, float* d_scores, int64_t* d_ids, cudaStream_t st) {
+  bool prepass = ix->n >= 262144 && nq >= BLOCK_M && k <= ix->n / 16;
+  if (const char* v = std::getenv("ARB_DENSE_PREPASS")) prepass = prepass && atoi(v) != 0;
+  ProfileScope ps(PROF_DENSE_TOPK, st);
+  if (!prepass) return run_dense_rows<EPL>(ix, ix->n, nullptr, qplanes, q_planes, nq, k, id_base, d_scores, d_ids, st);
+  const int64_t n_pre = ((ix->n / 10 + BLOCK_N - 1) / BLOCK_N) * BLOCK_N;
+  AsyncBuf thr;
+  ARB_CUDA(thr.alloc(static_cast<size_t>(nq) * 4, st));
+  int rc = run_dense_rows<EPL>(ix, n_pre, nullptr, qplanes, q_planes, nq, k, id_base, d_scores, d_ids, st);
+  if (rc) return rc;
+  prepass_bound_kernel<<<static_cast<unsigned>((nq + 255) / 256), 256, 0, st>>>(d_scores, d_ids, static_cast<int>(nq), k, thr.as<uint32_t>());
+  ARB_LAUNCH_OK();
+  return run_dense_rows<EPL>(ix, ix->n, thr.as<uint32_t>(), qplanes, q_planes, nq, k, id_base, d_scores, d_ids, st);
 }
 
 extern "C" int arb_index_search(const arb_index* ix, const void* queries, int dtype, int64_t nq, int queries_is_device,

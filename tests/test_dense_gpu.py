@@ -190,3 +190,32 @@ def test_errors_are_reported_not_swallowed_at_the_abi():
         ix.search(np.zeros((1, 32), np.float32), 1000)          # k beyond ARB_MAX_TOPK
     with pytest.raises(ValueError):
         ix.search(np.zeros((1, 31), np.float32), 5)
+
+
+def test_prepass_and_cta_pair_variants_are_bit_identical(monkeypatch):
+    """The two-pass search (pre-pass over a tenth of the rows seeds the thresholds) and the cta_group::2 kernel
+    must return exactly what the plain single-CTA scan returns; the plain scan is pinned to the oracle above."""
+    import torch
+    engine, od = _mods()
+    rng = np.random.default_rng(77)
+    n, d, nq, k = 300_000, 64, 384, 50
+    x = rng.standard_normal((n, d)).astype(np.float32)
+    x[1000:1040] = x[10:50]                                     # exact duplicates: ties across the pre-pass boundary
+    q = (x[rng.integers(0, n, nq)] + 0.4 * rng.standard_normal((nq, d))).astype(np.float32)
+    ix = engine.DenseIndex(d, storage="fp32", normalize=True)
+    ix.add(x)
+    qd = torch.from_numpy(q).cuda()
+    out = {}
+    for pair in ("0", "1"):
+        for pre in ("0", "1"):
+            monkeypatch.setenv("ARB_DENSE_PAIR", pair)
+            monkeypatch.setenv("ARB_DENSE_PREPASS", pre)
+            s, i = ix.search(qd, k)
+            out[pair, pre] = (s.cpu().numpy(), i.cpu().numpy())
+    base = out["0", "0"]
+    for key, (s, i) in out.items():
+        assert np.array_equal(i, base[1]) and np.array_equal(s, base[0]), key
+    ws, wi = od.flat_ip_topk(od.preprocess_vectors(q[:16]), od.preprocess_vectors(x), k)
+    ok, _, _, worst = od.compare_topk(base[1][:16], base[0][:16], wi, ws, tol=TOL)
+    assert ok, worst
+    ix.close()
