@@ -43,7 +43,8 @@ constexpr int B_BYTES = BLOCK_N * BLOCK_K * 2;
 constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
 constexpr int ACC_STAGES = 2;
 constexpr int TMEM_COLS = ACC_STAGES * BLOCK_N;   // 512: the whole TMEM of the SM
-constexpr int DENSE_THREADS = 192;                // warp0 TMA, warp1 MMA, warps2-5 epilogue
+constexpr int EPI_HALVES = 2;                     // epilogue warps per TMEM lane quadrant: each takes half of a tile's columns
+constexpr int DENSE_THREADS = 64 + 128 * EPI_HALVES;   // warp0 TMA, warp1 MMA, warps 2..9 epilogue
 constexpr int DENSE_SMEM = STAGES * STAGE_BYTES + 256 + 1024;
 constexpr int PSTAGES = 6;                        // CTA-pair kernel: A 128 x 64 + half of B (128 x 64) per stage
 constexpr int PSTAGE_BYTES = A_BYTES + B_BYTES / 2;
@@ -158,7 +159,7 @@ dense_topk_kernel(const __grid_constant__ CUtensorMap tmap_a,
     prefetch_tmap(&tmap_a);
     prefetch_tmap(&tmap_b);
     for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-    for (int a = 0; a < ACC_STAGES; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], 4); }
+    for (int a = 0; a < ACC_STAGES; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], 4 * EPI_HALVES); }
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, TMEM_COLS);
@@ -237,8 +238,9 @@ dense_topk_kernel(const __grid_constant__ CUtensorMap tmap_a,
       }
     }
   } else {
-    // ------------------------------------------------------------ epilogue (4 warps)
+    // ------------------------------------------------------------ epilogue (4 * EPI_HALVES warps)
     const int quad = warp & 3;                   // TMEM lane quadrant this warp may read
+    const int half = (warp - 2) >> 2;            // which half of every tile's columns this warp scans
     const int row = quad * 32 + lane;            // query row inside the tile
     int acc = 0; uint32_t acc_phase = 0;
     for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
@@ -246,7 +248,7 @@ dense_topk_kernel(const __grid_constant__ CUtensorMap tmap_a,
       decode(item, a_row0, b_row0, t0, t1, b_end);
       const int q = IVF ? __ldg(p.row_query + a_row0 + row) : a_row0 + row;
       const bool valid = q >= 0 && q < p.nq;
-      uint2* list = p.lists + (static_cast<size_t>(item) * BLOCK_M + row) * C;
+      uint2* list = p.lists + ((static_cast<size_t>(item) * BLOCK_M + row) * EPI_HALVES + half) * C;
       int cnt = 0;
       uint32_t thr_key = KEY_NEG_INF;
       float thr = valid ? -INFINITY : INFINITY;
@@ -261,11 +263,11 @@ dense_topk_kernel(const __grid_constant__ CUtensorMap tmap_a,
         const bool tail = n_base + BLOCK_N > b_end;
         const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * BLOCK_N;
 #pragma unroll 1
-        for (int c = 0; c < BLOCK_N / 32; ++c) {
+        for (int c = half * (BLOCK_N / 32 / EPI_HALVES); c < (half + 1) * (BLOCK_N / 32 / EPI_HALVES); ++c) {
           uint32_t v[32];
           tmem_ld_32x32(taddr + c * 32, v);
           tmem_ld_wait();
-          if (c == BLOCK_N / 32 - 1) {
+          if (c == (half + 1) * (BLOCK_N / 32 / EPI_HALVES) - 1) {
             // all of this warp's reads of the accumulator are done: hand it back
             tc_fence_before();
             __syncwarp();
@@ -312,7 +314,7 @@ dense_topk_kernel(const __grid_constant__ CUtensorMap tmap_a,
         }
         if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1u; }
       }
-      p.counts[static_cast<size_t>(item) * BLOCK_M + row] = valid ? cnt : 0;
+      p.counts[(static_cast<size_t>(item) * BLOCK_M + row) * EPI_HALVES + half] = valid ? cnt : 0;
     }
   }
 
@@ -355,7 +357,7 @@ dense_topk_pair_kernel(const __grid_constant__ CUtensorMap tmap_a,
     prefetch_tmap(&tmap_b);
     for (int s = 0; s < PSTAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
     // the leader's "accumulator drained" barrier collects the epilogue warps of BOTH CTAs
-    for (int a = 0; a < ACC_STAGES; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], 8); }
+    for (int a = 0; a < ACC_STAGES; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], 8 * EPI_HALVES); }
     fence_barrier_init();
   }
   __syncthreads();
@@ -439,8 +441,9 @@ dense_topk_pair_kernel(const __grid_constant__ CUtensorMap tmap_a,
       }
     }
   } else {
-    // ------------------------------------------------------------ epilogue (4 warps)
+    // ------------------------------------------------------------ epilogue (4 * EPI_HALVES warps)
     const int quad = warp & 3;                   // TMEM lane quadrant this warp may read
+    const int half = (warp - 2) >> 2;            // which half of every tile's columns this warp scans
     const int row = quad * 32 + lane;            // query row inside the tile
     int acc = 0; uint32_t acc_phase = 0;
     for (int item = pair; item < n_items; item += n_pairs) {
@@ -451,7 +454,7 @@ dense_topk_pair_kernel(const __grid_constant__ CUtensorMap tmap_a,
       // candidate-list slot of this CTA's query tile: same numbering as the single-CTA kernel (split-major)
       const int n_qt2 = p.n_qtiles >> 1;
       const size_t list_item = static_cast<size_t>(item / n_qt2) * p.n_qtiles + 2 * (item % n_qt2) + cta_rank;
-      uint2* list = p.lists + (list_item * BLOCK_M + row) * C;
+      uint2* list = p.lists + ((list_item * BLOCK_M + row) * EPI_HALVES + half) * C;
       int cnt = 0;
       uint32_t thr_key = KEY_NEG_INF;
       float thr = valid ? -INFINITY : INFINITY;
@@ -466,11 +469,11 @@ dense_topk_pair_kernel(const __grid_constant__ CUtensorMap tmap_a,
         const bool tail = n_base + BLOCK_N > b_end;
         const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * BLOCK_N;
 #pragma unroll 1
-        for (int c = 0; c < BLOCK_N / 32; ++c) {
+        for (int c = half * (BLOCK_N / 32 / EPI_HALVES); c < (half + 1) * (BLOCK_N / 32 / EPI_HALVES); ++c) {
           uint32_t v[32];
           tmem_ld_32x32(taddr + c * 32, v);
           tmem_ld_wait();
-          if (c == BLOCK_N / 32 - 1) {
+          if (c == (half + 1) * (BLOCK_N / 32 / EPI_HALVES) - 1) {
             // all of this warp's reads of the accumulator are done: hand it back
             tc_fence_before();
             __syncwarp();
@@ -517,7 +520,7 @@ dense_topk_pair_kernel(const __grid_constant__ CUtensorMap tmap_a,
         }
         if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1u; }
       }
-      p.counts[list_item * BLOCK_M + row] = valid ? cnt : 0;
+      p.counts[(list_item * BLOCK_M + row) * EPI_HALVES + half] = valid ? cnt : 0;
     }
   }
 
@@ -559,8 +562,9 @@ dense_merge_kernel(const DenseParams p, int64_t id_base, float* __restrict__ out
     } else {
       slot = (static_cast<size_t>(sp) * p.n_qtiles + qt) * BLOCK_M + row;
     }
-    const uint2* L = p.lists + slot * C;
-    const int n = p.counts[slot];
+    for (int hb = 0; hb < EPI_HALVES; ++hb) {
+    const uint2* L = p.lists + (slot * EPI_HALVES + hb) * C;
+    const int n = p.counts[slot * EPI_HALVES + hb];
     for (int b = 0; b < n; b += 32) {
       uint2 e = make_uint2(0u, 0u);
       if (b + lane < n) {
@@ -576,6 +580,7 @@ dense_merge_kernel(const DenseParams p, int64_t id_base, float* __restrict__ out
         cnt = p.k;
         thr_key = max(thr_key, T);
       }
+    }
     }
   }
   __syncwarp();
@@ -940,8 +945,8 @@ static int run_dense_rows(const arb_index* ix, int64_t n_rows, const uint32_t* t
   const size_t n_slots = static_cast<size_t>(p.n_splits) * p.n_qtiles;   // candidate lists per query row
 
   AsyncBuf lists, counts, gthr;
-  ARB_CUDA(lists.alloc(n_slots * BLOCK_M * C * sizeof(uint2), st));
-  ARB_CUDA(counts.alloc(n_slots * BLOCK_M * sizeof(int), st));
+  ARB_CUDA(lists.alloc(n_slots * BLOCK_M * EPI_HALVES * C * sizeof(uint2), st));
+  ARB_CUDA(counts.alloc(n_slots * BLOCK_M * EPI_HALVES * sizeof(int), st));
   ARB_CUDA(gthr.alloc(static_cast<size_t>(p.n_qtiles) * BLOCK_M * sizeof(uint32_t), st));
   p.lists = lists.as<uint2>();
   p.counts = counts.as<int>();
@@ -993,7 +998,7 @@ static int run_dense_rows(const arb_index* ix, int64_t n_rows, const uint32_t* t
   return ARB_OK;
 }
 
-// Exact flat search.  Large corpora are scanned twice: a pre-pass over the first tenth of the rows gives every
+// Exact flat search.  Optionally the corpus is scanned twice: a pre-pass over the first tenth of the rows gives every
 // query the k-th score of that sample, and the full scan starts from that bound instead of -inf.  The epilogue
 // pays ~45 warp instructions whenever any of a warp's 32 queries has a score above its threshold in a group of 8
 // columns; with cold thresholds that is ~17 % of all column steps and the four epilogue warps -- not the tensor
@@ -1001,8 +1006,10 @@ static int run_dense_rows(const arb_index* ix, int64_t n_rows, const uint32_t* t
 template <int EPL>
 static int run_dense(const arb_index* ix, const __nv_bfloat16* qplanes, int q_planes, int64_t nq, int k,
                      int64_t id_base, float* d_scores, int64_t* d_ids, cudaStream_t st) {
-  bool prepass = ix->n >= 262144 && nq >= BLOCK_M && k <= ix->n / 16;
-  if (const char* v = std::getenv("ARB_DENSE_PREPASS")) prepass = prepass && atoi(v) != 0;
+  // (with two epilogue warps per TMEM quadrant the pre-pass no longer pays on cfg3 -- 5.68 vs 5.69 ms -- so it is
+  //  opt-in: ARB_DENSE_PREPASS=1; it was worth 1 ms with four epilogue warps)
+  bool prepass = false;
+  if (const char* v = std::getenv("ARB_DENSE_PREPASS")) prepass = atoi(v) != 0 && ix->n >= 262144 && nq >= BLOCK_M && k <= ix->n / 16;
   ProfileScope ps(PROF_DENSE_TOPK, st);
   if (!prepass) return run_dense_rows<EPL>(ix, ix->n, nullptr, qplanes, q_planes, nq, k, id_base, d_scores, d_ids, st);
   const int64_t n_pre = ((ix->n / 10 + BLOCK_N - 1) / BLOCK_N) * BLOCK_N;
@@ -1437,8 +1444,8 @@ static int run_ivf(arb_index* ix, const __nv_bfloat16* qplanes, int q_planes, in
   p.pair_pos = pair_pos.as<int>();
   p.nprobe = nprobe;
   p.row_ids = ix->g_ids;
-  ARB_CUDA(lists.alloc(static_cast<size_t>(max_items) * BLOCK_M * C * sizeof(uint2), st));
-  ARB_CUDA(counts.alloc(static_cast<size_t>(max_items) * BLOCK_M * sizeof(int), st));
+  ARB_CUDA(lists.alloc(static_cast<size_t>(max_items) * BLOCK_M * EPI_HALVES * C * sizeof(uint2), st));
+  ARB_CUDA(counts.alloc(static_cast<size_t>(max_items) * BLOCK_M * EPI_HALVES * sizeof(int), st));
   ARB_CUDA(gthr.alloc(static_cast<size_t>(p.n_qtiles) * BLOCK_M * sizeof(uint32_t), st));
   p.lists = lists.as<uint2>();
   p.counts = counts.as<int>();
