@@ -454,8 +454,8 @@ bm25_sparse_pass_kernel(const Bm25Dev ix, const int32_t* __restrict__ q_terms_al
 // plane-pass threshold / the query's state.  One CTA per query.
 // ----------------------------------------------------------------------------
 __global__ void __launch_bounds__(128)
-bm25_a_merge_kernel(int64_t nq, int k, const BatchScratch sc) {
-  extern __shared__ __align__(16) uint8_t am_smem[];
+bm25_a_merge_kernel(int64_t nq, int k, const int A_MERGE_CAP, const BatchScratch sc) {
+  extern __shared__ __align__(16) uint8_t am_smem[];             // A_MERGE_CAP x 12 B (a power of two >= parts * k)
   const int64_t q = blockIdx.x;
   const int tid = threadIdx.x;
   __shared__ int s_n, s_ovf, s_total;
@@ -476,18 +476,21 @@ bm25_a_merge_kernel(int64_t nq, int k, const BatchScratch sc) {
   __syncthreads();
   const unsigned long long fl = s_floor;
   unsigned long long* key = reinterpret_cast<unsigned long long*>(am_smem);
-  int n2max = 2;                                               // the launch reserves 12 B x this many slots
-  while (n2max < sc.parts * k) n2max <<= 1;
-  uint32_t* doc = reinterpret_cast<uint32_t*>(am_smem + static_cast<size_t>(n2max) * 8);
+  uint32_t* doc = reinterpret_cast<uint32_t*>(am_smem + static_cast<size_t>(A_MERGE_CAP) * 8);
   for (int i = tid; i < sc.parts * k; i += blockDim.x) {
     const int p = i / k, j = i - p * k;
     if (j < sc.pa_cnt[q * sc.parts + p]) {
       const unsigned long long kk = sc.pa_key[(q * sc.parts + p) * k + j];
-      if (kk >= fl) { const int pos = atomicAdd(&s_n, 1); key[pos] = kk; doc[pos] = sc.pa_doc[(q * sc.parts + p) * k + j]; }
+      if (kk >= fl) {
+        const int pos = atomicAdd(&s_n, 1);
+        if (pos < A_MERGE_CAP) { key[pos] = kk; doc[pos] = sc.pa_doc[(q * sc.parts + p) * k + j]; }
+      }
     }
   }
   __syncthreads();
-  const int n = s_n;
+  if (s_n > A_MERGE_CAP) { if (tid == 0) s_ovf = 1; }
+  const int n = min(s_n, A_MERGE_CAP);
+  __syncthreads();
   int n2 = 2;
   while (n2 < n) n2 <<= 1;
   for (int i = n + tid; i < n2; i += blockDim.x) { key[i] = 0ull; doc[i] = 0xFFFFFFFFu; }
@@ -561,78 +564,91 @@ bm25_plane_pass_kernel(const Bm25Dev ix, int64_t nq, int64_t q_per_group, const 
       if (threadIdx.x < P) tmax_s[threadIdx.x] = __ldg(ix.plane_tmax + tile * P + threadIdx.x);
     }
     __syncthreads();
-    // Per-query inputs: {threshold, packed plane slots} come from shared memory (staged once per CTA), the
-    // member byte is streamed from HBM (this tile's 32-byte records of consecutive queries) two iterations ahead.
+    // Per-query inputs: {threshold, packed plane slots} come from shared memory (staged once per CTA); the member
+    // byte is streamed from HBM (this tile's 32-byte records of consecutive queries).  Four queries are processed
+    // per outer iteration so that the loads of the next four are in flight, in their own registers, meanwhile.
     const uint8_t* bm_tile = bm_bytes + tile * sc.nq * (PLANE_TILE / 8) + lane;   // + q * 32: this lane's 8 member bits
-    uint32_t mb_n = 0u, mb_nn = 0u;
-    {
-      const int64_t q = q0 + warp;
-      if (q < q1) mb_n = __ldg(bm_tile + q * 32);
-      if (q + PL_WARPS < q1) mb_nn = __ldg(bm_tile + (q + PL_WARPS) * 32);
-    }
-    for (int64_t q = q0 + warp; q < q1; q += PL_WARPS) {
+    auto process = [&](const int64_t q, const uint32_t mb) {
       const ulonglong2 rec = qrec[q - q0];                   // {k-th score of A as fp64 bits, packed plane slots}
       unsigned long long pk = rec.y;
-      const uint32_t mb = mb_n;
-      mb_n = mb_nn;
-      if (q + 2 * PL_WARPS < q1) mb_nn = __ldg(bm_tile + (q + 2 * PL_WARPS) * 32);
-      uint32_t ps = static_cast<uint32_t>(pk) & 0xFFu;
-      if (ps == 0xFFu) continue;                             // skipped query (no plane tokens / fallback / bounded out)
-      const double thr_d = __longlong_as_double(static_cast<long long>(rec.x));
-      {
-        // this tile's bound for the query (same token order); all lanes read the same shared-memory words
-        double ub = tmax_s[ps];
-        unsigned long long pb = pk;
+        uint32_t ps = static_cast<uint32_t>(pk) & 0xFFu;
+        if (ps == 0xFFu) return;                             // skipped query (no plane tokens / fallback / bounded out)
+        const double thr_d = __longlong_as_double(static_cast<long long>(rec.x));
+        {
+          // this tile's bound for the query (same token order); all lanes read the same shared-memory words
+          double ub = tmax_s[ps];
+          unsigned long long pb = pk;
+          for (int i = 1; i < sc.qd_stride; ++i) {
+            if ((i & 7) == 0) pb = __ldg(qd64 + q * qw + (i >> 3)); else pb >>= 8;
+            const uint32_t s2 = static_cast<uint32_t>(pb) & 0xFFu;
+            if (s2 == 0xFFu) break;
+            ub = __dadd_rn(ub, tmax_s[s2]);
+          }
+          if (ub < thr_d) return;
+        }
+        // first plane token: 0.0 + x == x (plane values are never -0.0), so the accumulators start as its row
+        double acc[8];
+        {
+          const double2* row = reinterpret_cast<const double2*>(pl_smem + ps * PLANE_TILE) + lane;
+  #pragma unroll
+          for (int j = 0; j < 4; ++j) { const double2 v = row[j * 32]; acc[2 * j] = v.x; acc[2 * j + 1] = v.y; }
+        }
         for (int i = 1; i < sc.qd_stride; ++i) {
-          if ((i & 7) == 0) pb = __ldg(qd64 + q * qw + (i >> 3)); else pb >>= 8;
-          const uint32_t s2 = static_cast<uint32_t>(pb) & 0xFFu;
-          if (s2 == 0xFFu) break;
-          ub = __dadd_rn(ub, tmax_s[s2]);
-        }
-        if (ub < thr_d) continue;
-      }
-      // first plane token: 0.0 + x == x (plane values are never -0.0), so the accumulators start as its row
-      double acc[8];
-      {
-        const double2* row = reinterpret_cast<const double2*>(pl_smem + ps * PLANE_TILE) + lane;
-#pragma unroll
-        for (int j = 0; j < 4; ++j) { const double2 v = row[j * 32]; acc[2 * j] = v.x; acc[2 * j + 1] = v.y; }
-      }
-      for (int i = 1; i < sc.qd_stride; ++i) {
-        if ((i & 7) == 0) pk = __ldg(qd64 + q * qw + (i >> 3)); else pk >>= 8;
-        ps = static_cast<uint32_t>(pk) & 0xFFu;
-        if (ps == 0xFFu) break;
-        const double2* row = reinterpret_cast<const double2*>(pl_smem + ps * PLANE_TILE) + lane;
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const double2 v = row[j * 32];
-          acc[2 * j] = __dadd_rn(acc[2 * j], v.x);
-          acc[2 * j + 1] = __dadd_rn(acc[2 * j + 1], v.y);
-        }
-      }
-      // docs that reach A's k-th score (a positive fp64, so comparing doubles is comparing keys) and are not
-      // members of the sparse pass
-      uint32_t pass = 0u;
-#pragma unroll
-      for (int r = 0; r < 8; ++r) if (acc[r] >= thr_d) pass |= 1u << r;
-      pass &= ~mb;
-      if (__ballot_sync(0xffffffffu, pass != 0u) == 0u) continue;
-#pragma unroll
-      for (int r = 0; r < 8; ++r) {
-        const bool p = (pass >> r) & 1u;
-        const uint32_t m = __ballot_sync(0xffffffffu, p);
-        if (m == 0u) continue;
-        int base = 0;
-        if (lane == 0) base = atomicAdd(&sc.e_cnt[q], __popc(m));
-        base = __shfl_sync(0xffffffffu, base, 0);
-        if (p) {
-          const int pos = base + __popc(m & lt);
-          if (pos < E_CAP) {
-            sc.e_key[q * E_CAP + pos] = f64_key(acc[r]);
-            sc.e_doc[q * E_CAP + pos] = static_cast<uint32_t>(tile * PLANE_TILE + 8 * lane + r);
+          if ((i & 7) == 0) pk = __ldg(qd64 + q * qw + (i >> 3)); else pk >>= 8;
+          ps = static_cast<uint32_t>(pk) & 0xFFu;
+          if (ps == 0xFFu) break;
+          const double2* row = reinterpret_cast<const double2*>(pl_smem + ps * PLANE_TILE) + lane;
+  #pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const double2 v = row[j * 32];
+            acc[2 * j] = __dadd_rn(acc[2 * j], v.x);
+            acc[2 * j + 1] = __dadd_rn(acc[2 * j + 1], v.y);
           }
         }
+        // docs that reach A's k-th score (a positive fp64, so comparing doubles is comparing keys) and are not
+        // members of the sparse pass
+        uint32_t pass = 0u;
+  #pragma unroll
+        for (int r = 0; r < 8; ++r) if (acc[r] >= thr_d) pass |= 1u << r;
+        pass &= ~mb;
+        if (__ballot_sync(0xffffffffu, pass != 0u) == 0u) return;
+  #pragma unroll
+        for (int r = 0; r < 8; ++r) {
+          const bool p = (pass >> r) & 1u;
+          const uint32_t m = __ballot_sync(0xffffffffu, p);
+          if (m == 0u) continue;
+          int base = 0;
+          if (lane == 0) base = atomicAdd(&sc.e_cnt[q], __popc(m));
+          base = __shfl_sync(0xffffffffu, base, 0);
+          if (p) {
+            const int pos = base + __popc(m & lt);
+            if (pos < E_CAP) {
+              sc.e_key[q * E_CAP + pos] = f64_key(acc[r]);
+              sc.e_doc[q * E_CAP + pos] = static_cast<uint32_t>(tile * PLANE_TILE + 8 * lane + r);
+            }
+          }
+        }
+    };
+    constexpr int PF = 4;
+    uint32_t cur[PF], nxt[PF];
+#pragma unroll
+    for (int u = 0; u < PF; ++u) {
+      const int64_t qq = q0 + warp + static_cast<int64_t>(u) * PL_WARPS;
+      cur[u] = qq < q1 ? __ldg(bm_tile + qq * 32) : 0u;
+    }
+    for (int64_t q = q0 + warp; q < q1; q += PF * PL_WARPS) {
+#pragma unroll
+      for (int u = 0; u < PF; ++u) {
+        const int64_t qq = q + static_cast<int64_t>(PF + u) * PL_WARPS;
+        nxt[u] = qq < q1 ? __ldg(bm_tile + qq * 32) : 0u;
       }
+#pragma unroll
+      for (int u = 0; u < PF; ++u) {
+        const int64_t qq = q + static_cast<int64_t>(u) * PL_WARPS;
+        if (qq < q1) process(qq, cur[u]);
+      }
+#pragma unroll
+      for (int u = 0; u < PF; ++u) cur[u] = nxt[u];
     }
   }
 }
@@ -730,6 +746,7 @@ static int batch_set_attrs() {
       err = cudaFuncSetAttribute(bm25_flag_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 4096 * 16);
     if (err == cudaSuccess)
       err = cudaFuncSetAttribute(bm25_a_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 8192 * 12);
+
   });
   ARB_CUDA(err);
   return bm25_set_smem_attrs();
@@ -793,7 +810,7 @@ static int batch_chunk(const Bm25Dev& ix, const int32_t* d_terms, int64_t nq, in
     ARB_LAUNCH_OK();
     int n2 = 2;
     while (n2 < sc.parts * k) n2 <<= 1;
-    bm25_a_merge_kernel<<<static_cast<unsigned>(nq), 128, static_cast<size_t>(n2) * 12, st>>>(nq, k, sc);
+    bm25_a_merge_kernel<<<static_cast<unsigned>(nq), 128, static_cast<size_t>(n2) * 12, st>>>(nq, k, n2, sc);
     ARB_LAUNCH_OK();
   }
   if (planes) {
@@ -815,7 +832,7 @@ static int batch_chunk(const Bm25Dev& ix, const int32_t* d_terms, int64_t nq, in
     ProfileScope ps(PROF_BM25_FINAL, st);
     bm25_final_merge_kernel<<<static_cast<unsigned>(nq), 128, FM_SMEM, st>>>(nq, k, id_base, sc, d_scores, d_ids);
     ARB_LAUNCH_OK();
-    if (planes) {
+    {
       // fallback for the flagged queries (the count lives on the device; CTAs with nothing to do exit)
       int n_split = static_cast<int>(std::min<int64_t>(ix.nb, 8));
       n_split = std::max(1, std::min(n_split, 4096 / k));
