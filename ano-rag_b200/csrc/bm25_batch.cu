@@ -512,6 +512,83 @@ bm25_a_merge_kernel(int64_t nq, int k, const int A_MERGE_CAP, const BatchScratch
   }
 }
 
+// 1b'. the same merge for the common shapes (parts * k keys fit 20 KB): one WARP per query.  The part lists are
+// sorted, so the merged k-th key is found by a bitwise search in which lane p counts, by binary search in its
+// own list (held in shared memory), how many of part p's keys reach the candidate; only the <= k (+ ties)
+// entries at or above that key are gathered and sorted.
+constexpr int AMW_WARPS = 4;
+constexpr int AMW_KEYS = 2560;                      // keys per warp (20 KB)
+constexpr int AMW_OUT = 512;                        // gathered entries per warp
+struct AmWarp { unsigned long long keys[AMW_KEYS]; unsigned long long okey[AMW_OUT]; uint32_t odoc[AMW_OUT]; };
+__global__ void __launch_bounds__(AMW_WARPS * 32)
+bm25_a_merge_warp_kernel(int64_t nq, int k, const BatchScratch sc) {
+  extern __shared__ __align__(16) uint8_t amw_smem[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t q = blockIdx.x * static_cast<int64_t>(AMW_WARPS) + warp;
+  if (q >= nq) return;
+  AmWarp& W = reinterpret_cast<AmWarp*>(amw_smem)[warp];
+  const int parts = sc.parts;
+  int my_cnt = 0;
+  bool ovf = false;
+  if (lane < parts) { my_cnt = sc.pa_cnt[q * parts + lane]; if (my_cnt < 0) { ovf = true; my_cnt = 0; } }
+  ovf = __any_sync(0xffffffffu, ovf);
+  for (int p = 0; p < parts; ++p) {
+    const int c = __shfl_sync(0xffffffffu, my_cnt, p);
+    for (int j = lane; j < c; j += 32) W.keys[p * k + j] = sc.pa_key[(q * parts + p) * k + j];
+  }
+  __syncwarp();
+  const int total = __reduce_add_sync(0xffffffffu, my_cnt);
+  // number of keys of this lane's part that are >= cand (the list is sorted descending)
+  auto count_ge = [&](unsigned long long cand) {
+    int lo = 0, hi = my_cnt;
+    const unsigned long long* L = W.keys + lane * k;
+    while (lo < hi) { const int mid = (lo + hi) >> 1; if (L[mid] >= cand) lo = mid + 1; else hi = mid; }
+    return lo;
+  };
+  unsigned long long T = 0ull;
+  if (total > k) {
+    for (int bit = 63; bit >= 0; --bit) {
+      const unsigned long long cand = T | (1ull << bit);
+      const int c = __reduce_add_sync(0xffffffffu, lane < parts ? count_ge(cand) : 0);
+      if (c >= k) T = cand;                                    // at least k keys reach cand: the k-th key does too
+    }
+  }
+  // gather everything at or above the k-th key (exactly k entries unless keys tie there)
+  const int mine = lane < parts ? (total > k ? count_ge(T) : my_cnt) : 0;
+  int incl = mine;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
+  const int n = __shfl_sync(0xffffffffu, incl, 31);
+  const bool too_many = n > AMW_OUT;
+  if (!too_many) {
+    for (int p = 0; p < parts; ++p) {
+      const int c = __shfl_sync(0xffffffffu, mine, p), base = __shfl_sync(0xffffffffu, incl - mine, p);
+      for (int j = lane; j < c; j += 32) { W.okey[base + j] = W.keys[p * k + j]; W.odoc[base + j] = sc.pa_doc[(q * parts + p) * k + j]; }
+    }
+  }
+  int n2 = 32;
+  while (n2 < n && n2 < AMW_OUT) n2 <<= 1;
+  const int nn = too_many ? 0 : n;
+  for (int i = nn + lane; i < n2; i += 32) { W.okey[i] = 0ull; W.odoc[i] = 0xFFFFFFFFu; }
+  warp_sort_desc(W.okey, W.odoc, n2, lane);
+  const int cnt = min(nn, k);
+  for (int i = lane; i < k; i += 32) {
+    sc.a_key[q * k + i] = i < cnt ? W.okey[i] : 0ull;
+    sc.a_doc[q * k + i] = i < cnt ? W.odoc[i] : 0xFFFFFFFFu;
+  }
+  if (lane == 0) {
+    const bool has_planes = sc.qd[q * sc.qd_stride] != 0xFF;
+    const bool bad = ovf || too_many;
+    sc.a_cnt[q] = cnt;
+    if (!has_planes && !bad)   { sc.state[q] = 1; sc.thr[q] = THR_SKIP; }
+    else if (cnt >= k && !bad) { sc.state[q] = 0; sc.thr[q] = W.okey[k - 1]; }
+    else {
+      sc.state[q] = 2; sc.thr[q] = THR_SKIP;
+      sc.flag_list[atomicAdd(&sc.counters[1], 1)] = static_cast<int>(q);
+    }
+  }
+}
+
 // ----------------------------------------------------------------------------
 // 2. plane pass: grid (tile sets, query groups).  The CTA stages one 256-doc tile of every
 // plane in shared memory; each warp then scores that tile for its queries with 8 register
@@ -746,6 +823,9 @@ static int batch_set_attrs() {
       err = cudaFuncSetAttribute(bm25_flag_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 4096 * 16);
     if (err == cudaSuccess)
       err = cudaFuncSetAttribute(bm25_a_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 8192 * 12);
+    if (err == cudaSuccess)
+      err = cudaFuncSetAttribute(bm25_a_merge_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 AMW_WARPS * static_cast<int>(sizeof(AmWarp)));
 
   });
   ARB_CUDA(err);
@@ -808,9 +888,14 @@ static int batch_chunk(const Bm25Dev& ix, const int32_t* d_terms, int64_t nq, in
       bm25_sparse_pass_kernel<512><<<grid, W * 32, W * sizeof(SpWarp<512>), st>>>(ix, d_terms, mq, nq, k, sc);
     }
     ARB_LAUNCH_OK();
-    int n2 = 2;
-    while (n2 < sc.parts * k) n2 <<= 1;
-    bm25_a_merge_kernel<<<static_cast<unsigned>(nq), 128, static_cast<size_t>(n2) * 12, st>>>(nq, k, n2, sc);
+    if (sc.parts * k <= AMW_KEYS) {
+      bm25_a_merge_warp_kernel<<<static_cast<unsigned>((nq + AMW_WARPS - 1) / AMW_WARPS), AMW_WARPS * 32,
+                                 AMW_WARPS * sizeof(AmWarp), st>>>(nq, k, sc);
+    } else {
+      int n2 = 2;
+      while (n2 < sc.parts * k) n2 <<= 1;
+      bm25_a_merge_kernel<<<static_cast<unsigned>(nq), 128, static_cast<size_t>(n2) * 12, st>>>(nq, k, n2, sc);
+    }
     ARB_LAUNCH_OK();
   }
   if (planes) {
