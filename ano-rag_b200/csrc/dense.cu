@@ -1056,8 +1056,11 @@ extern "C" int arb_index_search(const arb_index* ix, const void* queries, int dt
     d_scores = oscores.as<float>();
     d_ids = oids.as<int64_t>();
   }
-  if (k <= 128) rc = run_dense<16>(ix, qplanes.as<__nv_bfloat16>(), query_planes, nq, k, id_base, d_scores, d_ids, st);
-  else          rc = run_dense<32>(ix, qplanes.as<__nv_bfloat16>(), query_planes, nq, k, id_base, d_scores, d_ids, st);
+  // candidate lists of 256 / 512 / 1024 entries: a smaller list is compacted more often, so its threshold stays
+  // closer to the running k-th score and fewer columns take the append path
+  if (k <= 100)      rc = run_dense<8>(ix, qplanes.as<__nv_bfloat16>(), query_planes, nq, k, id_base, d_scores, d_ids, st);
+  else if (k <= 128) rc = run_dense<16>(ix, qplanes.as<__nv_bfloat16>(), query_planes, nq, k, id_base, d_scores, d_ids, st);
+  else               rc = run_dense<32>(ix, qplanes.as<__nv_bfloat16>(), query_planes, nq, k, id_base, d_scores, d_ids, st);
   if (rc) return rc;
   if (!out_is_device) {
     ARB_CUDA(cudaMemcpyAsync(out_scores, d_scores, static_cast<size_t>(nq) * k * 4, cudaMemcpyDeviceToHost, st));
@@ -1517,8 +1520,9 @@ extern "C" int arb_index_ivf_search(arb_index* ix, const void* queries, int dtyp
     d_scores = oscores.as<float>();
     d_ids = oids.as<int64_t>();
   }
-  if (k <= 128) rc = run_ivf<16>(ix, qplanes.as<__nv_bfloat16>(), query_planes, nq, k, nprobe, id_base, d_scores, d_ids, st);
-  else          rc = run_ivf<32>(ix, qplanes.as<__nv_bfloat16>(), query_planes, nq, k, nprobe, id_base, d_scores, d_ids, st);
+  if (k <= 100)      rc = run_ivf<8>(ix, qplanes.as<__nv_bfloat16>(), query_planes, nq, k, nprobe, id_base, d_scores, d_ids, st);
+  else if (k <= 128) rc = run_ivf<16>(ix, qplanes.as<__nv_bfloat16>(), query_planes, nq, k, nprobe, id_base, d_scores, d_ids, st);
+  else               rc = run_ivf<32>(ix, qplanes.as<__nv_bfloat16>(), query_planes, nq, k, nprobe, id_base, d_scores, d_ids, st);
   if (rc) return rc;
   if (!out_is_device) {
     ARB_CUDA(cudaMemcpyAsync(out_scores, d_scores, static_cast<size_t>(nq) * k * 4, cudaMemcpyDeviceToHost, st));
