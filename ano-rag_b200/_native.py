@@ -59,6 +59,8 @@ _SIGS = {
     "arb_index_reconstruct": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_int, c_void_p]),
     "arb_index_search": (c_int, [c_void_p, c_void_p, c_int, c_int64, c_int, c_int, c_int, c_int64,
                                  c_void_p, c_void_p, c_int, c_void_p]),
+    "arb_index_score_rows": (c_int, [c_void_p, c_void_p, c_int, c_int64, c_int, c_void_p, c_int, c_int, c_int, c_int, c_void_p,
+                                     c_int, c_void_p]),
     "arb_index_ivf_set_centroids": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p]),
     "arb_index_ivf_train": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int64, c_int, c_int, c_int, c_void_p]),
     "arb_index_ivf_nlist": (c_int, [c_void_p]),
@@ -79,6 +81,8 @@ _SIGS = {
     "arb_combine_fields": (c_int, [c_int, POINTER(c_void_p), POINTER(c_double), c_int64, c_int64, c_void_p, c_void_p]),
     "arb_fuse": (c_int, [c_int, POINTER(c_double), c_double, c_int, c_int64, POINTER(c_void_p), POINTER(c_void_p),
                          POINTER(c_int), POINTER(c_int), c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
+    "arb_rescore_candidates": (c_int, [c_int, c_int64, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                       c_double, c_double, c_double, c_void_p, c_void_p, c_void_p]),
     "arb_merge_topk": (c_int, [c_int, c_void_p, c_void_p, c_int, c_int64, c_int, c_int, c_void_p, c_void_p,
                                c_void_p]),
 }

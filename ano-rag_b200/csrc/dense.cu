@@ -1531,3 +1531,76 @@ extern "C" int arb_index_ivf_search(arb_index* ix, const void* queries, int dtyp
   }
   return ARB_OK;
 }
+
+// ----------------------------------------------------------------------------
+// Per-candidate similarities (replaces the Python loop of QueryProcessor._calculate_vector_similarities,
+// query/query_processor.py:3543-3589: cosine of the query with the stored embedding of every note of a
+// candidate pool, clamped at 0).  One warp per (query, candidate): both vectors are read back from their
+// bf16 planes (hi + mid + lo = the stored fp32 value), fp32 FMA dot product, warp reduction.
+// ----------------------------------------------------------------------------
+namespace arb {
+__global__ void __launch_bounds__(256)
+score_rows_kernel(const __nv_bfloat16* __restrict__ rows, int64_t n_rows, int planes, const __nv_bfloat16* __restrict__ qplanes,
+                  int q_planes, int d_pad, const int64_t* __restrict__ cand, int64_t nq, int nc, int clamp_nonneg,
+                  float* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const int64_t pair = blockIdx.x * static_cast<int64_t>(blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (pair >= nq * nc) return;
+  const int64_t q = pair / nc;
+  const int64_t r = cand[pair];
+  float s = 0.f;
+  if (r >= 0 && r < n_rows) {
+    const __nv_bfloat16* x = rows + r * static_cast<int64_t>(planes) * d_pad;
+    const __nv_bfloat16* y = qplanes + q * static_cast<int64_t>(q_planes) * d_pad;
+    for (int i = lane; i < d_pad; i += 32) {
+      float a = 0.f, b = 0.f;
+      for (int pl = planes - 1; pl >= 0; --pl) a = __fadd_rn(a, __bfloat162float(x[pl * d_pad + i]));
+      for (int pl = q_planes - 1; pl >= 0; --pl) b = __fadd_rn(b, __bfloat162float(y[pl * d_pad + i]));
+      s = fmaf(a, b, s);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (clamp_nonneg) s = fmaxf(s, 0.f);                          // max(0.0, similarity) (:3567)
+  }
+  if (lane == 0) out[pair] = s;
+}
+}  // namespace arb
+
+extern "C" int arb_index_score_rows(const arb_index* ix, const void* queries, int dtype, int64_t nq, int queries_is_device,
+                                    const int64_t* cand_rows, int nc, int cand_is_device, int query_planes,
+                                    int clamp_nonneg, float* out, int out_is_device, void* stream) {
+  ARB_CHECK(ix != nullptr, ARB_EINVAL, "arb_index_score_rows: NULL index");
+  ARB_CHECK(nq >= 0 && nc >= 0 && (nq == 0 || nc == 0 || (queries && cand_rows && out)), ARB_EINVAL, "arb_index_score_rows: bad argument");
+  ARB_CHECK(dtype == ARB_F32 || dtype == ARB_BF16, ARB_EINVAL, "arb_index_score_rows: dtype must be ARB_F32 or ARB_BF16");
+  ARB_CHECK(query_planes == 1 || query_planes == 3, ARB_EINVAL, "arb_index_score_rows: query_planes must be 1 or 3");
+  if (nq == 0 || nc == 0) return ARB_OK;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const size_t esz = dtype == ARB_F32 ? 4 : 2;
+  const int64_t n_pairs = nq * nc;
+  AsyncBuf qstage, qplanes, cstage, obuf;
+  const void* q_dev = queries;
+  if (!queries_is_device) {
+    ARB_CUDA(qstage.alloc(static_cast<size_t>(nq) * ix->dim * esz, st));
+    ARB_CUDA(cudaMemcpyAsync(qstage.p, queries, static_cast<size_t>(nq) * ix->dim * esz, cudaMemcpyHostToDevice, st));
+    q_dev = qstage.p;
+  }
+  ARB_CUDA(qplanes.alloc(static_cast<size_t>(nq) * query_planes * ix->d_pad * 2, st));
+  int rc = launch_prep(q_dev, dtype, nq, ix->dim, ix->d_pad, query_planes, ix->normalize, qplanes.as<__nv_bfloat16>(), st);
+  if (rc) return rc;
+  const int64_t* d_cand = cand_rows;
+  if (!cand_is_device) {
+    ARB_CUDA(cstage.alloc(static_cast<size_t>(n_pairs) * 8, st));
+    ARB_CUDA(cudaMemcpyAsync(cstage.p, cand_rows, static_cast<size_t>(n_pairs) * 8, cudaMemcpyHostToDevice, st));
+    d_cand = cstage.as<int64_t>();
+  }
+  float* d_out = out;
+  if (!out_is_device) { ARB_CUDA(obuf.alloc(static_cast<size_t>(n_pairs) * 4, st)); d_out = obuf.as<float>(); }
+  score_rows_kernel<<<static_cast<unsigned>((n_pairs + 7) / 8), 256, 0, st>>>(ix->rows, ix->n, ix->planes, qplanes.as<__nv_bfloat16>(),
+                                                                             query_planes, ix->d_pad, d_cand, nq, nc, clamp_nonneg, d_out);
+  ARB_LAUNCH_OK();
+  if (!out_is_device) {
+    ARB_CUDA(cudaMemcpyAsync(out, d_out, static_cast<size_t>(n_pairs) * 4, cudaMemcpyDeviceToHost, st));
+    ARB_CUDA(cudaStreamSynchronize(st));
+  }
+  return ARB_OK;
+}

@@ -306,6 +306,66 @@ int merge_topk_device(int score_dtype, const void* scores, const int64_t* ids, i
   return ARB_OK;
 }
 
+
+// ----------------------------------------------------------------------------
+// Candidate re-scoring of the live pipeline (reference QueryProcessor._hybrid_search,
+// query/query_processor.py:3681-3768): per query a list of nc candidates with a vector
+// similarity and a BM25 score each, guard flags computed by the host from the note text,
+// linear or RRF fusion in fp64 with exactly the reference's operation order, then a stable
+// descending sort.  One CTA per query; ranks are counted (O(nc^2 / threads)), nc <= 4096.
+// ----------------------------------------------------------------------------
+constexpr int RESCORE_MAXC = 4096;
+__global__ void __launch_bounds__(256)
+rescore_kernel(int method, int nc, const double* __restrict__ vec, const double* __restrict__ bm,
+               const int32_t* __restrict__ n_cand, const uint8_t* __restrict__ must_miss,
+               const uint8_t* __restrict__ n_ent, const uint8_t* __restrict__ n_pred, double vw, double bw, double rrf_k,
+               double* __restrict__ out_score, int32_t* __restrict__ out_order) {
+  extern __shared__ __align__(16) uint8_t rs_smem[];
+  double* sv = reinterpret_cast<double*>(rs_smem);              // [nc] vector similarity
+  double* sb = sv + nc;                                         // [nc] bm25 score
+  double* sf = sb + nc;                                         // [nc] fused score
+  const int64_t q = blockIdx.x;
+  const int n = n_cand ? min(nc, max(0, n_cand[q])) : nc;
+  const size_t base = static_cast<size_t>(q) * nc;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) { sv[i] = vec[base + i]; sb[i] = bm[base + i]; }
+  __syncthreads();
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    double f;
+    if (method == ARB_FUSE_LINEAR) {                              // :3709-3737
+      double v = sv[i], b = sb[i];
+      if (must_miss[base + i]) b = __dmul_rn(b, 0.1);
+      for (int e = 0; e < n_ent[base + i]; ++e) v = __dmul_rn(v, 1.2);
+      for (int e = 0; e < n_pred[base + i]; ++e) b = __dmul_rn(b, 1.3);
+      f = __dadd_rn(__dmul_rn(vw, v), __dmul_rn(bw, b));
+    } else {                                                      // :3739-3757: 0-based stable descending ranks
+      const double v = sv[i], b = sb[i];
+      int rv = 0, rb = 0;
+      for (int j = 0; j < n; ++j) {
+        const double vj = sv[j], bj = sb[j];
+        rv += (vj > v || (vj == v && j < i)) ? 1 : 0;
+        rb += (bj > b || (bj == b && j < i)) ? 1 : 0;
+      }
+      f = __dadd_rn(__ddiv_rn(vw, __dadd_rn(rrf_k, static_cast<double>(rv))),
+                    __ddiv_rn(bw, __dadd_rn(rrf_k, static_cast<double>(rb))));
+      if (must_miss[base + i]) f = __dmul_rn(f, 0.1);
+    }
+    sf[i] = f;
+    out_score[base + i] = f;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < nc; i += blockDim.x) {            // :3760 stable sort, descending
+    if (i < n) {
+      const double f = sf[i];
+      int r = 0;
+      for (int j = 0; j < n; ++j) { const double fj = sf[j]; r += (fj > f || (fj == f && j < i)) ? 1 : 0; }
+      out_order[base + r] = i;
+    } else {
+      out_order[base + i] = -1;
+      out_score[base + i] = 0.0;
+    }
+  }
+}
+
 }  // namespace arb
 
 using namespace arb;
@@ -377,5 +437,25 @@ extern "C" int arb_fuse(int method, const double weights[4], double rrf_k, int p
     ARB_CUDA(cudaMemcpyAsync(out_count, p.out_count, static_cast<size_t>(nq) * 4, cudaMemcpyDeviceToHost, st));
     ARB_CUDA(cudaStreamSynchronize(st));
   }
+  return ARB_OK;
+}
+
+extern "C" int arb_rescore_candidates(int method, int64_t nq, int nc, const double* vec, const double* bm25,
+                                      const int32_t* n_cand, const uint8_t* must_miss, const uint8_t* n_ent,
+                                      const uint8_t* n_pred, double vector_weight, double bm25_weight, double rrf_k,
+                                      double* out_score, int32_t* out_order, void* stream) {
+  ARB_CHECK(method == ARB_FUSE_LINEAR || method == ARB_FUSE_RRF, ARB_EINVAL, "arb_rescore_candidates: unknown method");
+  ARB_CHECK(nq >= 0 && nc >= 0 && nc <= RESCORE_MAXC, ARB_ELIMIT, "arb_rescore_candidates: at most 4096 candidates per query");
+  if (nq == 0 || nc == 0) return ARB_OK;
+  ARB_CHECK(vec && bm25 && must_miss && n_ent && n_pred && out_score && out_order, ARB_EINVAL, "arb_rescore_candidates: NULL argument");
+  static std::once_flag once;
+  static cudaError_t err = cudaSuccess;
+  std::call_once(once, [] {
+    err = cudaFuncSetAttribute(rescore_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, RESCORE_MAXC * 24);
+  });
+  ARB_CUDA(err);
+  rescore_kernel<<<static_cast<unsigned>(nq), 256, static_cast<size_t>(nc) * 24, static_cast<cudaStream_t>(stream)>>>(
+      method, nc, vec, bm25, n_cand, must_miss, n_ent, n_pred, vector_weight, bm25_weight, rrf_k, out_score, out_order);
+  ARB_LAUNCH_OK();
   return ARB_OK;
 }

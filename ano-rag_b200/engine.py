@@ -134,6 +134,19 @@ class DenseIndex:
         return scores, ids
 
 
+    def score_rows(self, queries, cand_rows, query_planes: Optional[int] = None, clamp_nonneg: bool = True) -> np.ndarray:
+        """Similarity of query q with stored row cand_rows[q, c] -> fp32 [nq, nc] (host); rows < 0 score 0."""
+        if query_planes is None:
+            query_planes = 3 if self.storage == "fp32" else 1
+        b = _Buf(queries, (np.dtype(np.float32),), (torch.float32, torch.bfloat16) if torch is not None else (), "queries")
+        cand = np.ascontiguousarray(cand_rows, dtype=np.int64)
+        if len(b.shape) != 2 or b.shape[1] != self.dim or cand.ndim != 2 or cand.shape[0] != b.shape[0]:
+            raise ValueError("queries must be [nq, dim] and cand_rows [nq, nc]")
+        out = np.empty(cand.shape, dtype=np.float32)
+        nat.check(nat.lib.arb_index_score_rows(self._h, b.ptr, b.code, b.shape[0], b.is_device, cand.ctypes.data, cand.shape[1], 0,
+                                               query_planes, 1 if clamp_nonneg else 0, out.ctypes.data, 0, _stream_ptr(b.device)))
+        return out
+
     # -- IVF (IndexIVFFlat): the same handle, once it has centroids
     @property
     def nlist(self) -> int:

@@ -137,6 +137,45 @@ class VectorRetriever:
         emb = self.embedding_manager.encode_queries(queries)
         return self.vector_index.search_tensors(emb, top_k or self.top_k)
 
+    def calculate_vector_similarities(self, queries: List[str], notes_pools: List[List[Dict[str, Any]]]) -> List[List[float]]:
+        """Batched form of QueryProcessor._calculate_vector_similarities (reference query/query_processor.py:3543-3589):
+        cosine similarity of every query with every note of its candidate pool, clamped at 0.  Notes known to the
+        index are scored on the device from their stored embeddings (one gather kernel for the whole batch); a note
+        without a stored embedding is encoded from its content like the reference does (:3572-3581); 0.0 otherwise.
+        Never raises (:3587-3589)."""
+        try:
+            q_emb = self.embedding_manager.encode_queries(list(queries))
+            nq = len(queries)
+            nc = max((len(p) for p in notes_pools), default=0)
+            out = [[0.0] * len(p) for p in notes_pools]
+            if nq == 0 or nc == 0:
+                return out
+            cand = np.full((nq, nc), -1, dtype=np.int64)
+            dynamic = []
+            total = self.vector_index.total_vectors
+            for r, pool in enumerate(notes_pools):
+                for c, note in enumerate(pool):
+                    nid = note.get("note_id")
+                    idx = self.note_id_to_index.get(nid) if nid else None
+                    if idx is not None and idx < total:
+                        cand[r, c] = idx
+                    elif idx is None and note.get("content", ""):
+                        dynamic.append((r, c, note.get("content", "")))
+            if total > 0:
+                sims = self.vector_index.index.score_rows(self.vector_index._as_rows(q_emb), cand, clamp_nonneg=True)
+                for r, pool in enumerate(notes_pools):
+                    out[r] = [float(x) for x in sims[r, :len(pool)]]
+            if dynamic:
+                qn = np.asarray(q_emb.cpu() if torch is not None and isinstance(q_emb, torch.Tensor) else q_emb, dtype=np.float32)
+                emb = np.asarray(self.embedding_manager.encode_queries([t for _, _, t in dynamic]), dtype=np.float32)
+                for (r, c, _), e in zip(dynamic, emb):
+                    sim = np.dot(qn[r], e) / (np.linalg.norm(qn[r]) * np.linalg.norm(e))
+                    out[r][c] = float(max(0.0, sim))
+            return out
+        except Exception as e:
+            logger.error(f"Error calculating vector similarities: {e}")
+            return [[0.0] * len(p) for p in notes_pools]
+
     def search(self, queries: List[str], top_k: Optional[int] = None,
                similarity_threshold: Optional[float] = None,
                include_metadata: bool = True) -> List[List[Dict[str, Any]]]:

@@ -120,6 +120,14 @@ ARB_API int arb_index_search(const arb_index* index, const void* queries, int dt
                      int queries_is_device, int k, int query_planes, int64_t id_base,
                      float* out_scores, int64_t* out_ids, int out_is_device, void* stream);
 
+/* Per-candidate similarities (replaces the loop of QueryProcessor._calculate_vector_similarities,
+ * query/query_processor.py:3543-3589): out[q, c] = inner product of query q (pre-processed like a
+ * search query: L2-normalised when the index normalises) with stored row cand_rows[q, c]; with
+ * clamp_nonneg != 0 the result is max(0, .) (:3567); rows < 0 or >= ntotal score 0. */
+ARB_API int arb_index_score_rows(const arb_index* index, const void* queries, int dtype, int64_t nq,
+                         int queries_is_device, const int64_t* cand_rows, int nc, int cand_is_device,
+                         int query_planes, int clamp_nonneg, float* out, int out_is_device, void* stream);
+
 /* ------------------------------------------------------------------------- *
  * IVF: faiss.IndexIVFFlat(IndexFlatIP(d), d, nlist, METRIC_INNER_PRODUCT) behind VectorIndex
  * (vector_index.py:85-91 create, :126-169 train_index, :187-193 add_with_ids, :223 search with
@@ -208,6 +216,21 @@ ARB_API int arb_fuse(int method, const double weights[4], double rrf_k, int pool
              const int64_t* const ids[4], const void* const scores[4], const int score_dtype[4],
              const int k_src[4], int64_t* out_ids, double* out_final, double* out_src,
              int32_t* out_count, int is_device, void* stream);
+
+/* Candidate re-scoring of the live pipeline (replaces the fusion arithmetic and the sort of
+ * QueryProcessor._hybrid_search, query/query_processor.py:3709-3760).  Per query q, candidates
+ * i < n_cand[q] (NULL: all nc): `vec`/`bm25` [nq, nc] fp64 (missing scores = 0.0, :3712-3713);
+ * guard flags computed by the host from the note text (:3717-3733): must_miss (no must-have term in
+ * the content), n_ent / n_pred (matching boost entities / predicates, with multiplicity).
+ *   ARB_FUSE_LINEAR: b *= 0.1 if must_miss; v *= 1.2 per entity; b *= 1.3 per predicate; vw*v + bw*b
+ *   ARB_FUSE_RRF:    vw/(rrf_k + rank_v) + bw/(rrf_k + rank_b), 0-based stable descending ranks;
+ *                    *= 0.1 if must_miss
+ * out_score [nq, nc] in candidate order; out_order [nq, nc] = candidate indices by descending score
+ * (stable), -1 beyond n_cand.  All pointers are device pointers; nc <= 4096. */
+ARB_API int arb_rescore_candidates(int method, int64_t nq, int nc, const double* vec, const double* bm25,
+                           const int32_t* n_cand, const uint8_t* must_miss, const uint8_t* n_ent,
+                           const uint8_t* n_pred, double vector_weight, double bm25_weight, double rrf_k,
+                           double* out_score, int32_t* out_order, void* stream);
 
 /* ------------------------------------------------------------------------- *
  * Multi-GPU merge (new design): `parts` per-shard top-k lists,

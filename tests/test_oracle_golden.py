@@ -191,3 +191,18 @@ def test_bf16_helpers():
     assert np.array_equal((hi.astype(np.float64) + mid + lo).astype(np.float32), x)
     for p in (hi, mid, lo):
         assert np.array_equal(odense.bf16_round(p), p)
+
+
+def test_rescore_oracle_matches_reference_golden(golden_dir):
+    """QueryProcessor._hybrid_search arithmetic (query/query_processor.py:3681-3768), bit-exact."""
+    from oracle import rescore
+    with open(os.path.join(golden_dir, "rescore_golden.json")) as f:
+        golden = json.load(f)
+    assert len(golden["cases"]) >= 30
+    for case in golden["cases"]:
+        order, score = rescore.hybrid_search_rescore(
+            [float.fromhex(v) for v in case["vector"]], [float.fromhex(v) for v in case["bm25"]], case["contents"],
+            case["method"], case["vector_weight"], case["bm25_weight"], case["rrf_k"], case["must_have_terms"],
+            case["boost_entities"], case["boost_predicates"])
+        assert order == case["order"]
+        assert score == [float.fromhex(v) for v in case["hybrid_score"]]
