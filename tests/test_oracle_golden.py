@@ -206,3 +206,32 @@ def test_rescore_oracle_matches_reference_golden(golden_dir):
             case["boost_entities"], case["boost_predicates"])
         assert order == case["order"]
         assert score == [float.fromhex(v) for v in case["hybrid_score"]]
+
+
+def test_ivf_oracle_is_consistent_with_flat_oracle():
+    """IVF restatement: probing every list equals the flat search; fewer probes only ever drop rows; padding is -1."""
+    from oracle import dense as od
+    rng = np.random.default_rng(11)
+    x = od.preprocess_vectors(rng.standard_normal((600, 24)).astype(np.float32))
+    q = od.preprocess_vectors(rng.standard_normal((9, 24)).astype(np.float32))
+    cent = od.preprocess_vectors(rng.standard_normal((13, 24)).astype(np.float32))
+    assign = od.ivf_assign(x, cent)
+    assert assign.shape == (600,) and assign.min() >= 0 and assign.max() < 13
+    assert np.array_equal(assign, np.argmax(x @ cent.T, axis=1))
+    fs, fi = od.flat_ip_topk(q, x, 10)
+    s, i, probes = od.ivf_search(q, x, cent, assign, 10, 13)
+    assert np.array_equal(i, fi) and np.allclose(s, fs, atol=1e-6) and probes.shape == (9, 13)   # BLAS gemv vs gemm order
+    s3, i3, p3 = od.ivf_search(q, x, cent, assign, 10, 3)
+    for r in range(9):
+        allowed = set(np.flatnonzero(np.isin(assign, p3[r])).tolist())
+        got = [int(v) for v in i3[r] if v >= 0]
+        assert set(got) <= allowed and got == [int(v) for v in fi_restricted(q[r], x, sorted(allowed), 10)]
+    tiny = od.ivf_search(q[:1], x[:3], cent, assign[:3], 10, 13)
+    assert (tiny[1][0, 3:] == -1).all() and (tiny[0][0, 3:] == od.LOWEST_F32).all()
+
+
+def fi_restricted(qv, x, rows, k):
+    rows = np.asarray(rows)
+    s = x[rows] @ qv
+    order = np.lexsort((rows, -s.astype(np.float64)))[:k]
+    return rows[order]
