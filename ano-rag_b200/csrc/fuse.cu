@@ -191,10 +191,13 @@ fuse_kernel(const FuseParams p) {
   }
   __syncthreads();
 
-  // ---- stable descending sort: (final desc, traversal sequence asc)
-  for (int size = 2; size <= FUSE_MAXU; size <<= 1) {
+  // ---- stable descending sort: (final desc, traversal sequence asc), over the smallest power of two that
+  //      holds the union (the slots beyond it were initialised to "empty", which sorts last)
+  int n_sort = 32;
+  while (n_sort < s.n_union) n_sort <<= 1;
+  for (int size = 2; size <= n_sort; size <<= 1) {
     for (int stride = size >> 1; stride > 0; stride >>= 1) {
-      for (int i = tid; i < FUSE_MAXU / 2; i += FUSE_THREADS) {
+      for (int i = tid; i < n_sort / 2; i += FUSE_THREADS) {
         const int lo = 2 * i - (i & (stride - 1));
         const int hi = lo + stride;
         const bool best_first = ((lo & size) == 0);
