@@ -9,9 +9,9 @@ query/query_processor.py:1964,3706-3758) expressed over the same three component
 Sharding (new design): rank g holds rows [base_g, base_g + n_g) of
 the embedding matrix and the postings of exactly those docs, with corpus-GLOBAL
 BM25 statistics.  Per batch each rank computes its local top-k with global ids,
-one all-gather per source moves [world, nq, k] candidates over NVLink (NCCL), and
-every rank merges and fuses a slice of the queries (nq / world each), so the merge
-work is not replicated.
+one all-to-all per list moves, to every rank, the candidates of ITS slice of the
+queries (nq / world each) from all ranks over NVLink (NCCL), and the rank merges and fuses
+that slice, so neither the merge work nor the exchanged bytes are replicated.
 """
 from __future__ import annotations
 
@@ -42,10 +42,18 @@ class HybridPipeline:
             self.rank = torch.distributed.get_rank(group)
 
     # ------------------------------------------------------------------ device-resident inputs
-    def _gather(self, t: torch.Tensor) -> torch.Tensor:
-        out = torch.empty((self.world,) + tuple(t.shape), dtype=t.dtype, device=t.device)
-        torch.distributed.all_gather_into_tensor(out, t.contiguous(), group=self.group)
-        return out
+    def _exchange(self, t: torch.Tensor, pad) -> torch.Tensor:
+        """[nq, k] local lists -> [world, per, k]: from every rank, its lists for THIS rank's query slice.
+        An all-to-all moves only the slice each rank merges (1/world of what an all-gather would move)."""
+        nq, k = t.shape
+        per = (nq + self.world - 1) // self.world
+        send = t
+        if per * self.world != nq:
+            send = torch.full((per * self.world, k), pad, dtype=t.dtype, device=t.device)
+            send[:nq] = t
+        recv = torch.empty((self.world, per, k), dtype=t.dtype, device=t.device)
+        torch.distributed.all_to_all_single(recv, send.contiguous(), group=self.group)
+        return recv
 
     def search_device(self, q_emb: torch.Tensor, q_terms: Optional[torch.Tensor]):
         """q_emb [nq, d] CUDA (fp32 or bf16), q_terms [nq, max_qt] CUDA int32 (or None: dense only).
@@ -58,9 +66,11 @@ class HybridPipeline:
             b_sc, b_id = self.bm25.search(q_terms, self.k_bm25, id_base=self.id_base)
         if self.world > 1:
             lo, hi = self.query_slice(q_emb.shape[0])
-            d_sc, d_id = engine.merge_topk(self._gather(d_sc)[:, lo:hi].contiguous(), self._gather(d_id)[:, lo:hi].contiguous())
+            d_sc, d_id = engine.merge_topk(self._exchange(d_sc, float("-inf")), self._exchange(d_id, -1))
+            d_sc, d_id = d_sc[: hi - lo], d_id[: hi - lo]
             if b_sc is not None:
-                b_sc, b_id = engine.merge_topk(self._gather(b_sc)[:, lo:hi].contiguous(), self._gather(b_id)[:, lo:hi].contiguous())
+                b_sc, b_id = engine.merge_topk(self._exchange(b_sc, 0.0), self._exchange(b_id, -1))
+                b_sc, b_id = b_sc[: hi - lo], b_id[: hi - lo]
         return self.searcher.fuse_tensors(dense=(d_id, d_sc), bm25=(b_id, b_sc) if b_sc is not None else None,
                                           pool=self.pool)
 
