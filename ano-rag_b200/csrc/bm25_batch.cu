@@ -46,6 +46,19 @@ constexpr int PL_WARPS = 16;
 constexpr int PL_SMEM_MAX = 227 * 1024;             // planes tile + per-query records
 constexpr int E_CAP = 1024;                         // plane-pass emissions kept per query
 constexpr unsigned long long THR_SKIP = ~0ull;
+constexpr int H3_MAX = 1024;                        // queries per batch chunk that may take the histogram path
+constexpr int H3_BINS = 4096;                       // 128 bins per octave from 2^-12 up
+constexpr unsigned long long H3_TAG = 0xFFF8000000000000ull;   // qrec.x of a histogram query (a NaN pattern) | slot
+constexpr unsigned long long H3_BASE = (1ull << 18) | (static_cast<unsigned long long>(1023 - 12) << 7);
+// bin of a positive score: sign | exponent | 7 mantissa bits of its order-preserving key, clamped
+__device__ __forceinline__ int h3_bin(double v) {
+  const long long t = static_cast<long long>(f64_key(v) >> 45) - static_cast<long long>(H3_BASE);
+  return static_cast<int>(t < 0 ? 0 : (t > H3_BINS - 1 ? H3_BINS - 1 : t));
+}
+// smallest key of bin b (b >= 1); bin 0 also holds everything below 2^-12, so its edge is "any positive score"
+__device__ __forceinline__ unsigned long long h3_edge(int b) {
+  return b == 0 ? f64_key(0.0) + 1ull : (static_cast<unsigned long long>(b) + H3_BASE) << 45;
+}
 static_assert(SP_POOL >= SP_MAXM, "the pool holds at least the accumulators");
 
 // per-warp state of the sparse pass; CAP = candidate buffer (>= 2k + 32)
@@ -97,7 +110,11 @@ struct BatchScratch {
   int* pa_cnt;                 // [nq, parts]  entries, or -1 if the part overflowed its staging areas
   unsigned long long* gthr;    // [nq] largest k-th key any part of the query has reached so far (0 = none): a doc
                                // strictly below it cannot be in the query's top-k, whichever part it lies in
-  int* counters;               // [0] next query of the sparse pass, [1] number of flagged queries
+  int* counters;               // [0] next unit of the sparse pass, [1] number of flagged queries, [2] histogram queries
+  // queries whose list A holds fewer than k docs while they have plane tokens get their plane-pass threshold from
+  // a histogram of the plane-only scores of all their non-member docs (bm25_plane_list_kernel)
+  int* h3_list;                // [H3_MAX]
+  uint32_t* hist;              // [H3_MAX, H3_BINS]
 };
 
 // bitonic sort of n_pow2 (key, doc) pairs by (key desc, doc asc); one warp
@@ -503,9 +520,12 @@ bm25_a_merge_kernel(int64_t nq, int k, const int A_MERGE_CAP, const BatchScratch
   if (tid == 0) {
     const bool has_planes = sc.qd[q * sc.qd_stride] != 0xFF;
     sc.a_cnt[q] = cnt;
+    int h3 = H3_MAX;
     if (!has_planes && !s_ovf)   { sc.state[q] = 1; sc.thr[q] = THR_SKIP; }
     else if (cnt >= k && !s_ovf) { sc.state[q] = 0; sc.thr[q] = key[k - 1]; }
-    else {
+    else if (!s_ovf && (h3 = atomicAdd(&sc.counters[2], 1)) < H3_MAX) {
+      sc.state[q] = 3; sc.thr[q] = THR_SKIP; sc.h3_list[h3] = static_cast<int>(q);
+    } else {
       sc.state[q] = 2; sc.thr[q] = THR_SKIP;
       sc.flag_list[atomicAdd(&sc.counters[1], 1)] = static_cast<int>(q);
     }
@@ -580,9 +600,12 @@ bm25_a_merge_warp_kernel(int64_t nq, int k, const BatchScratch sc) {
     const bool has_planes = sc.qd[q * sc.qd_stride] != 0xFF;
     const bool bad = ovf || too_many;
     sc.a_cnt[q] = cnt;
+    int h3 = H3_MAX;
     if (!has_planes && !bad)   { sc.state[q] = 1; sc.thr[q] = THR_SKIP; }
     else if (cnt >= k && !bad) { sc.state[q] = 0; sc.thr[q] = W.okey[k - 1]; }
-    else {
+    else if (!bad && (h3 = atomicAdd(&sc.counters[2], 1)) < H3_MAX) {
+      sc.state[q] = 3; sc.thr[q] = THR_SKIP; sc.h3_list[h3] = static_cast<int>(q);
+    } else {
       sc.state[q] = 2; sc.thr[q] = THR_SKIP;
       sc.flag_list[atomicAdd(&sc.counters[1], 1)] = static_cast<int>(q);
     }
@@ -613,7 +636,12 @@ bm25_plane_pass_kernel(const Bm25Dev ix, int64_t nq, int64_t q_per_group, const 
   for (int64_t q = q0 + threadIdx.x; q < q1; q += PL_WARPS * 32) {
     const unsigned long long t = __ldg(sc.thr + q);
     ulonglong2 rec = make_ulonglong2(0ull, ~0ull);
-    if (t != THR_SKIP) {
+    if (sc.state[q] == 3) {                                    // no bound yet: this sweep fills its score histogram
+      int slot = 0;
+      const int n3 = min(sc.counters[2], H3_MAX);
+      while (slot < n3 && sc.h3_list[slot] != static_cast<int>(q)) ++slot;
+      if (slot < n3) rec = make_ulonglong2(H3_TAG | static_cast<unsigned long long>(slot), __ldg(qd64 + q * qw));
+    } else if (t != THR_SKIP) {
       const double thr_d = key_f64(t);
       double ub = 0.0;
       for (int i = 0; i < sc.qd_stride; ++i) {
@@ -650,8 +678,9 @@ bm25_plane_pass_kernel(const Bm25Dev ix, int64_t nq, int64_t q_per_group, const 
       unsigned long long pk = rec.y;
         uint32_t ps = static_cast<uint32_t>(pk) & 0xFFu;
         if (ps == 0xFFu) return;                             // skipped query (no plane tokens / fallback / bounded out)
-        const double thr_d = __longlong_as_double(static_cast<long long>(rec.x));
-        {
+        const bool hist = (rec.x & H3_TAG) == H3_TAG;
+        const double thr_d = hist ? 0.0 : __longlong_as_double(static_cast<long long>(rec.x));
+        if (!hist) {
           // this tile's bound for the query (same token order); all lanes read the same shared-memory words
           double ub = tmax_s[ps];
           unsigned long long pb = pk;
@@ -684,6 +713,13 @@ bm25_plane_pass_kernel(const Bm25Dev ix, int64_t nq, int64_t q_per_group, const 
         }
         // docs that reach A's k-th score (a positive fp64, so comparing doubles is comparing keys) and are not
         // members of the sparse pass
+        if (hist) {
+          uint32_t* H = sc.hist + static_cast<size_t>(rec.x & 0xFFFFu) * H3_BINS;
+  #pragma unroll
+          for (int r = 0; r < 8; ++r)
+            if (acc[r] > 0.0 && !((mb >> r) & 1u)) atomicAdd(&H[h3_bin(acc[r])], 1u);
+          return;
+        }
         uint32_t pass = 0u;
   #pragma unroll
         for (int r = 0; r < 8; ++r) if (acc[r] >= thr_d) pass |= 1u << r;
@@ -728,6 +764,117 @@ bm25_plane_pass_kernel(const Bm25Dev ix, int64_t nq, int64_t q_per_group, const 
       for (int u = 0; u < PF; ++u) cur[u] = nxt[u];
     }
   }
+}
+
+// The histogram path costs one extra sweep over all plane tiles; the per-query fallback costs ~13 us per query and
+// 16K-doc block.  With fewer than H3_MIN listed queries the fallback is cheaper: hand them over.  One block.
+constexpr int H3_MIN = 64;
+__global__ void __launch_bounds__(256)
+bm25_h3_decide_kernel(const BatchScratch sc) {
+  const int n3 = min(sc.counters[2], H3_MAX);
+  if (n3 == 0 || n3 >= H3_MIN) return;
+  for (int i = threadIdx.x; i < n3; i += blockDim.x) {
+    const int q = sc.h3_list[i];
+    sc.state[q] = 2;
+    sc.flag_list[atomicAdd(&sc.counters[1], 1)] = q;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) sc.counters[2] = 0;
+}
+
+// ----------------------------------------------------------------------------
+// 2b. plane pass over the (few) queries of h3_list.  HIST: histogram of the plane-only scores of their non-member
+// docs; otherwise: emission against the threshold that bm25_h3_threshold_kernel derived from the histogram.
+// All three launches return at once when the list is empty.
+// ----------------------------------------------------------------------------
+template <bool HIST>
+__global__ void __launch_bounds__(PL_WARPS * 32, 1)
+bm25_plane_list_kernel(const Bm25Dev ix, const BatchScratch sc) {
+  extern __shared__ __align__(16) double pll_smem[];           // [n_planes][256]
+  const int n3 = min(sc.counters[2], H3_MAX);
+  if (n3 == 0) return;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int P = ix.n_planes;
+  const uint32_t lt = (1u << lane) - 1u;
+  const uint8_t* bm_bytes = reinterpret_cast<const uint8_t*>(sc.bitmap);
+  for (int64_t tile = blockIdx.x; tile < ix.n_tiles; tile += gridDim.x) {
+    __syncthreads();
+    {
+      const double2* src = reinterpret_cast<const double2*>(ix.planes + tile * P * PLANE_TILE);
+      double2* dst = reinterpret_cast<double2*>(pll_smem);
+      for (int i = threadIdx.x; i < P * (PLANE_TILE / 2); i += PL_WARPS * 32) dst[i] = __ldg(src + i);
+    }
+    __syncthreads();
+    for (int idx = warp; idx < n3; idx += PL_WARPS) {
+      const int64_t q = sc.h3_list[idx];
+      double thr_d = 0.0;
+      if (!HIST) {
+        const unsigned long long t = sc.thr[q];
+        if (t == THR_SKIP) continue;
+        thr_d = key_f64(t);
+      }
+      double acc[8];
+#pragma unroll
+      for (int r = 0; r < 8; ++r) acc[r] = 0.0;
+      for (int i = 0; i < sc.qd_stride; ++i) {
+        const uint32_t ps = sc.qd[q * sc.qd_stride + i];
+        if (ps == 0xFFu) break;
+        const double2* row = reinterpret_cast<const double2*>(pll_smem + ps * PLANE_TILE) + lane;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const double2 v = row[j * 32];
+          acc[2 * j] = __dadd_rn(acc[2 * j], v.x);
+          acc[2 * j + 1] = __dadd_rn(acc[2 * j + 1], v.y);
+        }
+      }
+      const uint32_t mb = bm_bytes[(tile * sc.nq + q) * (PLANE_TILE / 8) + lane];
+#pragma unroll
+      for (int r = 0; r < 8; ++r) {
+        const bool ok = acc[r] > 0.0 && !((mb >> r) & 1u);
+        if (HIST) {
+          if (ok) atomicAdd(&sc.hist[static_cast<size_t>(idx) * H3_BINS + h3_bin(acc[r])], 1u);
+        } else {
+          const bool p = ok && acc[r] >= thr_d;
+          const uint32_t m = __ballot_sync(0xffffffffu, p);
+          if (m == 0u) continue;
+          int base = 0;
+          if (lane == 0) base = atomicAdd(&sc.e_cnt[q], __popc(m));
+          base = __shfl_sync(0xffffffffu, base, 0);
+          if (p) {
+            const int pos = base + __popc(m & lt);
+            if (pos < E_CAP) {
+              sc.e_key[q * E_CAP + pos] = f64_key(acc[r]);
+              sc.e_doc[q * E_CAP + pos] = static_cast<uint32_t>(tile * PLANE_TILE + 8 * lane + r);
+            }
+          }
+        }
+      }
+    }
+  }
+}
+
+// threshold = lower edge of the highest bin at which the count of scores at or above it reaches k
+// (every positive score when there are fewer); one warp per listed query
+__global__ void __launch_bounds__(128)
+bm25_h3_threshold_kernel(int k, const BatchScratch sc) {
+  const int n3 = min(sc.counters[2], H3_MAX);
+  const int lane = threadIdx.x & 31;
+  const int idx = blockIdx.x * 4 + (threadIdx.x >> 5);
+  if (idx >= n3) return;
+  const int64_t q = sc.h3_list[idx];
+  const int need = k;        // the members of A may all rank below the k best non-members
+  const uint32_t* H = sc.hist + static_cast<size_t>(idx) * H3_BINS;
+  int running = 0, bin = 0;
+  for (int c = H3_BINS / 32 - 1; c >= 0; --c) {
+    const int h = static_cast<int>(H[c * 32 + lane]);
+    int suf = h;                                               // suffix sum over lanes >= lane
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_down_sync(0xffffffffu, suf, o); if (lane + o < 32) suf += v; }
+    const uint32_t reach = __ballot_sync(0xffffffffu, running + suf >= need);
+    if (reach) { bin = c * 32 + (31 - __clz(reach)); break; }
+    running += __shfl_sync(0xffffffffu, suf, 0);
+  }
+  if (lane == 0) { sc.thr[q] = h3_edge(bin); sc.state[q] = 0; }
 }
 
 // ----------------------------------------------------------------------------
@@ -820,6 +967,10 @@ static int batch_set_attrs() {
     if (err == cudaSuccess)
       err = cudaFuncSetAttribute(bm25_plane_pass_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PL_SMEM_MAX);
     if (err == cudaSuccess)
+      err = cudaFuncSetAttribute(bm25_plane_list_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_PLANES * PLANE_TILE * 8);
+    if (err == cudaSuccess)
+      err = cudaFuncSetAttribute(bm25_plane_list_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_PLANES * PLANE_TILE * 8);
+    if (err == cudaSuccess)
       err = cudaFuncSetAttribute(bm25_flag_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 4096 * 16);
     if (err == cudaSuccess)
       err = cudaFuncSetAttribute(bm25_a_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 8192 * 12);
@@ -839,7 +990,7 @@ static int batch_chunk(const Bm25Dev& ix, const int32_t* d_terms, int64_t nq, in
   BatchScratch sc{};
   sc.bm_tiles = static_cast<int64_t>(ix.nb) * (DOC_BLOCK / PLANE_TILE);  // whole 16K-doc blocks
   sc.nq = nq;
-  AsyncBuf b_akey, b_adoc, b_i32, b_thr, b_u8, b_bitmap, b_ekey, b_edoc, b_pakey, b_padoc, b_pacnt, b_gthr;
+  AsyncBuf b_akey, b_adoc, b_i32, b_thr, b_u8, b_bitmap, b_ekey, b_edoc, b_pakey, b_padoc, b_pacnt, b_gthr, b_hist;
   sc.parts = static_cast<int>(std::min<int64_t>(ix.nb, 24));
   if (const char* v = std::getenv("ARB_BM25_PARTS")) sc.parts = std::max(1, std::min<int>(std::min<int64_t>(ix.nb, 32), atoi(v)));
   ARB_CUDA(b_pakey.alloc(static_cast<size_t>(nq) * sc.parts * k * 8, st));
@@ -853,7 +1004,7 @@ static int batch_chunk(const Bm25Dev& ix, const int32_t* d_terms, int64_t nq, in
   sc.pa_cnt = b_pacnt.as<int>();
   ARB_CUDA(b_akey.alloc(static_cast<size_t>(nq) * k * 8, st));
   ARB_CUDA(b_adoc.alloc(static_cast<size_t>(nq) * k * 4, st));
-  ARB_CUDA(b_i32.alloc((static_cast<size_t>(nq) * 3 + 2) * 4, st));       // e_cnt | counters | a_cnt | flag_list
+  ARB_CUDA(b_i32.alloc((static_cast<size_t>(nq) * 3 + 4 + H3_MAX) * 4, st));   // e_cnt | counters | a_cnt | flag_list | h3_list
   ARB_CUDA(b_thr.alloc(static_cast<size_t>(nq) * 8, st));
   sc.qd_stride = (mq + 7) & ~7;
   ARB_CUDA(b_u8.alloc(static_cast<size_t>(nq) * (sc.qd_stride + 8) + 16, st));
@@ -866,15 +1017,21 @@ static int batch_chunk(const Bm25Dev& ix, const int32_t* d_terms, int64_t nq, in
   sc.a_doc = b_adoc.as<uint32_t>();
   sc.e_cnt = b_i32.as<int>();
   sc.counters = sc.e_cnt + nq;
-  sc.a_cnt = sc.counters + 2;
+  sc.a_cnt = sc.counters + 4;
   sc.flag_list = sc.a_cnt + nq;
+  sc.h3_list = sc.flag_list + nq;
   sc.thr = b_thr.as<unsigned long long>();
   sc.qd = b_u8.as<uint8_t>();                                   // 8-byte aligned rows first
   sc.state = sc.qd + static_cast<size_t>(nq) * sc.qd_stride;
   sc.bitmap = planes ? b_bitmap.as<uint32_t>() : nullptr;
   sc.e_key = planes ? b_ekey.as<unsigned long long>() : nullptr;
   sc.e_doc = planes ? b_edoc.as<uint32_t>() : nullptr;
-  ARB_CUDA(cudaMemsetAsync(sc.e_cnt, 0, (static_cast<size_t>(nq) + 2) * 4, st));
+  ARB_CUDA(cudaMemsetAsync(sc.e_cnt, 0, (static_cast<size_t>(nq) + 4) * 4, st));
+  if (planes) {
+    ARB_CUDA(b_hist.alloc(static_cast<size_t>(H3_MAX) * H3_BINS * 4, st));
+    sc.hist = b_hist.as<uint32_t>();
+    ARB_CUDA(cudaMemsetAsync(sc.hist, 0, static_cast<size_t>(H3_MAX) * H3_BINS * 4, st));
+  }
 
   {
     ProfileScope ps(PROF_BM25_SPARSE, st);
@@ -900,6 +1057,8 @@ static int batch_chunk(const Bm25Dev& ix, const int32_t* d_terms, int64_t nq, in
   }
   if (planes) {
     ProfileScope ps(PROF_BM25_PLANES, st);
+    bm25_h3_decide_kernel<<<1, 256, 0, st>>>(sc);
+    ARB_LAUNCH_OK();
     // enough CTAs to fill the GPU: tile sets first, query groups when the corpus has few tiles
     const int64_t sets = std::min<int64_t>(ix.n_tiles, sms);
     const size_t plane_smem = static_cast<size_t>(ix.n_planes) * PLANE_TILE * 8;
@@ -911,6 +1070,11 @@ static int batch_chunk(const Bm25Dev& ix, const int32_t* d_terms, int64_t nq, in
     groups = (nq + qpg - 1) / qpg;
     dim3 grid(static_cast<unsigned>(sets), static_cast<unsigned>(groups));
     bm25_plane_pass_kernel<<<grid, PL_WARPS * 32, plane_smem + tmax_smem + static_cast<size_t>(qpg) * 16, st>>>(ix, nq, qpg, sc);
+    ARB_LAUNCH_OK();
+    // queries without a bound from list A: their score histogram was filled by the sweep above -> threshold -> emission
+    bm25_h3_threshold_kernel<<<H3_MAX / 4, 128, 0, st>>>(k, sc);
+    ARB_LAUNCH_OK();
+    bm25_plane_list_kernel<false><<<static_cast<unsigned>(sets), PL_WARPS * 32, plane_smem, st>>>(ix, sc);
     ARB_LAUNCH_OK();
   }
   {
@@ -946,7 +1110,7 @@ static int batch_chunk(const Bm25Dev& ix, const int32_t* d_terms, int64_t nq, in
     }
   }
   if (std::getenv("ARB_BM25_STATS")) {                           // diagnostics only: synchronises
-    std::vector<int> h(static_cast<size_t>(nq) + 2);
+    std::vector<int> h(static_cast<size_t>(nq) + 4);
     ARB_CUDA(cudaMemcpyAsync(h.data(), sc.e_cnt, h.size() * 4, cudaMemcpyDeviceToHost, st));
     ARB_CUDA(cudaStreamSynchronize(st));
     g_stats[0] += nq;
