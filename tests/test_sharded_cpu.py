@@ -64,3 +64,35 @@ def test_shard_range_covers_rows():
         spans = [sharded.shard_range(n, w, r) for r in range(w)]
         assert spans[0][0] == 0 and spans[-1][1] == n
         assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+
+
+def _exchange_worker(rank, world, port, nq, k, out):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from ano_rag_b200.pipeline import HybridPipeline
+        pipe = HybridPipeline.__new__(HybridPipeline)            # only the exchange logic: no device objects
+        pipe.world, pipe.rank, pipe.group = world, rank, None
+        local = torch.arange(nq * k, dtype=torch.int64).reshape(nq, k) + 1_000_000 * rank    # this rank's [nq, k] list
+        got = pipe._exchange(local, -1)
+        np.save(os.path.join(out, f"x{rank}.npy"), got.numpy())
+        np.save(os.path.join(out, f"s{rank}.npy"), np.array(pipe.query_slice(nq)))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("nq", [10, 7])
+def test_query_slice_exchange_world2(tmp_path, nq):
+    """all-to-all of query slices: rank r receives, from every rank, the rows of ITS slice (padded with -1)."""
+    world, k = 2, 3
+    mp.spawn(_exchange_worker, args=(world, _free_port(), nq, k, str(tmp_path)), nprocs=world, join=True)
+    per = (nq + world - 1) // world
+    for r in range(world):
+        got = np.load(os.path.join(str(tmp_path), f"x{r}.npy"))
+        lo, hi = np.load(os.path.join(str(tmp_path), f"s{r}.npy"))
+        assert got.shape == (world, per, k) and (lo, hi) == (min(nq, r * per), min(nq, (r + 1) * per))
+        for src in range(world):
+            want = np.arange(nq * k).reshape(nq, k)[lo:hi] + 1_000_000 * src
+            assert np.array_equal(got[src, : hi - lo], want)
+            assert (got[src, hi - lo:] == -1).all()
