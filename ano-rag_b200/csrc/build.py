@@ -40,18 +40,27 @@ def build(force=False, verbose=False):
     hdrs = [h if os.path.isabs(h) else os.path.join(HERE, h) for h in HEADERS]
     objs = []
     logs = []
+    jobs = []
     for src in SOURCES:
         sp = os.path.join(HERE, src)
         obj = os.path.join(HERE, src.replace(".cu", ".o"))
         objs.append(obj)
         if force or _newer(obj, [sp, __file__] + hdrs):
-            cmd = [nvcc] + ARCH + FLAGS + ["-c", sp, "-o", obj]
-            r = subprocess.run(cmd, capture_output=True, text=True)
-            logs.append(r.stderr)
-            if verbose:
-                print(" ".join(cmd)); print(r.stderr)
-            if r.returncode != 0:
-                raise RuntimeError(f"nvcc failed on {src}:\n{r.stdout}\n{r.stderr}")
+            jobs.append((src, [nvcc] + ARCH + FLAGS + ["-c", sp, "-o", obj]))
+
+    def compile_one(job):
+        src, cmd = job
+        return src, cmd, subprocess.run(cmd, capture_output=True, text=True)
+
+    if jobs:                                              # the translation units are independent: compile them in parallel
+        from concurrent.futures import ThreadPoolExecutor
+        with ThreadPoolExecutor(max_workers=min(len(jobs), os.cpu_count() or 1)) as pool:
+            for src, cmd, r in pool.map(compile_one, jobs):
+                logs.append(r.stderr)
+                if verbose:
+                    print(" ".join(cmd)); print(r.stderr)
+                if r.returncode != 0:
+                    raise RuntimeError(f"nvcc failed on {src}:\n{r.stdout}\n{r.stderr}")
     if force or _newer(LIB, objs):
         cmd = [nvcc] + ARCH + ["-shared", "-o", LIB] + objs + ["-cudart", "static"]
         r = subprocess.run(cmd, capture_output=True, text=True)
