@@ -161,3 +161,35 @@ def test_batched_pipeline_equals_per_query_kernel(n, v, nq, k, mean_len, planes,
         ws, wi = obm.topk_positive(ora.get_scores([t for t in qt[r] if t >= 0]), k)
         assert np.array_equal(i1[r], wi) and np.array_equal(s1[r], ws), f"query {r}"
     gpu.close()
+
+
+@pytest.mark.parametrize("n,v,nq,mq,k,mean_len", [(40_000, 3000, 70, 20, 1, 25), (33_333, 100_000, 128, 5, 17, 60),
+                                                  (25_000, 600, 90, 32, 100, 150), (70_001, 8000, 64, 8, 250, 10)])
+def test_batched_pipeline_shapes(n, v, nq, mq, k, mean_len, monkeypatch):
+    """Long queries (up to the 32-token limit of the pipeline), k = 1 and k near the maximum, a vocabulary larger than
+    the corpus (no planes worth having), long documents (large tf, > 4096 distinct (tf, dl) factors)."""
+    import ano_rag_b200  # noqa: F401
+    from ano_rag_b200 import synth
+    from ano_rag_b200.utils.bm25_search import GpuBM25
+    from oracle import bm25 as obm
+    ptr, tok = synth.bm25_corpus(n, v, mean_len, seed=n + mq)
+    rng = np.random.default_rng(mq)
+    cdf = synth.zipf_cdf(v)
+    qt = np.clip(np.searchsorted(cdf, rng.random((nq, mq))), 0, v - 1).astype(np.int32)
+    docs = rng.integers(0, n, nq)
+    for r in range(nq):                                          # half of the tokens come from a real document
+        d = tok[ptr[docs[r]]:ptr[docs[r] + 1]]
+        qt[r, : mq // 2] = rng.choice(d, mq // 2)
+    qt[1, 3:] = -1
+    qt[2, ::2] = qt[2, 0]                                        # heavy duplication
+    gpu = GpuBM25.from_token_ids(ptr, tok, v, variant="okapi")
+    monkeypatch.setenv("ARB_BM25_MODE", "query")
+    s0, i0 = gpu.search_terms(qt, k)
+    monkeypatch.setenv("ARB_BM25_MODE", "batch")
+    s1, i1 = gpu.search_terms(qt, k)
+    assert np.array_equal(i0, i1) and np.array_equal(s0, s1)
+    ora = obm.ArrayBM25Oracle(ptr, tok, variant="okapi")
+    for r in (0, 1, 2, nq - 1):
+        ws, wi = obm.topk_positive(ora.get_scores([t for t in qt[r] if t >= 0]), k)
+        assert np.array_equal(i1[r], wi) and np.array_equal(s1[r], ws), f"query {r}"
+    gpu.close()
