@@ -85,6 +85,8 @@ _SIGS = {
                                        c_double, c_double, c_double, c_void_p, c_void_p, c_void_p]),
     "arb_merge_topk": (c_int, [c_int, c_void_p, c_void_p, c_int, c_int64, c_int, c_int, c_void_p, c_void_p,
                                c_void_p]),
+    "arb_merge_topk_peers": (c_int, [c_int, POINTER(c_void_p), POINTER(c_void_p), c_int, c_int64, c_int64, c_int,
+                                     c_void_p, c_void_p, c_void_p]),
 }
 for _name, (_res, _args) in _SIGS.items():
     _fn = getattr(lib, _name)          # AttributeError here = ABI mismatch, fail loudly

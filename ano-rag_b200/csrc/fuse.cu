@@ -239,10 +239,20 @@ fuse_kernel(const FuseParams p) {
 // ----------------------------------------------------------------------------
 // merge: scores/ids [parts, nq, k] -> [nq, k]; descending score, ascending id.
 // ----------------------------------------------------------------------------
-template <typename T>
+// With PEERS the lists of part p start at src.scores[p] / src.ids[p] (one [rows, k] array per GPU, read over
+// NVLink through peer-mapped symmetric memory) and query q of this launch is row row0 + q of each of them.
+constexpr int MERGE_MAX_PEERS = 16;
+struct MergePeers {
+  const void* scores[MERGE_MAX_PEERS];
+  const int64_t* ids[MERGE_MAX_PEERS];
+  int64_t row0;
+};
+
+template <typename T, bool PEERS>
 __global__ void __launch_bounds__(256)
 merge_topk_kernel(const T* __restrict__ scores, const int64_t* __restrict__ ids, int parts, int64_t nq, int k,
-                  int n_pow2, T* __restrict__ out_scores, int64_t* __restrict__ out_ids, T pad_score) {
+                  int n_pow2, T* __restrict__ out_scores, int64_t* __restrict__ out_ids, T pad_score,
+                  const __grid_constant__ MergePeers src) {
   extern __shared__ __align__(16) uint8_t msm[];
   unsigned long long* key = reinterpret_cast<unsigned long long*>(msm);
   int64_t* id = reinterpret_cast<int64_t*>(msm + static_cast<size_t>(n_pow2) * 8);
@@ -253,8 +263,11 @@ merge_topk_kernel(const T* __restrict__ scores, const int64_t* __restrict__ ids,
     unsigned long long kk = 0ull; int64_t ii = 0x7fffffffffffffffll;
     if (i < m) {
       const int part = i / k, j = i % k;
-      const int64_t v = ids[(static_cast<int64_t>(part) * nq + q) * k + j];
-      if (v >= 0) { ii = v; kk = f64_key(static_cast<double>(scores[(static_cast<int64_t>(part) * nq + q) * k + j])); }
+      const int64_t at = PEERS ? (src.row0 + q) * k + j : (static_cast<int64_t>(part) * nq + q) * k + j;
+      const int64_t* pi = PEERS ? src.ids[part] : ids;
+      const T* ps = PEERS ? static_cast<const T*>(src.scores[part]) : scores;
+      const int64_t v = pi[at];
+      if (v >= 0) { ii = v; kk = f64_key(static_cast<double>(ps[at])); }
     }
     key[i] = kk; id[i] = ii;
   }
@@ -280,8 +293,8 @@ merge_topk_kernel(const T* __restrict__ scores, const int64_t* __restrict__ ids,
   }
 }
 
-int merge_topk_device(int score_dtype, const void* scores, const int64_t* ids, int parts, int64_t nq, int k,
-                      void* out_scores, int64_t* out_ids, cudaStream_t st) {
+static int merge_topk_launch(int score_dtype, const void* scores, const int64_t* ids, const MergePeers* peers, int parts,
+                             int64_t nq, int k, void* out_scores, int64_t* out_ids, cudaStream_t st) {
   ARB_CHECK(score_dtype == ARB_F32 || score_dtype == ARB_F64, ARB_EINVAL, "merge_topk: score dtype must be f32 or f64");
   ARB_CHECK(parts >= 1 && k >= 1 && nq >= 0, ARB_EINVAL, "merge_topk: bad shape");
   const int64_t m = static_cast<int64_t>(parts) * k;
@@ -293,20 +306,39 @@ int merge_topk_device(int score_dtype, const void* scores, const int64_t* ids, i
   static std::once_flag once;
   static cudaError_t err = cudaSuccess;
   std::call_once(once, [] {
-    err = cudaFuncSetAttribute(merge_topk_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8192 * 16);
-    if (err == cudaSuccess)
-      err = cudaFuncSetAttribute(merge_topk_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8192 * 16);
+    const void* fns[4] = {reinterpret_cast<const void*>(merge_topk_kernel<float, false>),
+                          reinterpret_cast<const void*>(merge_topk_kernel<double, false>),
+                          reinterpret_cast<const void*>(merge_topk_kernel<float, true>),
+                          reinterpret_cast<const void*>(merge_topk_kernel<double, true>)};
+    for (int i = 0; i < 4 && err == cudaSuccess; ++i)
+      err = cudaFuncSetAttribute(fns[i], cudaFuncAttributeMaxDynamicSharedMemorySize, 8192 * 16);
   });
   ARB_CUDA(err);
-  if (score_dtype == ARB_F32)
-    merge_topk_kernel<float><<<static_cast<unsigned>(nq), 256, smem, st>>>(
-        static_cast<const float*>(scores), ids, parts, nq, k, n_pow2, static_cast<float*>(out_scores), out_ids,
-        -3.4028234663852886e38f);
-  else
-    merge_topk_kernel<double><<<static_cast<unsigned>(nq), 256, smem, st>>>(
-        static_cast<const double*>(scores), ids, parts, nq, k, n_pow2, static_cast<double*>(out_scores), out_ids, 0.0);
+  const unsigned grid = static_cast<unsigned>(nq);
+  const MergePeers none{};
+  if (score_dtype == ARB_F32) {
+    const float pad = -3.4028234663852886e38f;
+    if (peers)
+      merge_topk_kernel<float, true><<<grid, 256, smem, st>>>(nullptr, nullptr, parts, nq, k, n_pow2,
+                                                             static_cast<float*>(out_scores), out_ids, pad, *peers);
+    else
+      merge_topk_kernel<float, false><<<grid, 256, smem, st>>>(static_cast<const float*>(scores), ids, parts, nq, k, n_pow2,
+                                                              static_cast<float*>(out_scores), out_ids, pad, none);
+  } else {
+    if (peers)
+      merge_topk_kernel<double, true><<<grid, 256, smem, st>>>(nullptr, nullptr, parts, nq, k, n_pow2,
+                                                              static_cast<double*>(out_scores), out_ids, 0.0, *peers);
+    else
+      merge_topk_kernel<double, false><<<grid, 256, smem, st>>>(static_cast<const double*>(scores), ids, parts, nq, k, n_pow2,
+                                                               static_cast<double*>(out_scores), out_ids, 0.0, none);
+  }
   ARB_LAUNCH_OK();
   return ARB_OK;
+}
+
+int merge_topk_device(int score_dtype, const void* scores, const int64_t* ids, int parts, int64_t nq, int k,
+                      void* out_scores, int64_t* out_ids, cudaStream_t st) {
+  return merge_topk_launch(score_dtype, scores, ids, nullptr, parts, nq, k, out_scores, out_ids, st);
 }
 
 
@@ -372,6 +404,23 @@ rescore_kernel(int method, int nc, const double* __restrict__ vec, const double*
 }  // namespace arb
 
 using namespace arb;
+
+extern "C" int arb_merge_topk_peers(int score_dtype, const void* const* part_scores, const int64_t* const* part_ids,
+                                    int parts, int64_t row0, int64_t nq, int k, void* out_scores, int64_t* out_ids,
+                                    void* stream) {
+  ARB_CHECK(part_scores && part_ids && out_scores && out_ids, ARB_EINVAL, "arb_merge_topk_peers: NULL argument");
+  ARB_CHECK(parts >= 1 && parts <= MERGE_MAX_PEERS, ARB_ELIMIT, "arb_merge_topk_peers: 1 <= parts <= 16");
+  ARB_CHECK(row0 >= 0, ARB_EINVAL, "arb_merge_topk_peers: row0 < 0");
+  MergePeers p{};
+  for (int i = 0; i < parts; ++i) {
+    ARB_CHECK(part_scores[i] && part_ids[i], ARB_EINVAL, "arb_merge_topk_peers: NULL list pointer");
+    p.scores[i] = part_scores[i];
+    p.ids[i] = part_ids[i];
+  }
+  p.row0 = row0;
+  return merge_topk_launch(score_dtype, nullptr, nullptr, &p, parts, nq, k, out_scores, out_ids,
+                           static_cast<cudaStream_t>(stream));
+}
 
 extern "C" int arb_merge_topk(int score_dtype, const void* scores, const int64_t* ids, int parts, int64_t nq, int k,
                               int positive_only, void* out_scores, int64_t* out_ids, void* stream) {

@@ -112,8 +112,9 @@ class DenseIndex:
         nat.check(nat.lib.arb_index_reconstruct(self._h, row0, n, out.ctypes.data, 0, _stream_ptr()))
         return out
 
-    def search(self, queries, k: int, query_planes: Optional[int] = None, id_base: int = 0):
-        """-> (scores fp32 [nq,k], ids int64 [nq,k]); numpy in -> numpy out, CUDA tensor in -> CUDA tensors out."""
+    def search(self, queries, k: int, query_planes: Optional[int] = None, id_base: int = 0, out=None):
+        """-> (scores fp32 [nq,k], ids int64 [nq,k]); numpy in -> numpy out, CUDA tensor in -> CUDA tensors out.
+        out = (scores, ids): contiguous CUDA tensors to write into (device queries only)."""
         if query_planes is None:
             query_planes = 3 if self.storage == "fp32" else 1
         b = _Buf(queries, (np.dtype(np.float32),), (torch.float32, torch.bfloat16) if torch is not None else (), "queries")
@@ -122,8 +123,7 @@ class DenseIndex:
         nq = b.shape[0]
         if b.is_device:
             with torch.cuda.device(b.device):
-                scores = torch.empty((nq, k), dtype=torch.float32, device=b.device)
-                ids = torch.empty((nq, k), dtype=torch.int64, device=b.device)
+                scores, ids = _out_lists(out, nq, k, torch.float32, b.device)
                 nat.check(nat.lib.arb_index_search(self._h, b.ptr, b.code, nq, 1, k, query_planes, id_base,
                                                    scores.data_ptr(), ids.data_ptr(), 1, _stream_ptr(b.device)))
             return scores, ids
@@ -243,14 +243,14 @@ class BM25Index:
             raise ValueError("q_terms must be [nq, max_qt]")
         return b
 
-    def search(self, q_terms, k: int, id_base: int = 0):
-        """-> (scores fp64 [nq,k], ids int64 [nq,k]) descending, -1 padded."""
+    def search(self, q_terms, k: int, id_base: int = 0, out=None):
+        """-> (scores fp64 [nq,k], ids int64 [nq,k]) descending, -1 padded.
+        out = (scores, ids): contiguous CUDA tensors to write into (device queries only)."""
         b = self._terms(q_terms)
         nq, mq = b.shape
         if b.is_device:
             with torch.cuda.device(b.device):
-                scores = torch.empty((nq, k), dtype=torch.float64, device=b.device)
-                ids = torch.empty((nq, k), dtype=torch.int64, device=b.device)
+                scores, ids = _out_lists(out, nq, k, torch.float64, b.device)
                 nat.check(nat.lib.arb_bm25_search(self._h, b.ptr, nq, mq, 1, k, id_base, scores.data_ptr(),
                                                   ids.data_ptr(), 1, _stream_ptr(b.device)))
             return scores, ids
@@ -361,6 +361,33 @@ def fuse_batch(method: str, weights, rrf_k: float, pool: int, dense=None, bm25=N
     nat.check(nat.lib.arb_fuse(code, wv, float(rrf_k), pool, nq, ids_p, sc_p, dt, ks, o_ids.ctypes.data,
                                o_fin.ctypes.data, o_src.ctypes.data, o_cnt.ctypes.data, 0, _stream_ptr()))
     return o_ids, o_fin, o_src, o_cnt
+
+
+def _out_lists(out, nq, k, score_dtype, device):
+    if out is None:
+        return (torch.empty((nq, k), dtype=score_dtype, device=device),
+                torch.empty((nq, k), dtype=torch.int64, device=device))
+    scores, ids = out
+    for t, dt in ((scores, score_dtype), (ids, torch.int64)):
+        if not (t.is_cuda and t.device == device and t.dtype == dt and tuple(t.shape) == (nq, k) and t.is_contiguous()):
+            raise ValueError(f"out tensors must be contiguous CUDA [{nq}, {k}] {score_dtype} / int64 on {device}")
+    return scores, ids
+
+
+def merge_topk_peers(score_ptrs, id_ptrs, score_dtype, row0: int, nq: int, k: int, device):
+    """Merge rows [row0, row0 + nq) of `parts` per-GPU [rows, k] lists given by raw (peer-mapped) device
+    addresses -> ([nq,k], [nq,k]) on `device`; see arb_merge_topk_peers."""
+    import ctypes
+    parts = len(score_ptrs)
+    code = nat.ARB_F32 if score_dtype == torch.float32 else nat.ARB_F64
+    sp = (ctypes.c_void_p * parts)(*score_ptrs)
+    ip = (ctypes.c_void_p * parts)(*id_ptrs)
+    with torch.cuda.device(device):
+        o_s = torch.empty((nq, k), dtype=score_dtype, device=device)
+        o_i = torch.empty((nq, k), dtype=torch.int64, device=device)
+        nat.check(nat.lib.arb_merge_topk_peers(code, sp, ip, parts, row0, nq, k, o_s.data_ptr(), o_i.data_ptr(),
+                                               _stream_ptr(device)))
+    return o_s, o_i
 
 
 def merge_topk(scores, ids):

@@ -15,6 +15,7 @@ that slice, so neither the merge work nor the exchanged bytes are replicated.
 """
 from __future__ import annotations
 
+import os
 from typing import Optional
 
 import numpy as np
@@ -22,6 +23,52 @@ import torch
 
 from . import engine
 from .retrieval.hybrid_search import HybridSearcher
+
+
+class PeerLists:
+    """Home of one rank's local top-k lists in NVLink peer-mapped symmetric memory (torch symmetric memory is
+    the allocator / rendezvous; the data path is the merge kernel's own loads from the peers' buffers).
+
+    Two buffer sets alternate between batches: a rank starts writing set A for batch i+2 only after passing
+    the barrier of batch i+1, which every rank reaches only after its merge of batch i (the last reader of
+    set A) was enqueued before it on the same stream -- so one barrier per batch is enough."""
+
+    _ALIGN = 256
+
+    def __init__(self, group, nq: int, k_dense: int, k_bm25: int, device: torch.device):
+        import torch.distributed._symmetric_memory as symm
+        self.nq, self.k_dense, self.k_bm25 = int(nq), int(k_dense), int(k_bm25)
+        sizes = [nq * k_dense * 4, nq * k_dense * 8, nq * k_bm25 * 8, nq * k_bm25 * 8]
+        self.offs, at = [], 0
+        for b in sizes:
+            self.offs.append(at)
+            at += (b + self._ALIGN - 1) // self._ALIGN * self._ALIGN
+        self.set_bytes = at
+        group = group if group is not None else torch.distributed.group.WORLD
+        with torch.cuda.device(device):
+            self.buf = symm.empty(2 * self.set_bytes, dtype=torch.uint8, device=device)
+            self.hdl = symm.rendezvous(self.buf, group)
+        self.peer_ptrs = [int(p) for p in self.hdl.buffer_ptrs]
+        self.turn = 0
+
+    def _view(self, which: int, dtype, k: int, nq: int) -> torch.Tensor:
+        lo = self.turn * self.set_bytes + self.offs[which]
+        return self.buf[lo: lo + nq * k * dtype.itemsize].view(dtype).view(nq, k)
+
+    def dense_out(self, nq: int):
+        return self._view(0, torch.float32, self.k_dense, nq), self._view(1, torch.int64, self.k_dense, nq)
+
+    def bm25_out(self, nq: int):
+        return self._view(2, torch.float64, self.k_bm25, nq), self._view(3, torch.int64, self.k_bm25, nq)
+
+    def ptrs(self, which: int):
+        return [p + self.turn * self.set_bytes + self.offs[which] for p in self.peer_ptrs]
+
+    def barrier(self):
+        self.hdl.barrier(channel=0)
+
+    def flip(self):
+        self.turn ^= 1
 
 
 class HybridPipeline:
@@ -40,6 +87,10 @@ class HybridPipeline:
         if group is not None or (torch.distributed.is_available() and torch.distributed.is_initialized()):
             self.world = torch.distributed.get_world_size(group)
             self.rank = torch.distributed.get_rank(group)
+        # cross-GPU exchange: "peer" = merge kernel loads from peer-mapped symmetric memory (default, <= 16 ranks),
+        # "nccl" = all-to-all of query slices followed by the merge
+        self.exchange = os.environ.get("ARB_EXCHANGE", "peer" if self.world <= 16 else "nccl")
+        self._peer: Optional[PeerLists] = None
 
     # ------------------------------------------------------------------ device-resident inputs
     def _exchange(self, t: torch.Tensor, pad) -> torch.Tensor:
@@ -60,9 +111,28 @@ class HybridPipeline:
         -> (ids [nq,pool] int64, final [nq,pool] fp64, src [nq,pool,4] fp64, count [nq] int32) on the device.
         With world > 1 every rank returns the rows of its own query slice
         [rank*ceil(nq/world), ...) -- see ``query_slice``."""
+        nq = q_emb.shape[0]
+        with_bm25 = self.bm25 is not None and q_terms is not None
+        if self.world > 1 and self.exchange == "peer":
+            peer = self._peer_lists(nq)
+            lo, hi = self.query_slice(nq)
+            self.dense.search(q_emb, self.k_dense, query_planes=self.query_planes, id_base=self.id_base,
+                              out=peer.dense_out(nq))
+            if with_bm25:
+                self.bm25.search(q_terms, self.k_bm25, id_base=self.id_base, out=peer.bm25_out(nq))
+            peer.barrier()                       # every rank's lists are written and visible
+            d_sc, d_id = engine.merge_topk_peers(peer.ptrs(0), peer.ptrs(1), torch.float32, lo, hi - lo,
+                                                 self.k_dense, self.device)
+            b_sc = b_id = None
+            if with_bm25:
+                b_sc, b_id = engine.merge_topk_peers(peer.ptrs(2), peer.ptrs(3), torch.float64, lo, hi - lo,
+                                                     self.k_bm25, self.device)
+            peer.flip()
+            return self.searcher.fuse_tensors(dense=(d_id, d_sc), bm25=(b_id, b_sc) if with_bm25 else None,
+                                              pool=self.pool)
         d_sc, d_id = self.dense.search(q_emb, self.k_dense, query_planes=self.query_planes, id_base=self.id_base)
         b_sc = b_id = None
-        if self.bm25 is not None and q_terms is not None:
+        if with_bm25:
             b_sc, b_id = self.bm25.search(q_terms, self.k_bm25, id_base=self.id_base)
         if self.world > 1:
             lo, hi = self.query_slice(q_emb.shape[0])
@@ -73,6 +143,13 @@ class HybridPipeline:
                 b_sc, b_id = b_sc[: hi - lo], b_id[: hi - lo]
         return self.searcher.fuse_tensors(dense=(d_id, d_sc), bm25=(b_id, b_sc) if b_sc is not None else None,
                                           pool=self.pool)
+
+    def _peer_lists(self, nq: int) -> PeerLists:
+        """(Re)allocate the symmetric buffers; collective, and every rank sees the same nq."""
+        if self._peer is None or self._peer.nq < nq:
+            torch.cuda.synchronize(self.device)
+            self._peer = PeerLists(self.group, nq, self.k_dense, self.k_bm25, self.device)
+        return self._peer
 
     def query_slice(self, nq: int):
         if self.world == 1:

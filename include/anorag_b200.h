@@ -241,6 +241,15 @@ ARB_API int arb_merge_topk(int score_dtype, const void* scores, const int64_t* i
                    int64_t nq, int k, int positive_only, void* out_scores, int64_t* out_ids,
                    void* stream);
 
+/* The same merge without the NCCL exchange (new design): part p's lists start at part_scores[p] /
+ * part_ids[p] -- one [rows, k] array per GPU, peer-mapped (CUDA IPC / symmetric memory), so the kernel
+ * loads the other shards' candidates straight over NVLink -- and query q of this call is row row0 + q
+ * of every part.  part_scores / part_ids are HOST arrays of `parts` (<= 16) device pointers.  The caller
+ * orders the peers' writes before this launch (a cross-GPU barrier on `stream`). */
+ARB_API int arb_merge_topk_peers(int score_dtype, const void* const* part_scores, const int64_t* const* part_ids,
+                         int parts, int64_t row0, int64_t nq, int k, void* out_scores, int64_t* out_ids,
+                         void* stream);
+
 #ifdef __cplusplus
 }
 #endif

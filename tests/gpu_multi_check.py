@@ -32,7 +32,25 @@ for method in ("rrf", "linear"):
     arr = bb.build_arrays(sptr, stok, V, stats=stats)
     bm = engine.BM25Index(hi - lo, arr.term_ptr, arr.post_doc, arr.post_gcode, stats.idf, arr.gtab)
     pipe = HybridPipeline(dense, bm, HybridSearcher(cfg), k_dense=K, k_bm25=K, pool=K, id_base=lo, query_planes=1, device=dev)
-    ids, fin, src, cnt = pipe.search_device(q, qt)
+    res = {}
+    for ex in ("peer", "nccl"):                             # NVLink peer-load merge vs NCCL all-to-all + merge
+        pipe.exchange = ex
+        for _ in range(3):
+            res[ex] = pipe.search_device(q, qt)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        dist.barrier(); torch.cuda.synchronize(); e0.record()
+        for _ in range(20):
+            res[ex] = pipe.search_device(q, qt)
+        e1.record(); torch.cuda.synchronize()
+        if rank == 0:
+            print(f"[{method}] exchange={ex}: {e0.elapsed_time(e1) / 20:.3f} ms/batch", flush=True)
+    same_ex = all(bool((a == b).all().item()) for a, b in zip(res["peer"][:2], res["nccl"][:2]))
+    same_ex &= bool((res["peer"][3] == res["nccl"][3]).all().item())
+    flag = torch.tensor([int(same_ex)], device=dev); dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    if rank == 0:
+        print(f"[{method}] peer exchange == nccl exchange on every rank: {bool(flag.item())}", flush=True)
+    ok &= bool(flag.item())
+    ids, fin, src, cnt = res["peer"]
     qlo, qhi = pipe.query_slice(Q)
     # gather every rank's slice on rank 0
     per = (Q + world - 1) // world
