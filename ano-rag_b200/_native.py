@@ -83,6 +83,11 @@ _SIGS = {
                          POINTER(c_int), POINTER(c_int), c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
     "arb_rescore_candidates": (c_int, [c_int, c_int64, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                        c_double, c_double, c_double, c_void_p, c_void_p, c_void_p]),
+    "arb_rescore_v2": (c_int, [c_int64, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                               c_double, c_double, c_double, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "arb_rescore_khop": (c_int, [c_int64, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                 c_void_p, c_void_p, c_void_p, c_void_p, c_double, c_double, c_double, c_double, c_double,
+                                 c_int, c_void_p, c_void_p, c_void_p]),
     "arb_merge_topk": (c_int, [c_int, c_void_p, c_void_p, c_int, c_int64, c_int, c_int, c_void_p, c_void_p,
                                c_void_p]),
     "arb_merge_topk_peers": (c_int, [c_int, POINTER(c_void_p), POINTER(c_void_p), c_int, c_int64, c_int64, c_int,

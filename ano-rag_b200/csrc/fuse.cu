@@ -401,9 +401,177 @@ rescore_kernel(int method, int nc, const double* __restrict__ vec, const double*
   }
 }
 
+
+// ----------------------------------------------------------------------------
+// The two other live fusion stages of QueryProcessor, same shape as rescore_kernel (one CTA per query,
+// fp64 with the reference's operation order, ranks by counting, stable descending sort):
+//   STAGE_V2    _enhanced_hybrid_search_v2 (query/query_processor.py:1089-1143)
+//   STAGE_KHOP  _rerank_khop_candidates (:1549-1635) + _rrf_score (:854-861)
+// Everything the reference derives from note TEXT (section / lexical multipliers, boosts, coverage,
+// consistency) and from hop_no arrives as per-candidate numbers computed by the host; a multiplier the
+// reference would skip is passed as 1.0 (x * 1.0 == x bit for bit).
+// ----------------------------------------------------------------------------
+struct StageParams {
+  int nc;
+  const int32_t* n_cand;
+  const double* a;            // dense similarity
+  const double* b;            // sparse / bm25 score
+  // V2
+  const double* section; const double* lexical; const uint8_t* satisfies; const double* ent_boost; const double* pred_boost;
+  double wa, wb, noise;
+  // KHOP
+  const double* focused; const double* cov; const double* cons; const double* prf_sim; const uint8_t* is_prf;
+  const int32_t* group; const double* focused_w; const double* hop_mult;
+  double cov_w, cons_w, rrf_lambda; int rrf_k;
+  double* out_score; int32_t* out_order; int32_t* out_kept;
+};
+enum { STAGE_V2 = 0, STAGE_KHOP = 1 };
+
+template <int STAGE>
+__global__ void __launch_bounds__(256)
+rescore_stage_kernel(const StageParams p) {
+  extern __shared__ __align__(16) uint8_t st_smem[];
+  const int nc = p.nc;
+  double* sa = reinterpret_cast<double*>(st_smem);              // [nc]
+  double* sb = sa + nc;                                         // [nc]
+  double* sf = sb + nc;                                         // [nc] final score
+  double* sp = sf + nc;                                         // [nc] prf similarity (KHOP)
+  int* rk = reinterpret_cast<int*>(sp + nc);                    // [3][nc] 1-based ranks: dense, bm25, prf (0 = not prf)
+  int* sg = rk + 3 * nc;                                        // [nc] note-id group
+  __shared__ int kept;
+  const int64_t q = blockIdx.x;
+  const int n = p.n_cand ? min(nc, max(0, p.n_cand[q])) : nc;
+  const size_t base = static_cast<size_t>(q) * nc;
+  if (threadIdx.x == 0) kept = 0;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    sa[i] = p.a[base + i]; sb[i] = p.b[base + i];
+    if (STAGE == STAGE_KHOP) {
+      const bool prf = p.is_prf && p.is_prf[base + i];
+      sp[i] = prf ? p.prf_sim[base + i] : 0.0;
+      rk[2 * nc + i] = prf ? 1 : 0;
+      sg[i] = p.group ? p.group[base + i] : i;
+    }
+  }
+  __syncthreads();
+  if (STAGE == STAGE_KHOP) {
+    // 1-based stable descending ranks (:1590-1601): over all candidates for dense / bm25, inside the prf subset for prf
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+      const double v = sa[i], b = sb[i], s = sp[i];
+      const bool prf = rk[2 * nc + i] != 0;
+      int rv = 1, rb = 1, rp = 1;
+      for (int j = 0; j < n; ++j) {
+        const double vj = sa[j], bj = sb[j];
+        rv += (vj > v || (vj == v && j < i)) ? 1 : 0;
+        rb += (bj > b || (bj == b && j < i)) ? 1 : 0;
+        if (prf && rk[2 * nc + j] != 0) { const double sj = sp[j]; rp += (sj > s || (sj == s && j < i)) ? 1 : 0; }
+      }
+      rk[i] = rv; rk[nc + i] = rb;
+      sf[i] = prf ? static_cast<double>(rp) : 0.0;              // parked: rk[2] is still read as the prf flag above
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < n; i += blockDim.x) rk[2 * nc + i] = static_cast<int>(sf[i]);
+    __syncthreads();
+  }
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    double f;
+    if (STAGE == STAGE_V2) {
+      f = __dadd_rn(__dmul_rn(p.wa, sa[i]), __dmul_rn(p.wb, sb[i]));                     // :1109
+      if (p.section) f = __dmul_rn(f, p.section[base + i]);                              // :1112-1114
+      if (p.lexical) f = __dmul_rn(f, p.lexical[base + i]);                              // :1117-1119
+      const bool ok = !p.satisfies || p.satisfies[base + i];
+      if (f < p.noise && !ok) f = 0.0;                                                   // :1122-1123
+      if (p.ent_boost) f = __dmul_rn(f, p.ent_boost[base + i]);                          // :1126-1132
+      if (p.pred_boost) f = __dmul_rn(f, p.pred_boost[base + i]);
+    } else {
+      int rv = rk[i], rb = rk[nc + i], rp = rk[2 * nc + i];
+      if (p.group) {                        // one RRF entry per note id: the LAST rank written wins (:1593, :858-860)
+        const int g = sg[i];
+        for (int j = 0; j < n; ++j)
+          if (sg[j] == g) { rv = max(rv, rk[j]); rb = max(rb, rk[nc + j]); rp = max(rp, rk[2 * nc + j]); }
+      }
+      double bonus = __ddiv_rn(1.0, static_cast<double>(p.rrf_k + rv));                  // 0.0 + x == x
+      bonus = __dadd_rn(bonus, __ddiv_rn(1.0, static_cast<double>(p.rrf_k + rb)));
+      if (rp > 0) bonus = __dadd_rn(bonus, __ddiv_rn(1.0, static_cast<double>(p.rrf_k + rp)));
+      f = __dadd_rn(__dmul_rn(p.wa, sa[i]), __dmul_rn(p.wb, sb[i]));                     // base (:1609-1610)
+      f = __dadd_rn(f, __dmul_rn(p.focused_w[base + i], p.focused ? p.focused[base + i] : 0.0));
+      f = __dadd_rn(f, __dmul_rn(p.cov_w, p.cov ? p.cov[base + i] : 0.0));
+      f = __dadd_rn(f, __dmul_rn(p.cons_w, p.cons ? p.cons[base + i] : 0.0));
+      f = __dadd_rn(f, __dmul_rn(p.rrf_lambda, bonus));                                  // :1625
+      if (p.hop_mult) f = __dmul_rn(f, p.hop_mult[base + i]);                            // :1626-1627
+    }
+    p.out_score[base + i] = f;
+    sf[i] = f;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < nc; i += blockDim.x) {
+    if (i < n) {
+      const double f = sf[i];
+      if (STAGE == STAGE_V2 && !(f > 0.0)) continue;                                     // :1139
+      int r = 0;
+      for (int j = 0; j < n; ++j) { const double fj = sf[j]; r += (fj > f || (fj == f && j < i)) ? 1 : 0; }
+      p.out_order[base + r] = i;
+      if (STAGE == STAGE_V2) atomicAdd(&kept, 1);
+    } else {
+      p.out_score[base + i] = 0.0;
+      if (STAGE == STAGE_KHOP) p.out_order[base + i] = -1;
+    }
+  }
+  if (STAGE == STAGE_V2) {
+    __syncthreads();
+    for (int i = kept + threadIdx.x; i < nc; i += blockDim.x) p.out_order[base + i] = -1;
+    if (threadIdx.x == 0 && p.out_kept) p.out_kept[q] = kept;
+  }
+}
+
+template <int STAGE>
+static int launch_stage(const StageParams& p, int64_t nq, cudaStream_t st) {
+  ARB_CHECK(nq >= 0 && p.nc >= 1 && p.nc <= RESCORE_MAXC, ARB_ELIMIT, "rescore: 1 <= nc <= 4096");
+  if (nq == 0) return ARB_OK;
+  const size_t smem = static_cast<size_t>(p.nc) * (4 * 8 + 4 * 4);
+  ARB_CUDA(cudaFuncSetAttribute(rescore_stage_kernel<STAGE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                RESCORE_MAXC * (4 * 8 + 4 * 4)));
+  rescore_stage_kernel<STAGE><<<static_cast<unsigned>(nq), 256, smem, st>>>(p);
+  ARB_LAUNCH_OK();
+  return ARB_OK;
+}
+
 }  // namespace arb
 
 using namespace arb;
+
+extern "C" int arb_rescore_v2(int64_t nq, int nc, const double* dense, const double* sparse, const int32_t* n_cand,
+                              const double* section_mult, const double* lexical_mult, const uint8_t* satisfies_must,
+                              const double* entity_boost, const double* predicate_boost, double dense_weight,
+                              double sparse_weight, double noise_threshold, double* out_score, int32_t* out_order,
+                              int32_t* out_kept, void* stream) {
+  ARB_CHECK(dense && sparse && out_score && out_order, ARB_EINVAL, "arb_rescore_v2: NULL argument");
+  StageParams p{};
+  p.nc = nc; p.n_cand = n_cand; p.a = dense; p.b = sparse;
+  p.section = section_mult; p.lexical = lexical_mult; p.satisfies = satisfies_must;
+  p.ent_boost = entity_boost; p.pred_boost = predicate_boost;
+  p.wa = dense_weight; p.wb = sparse_weight; p.noise = noise_threshold;
+  p.out_score = out_score; p.out_order = out_order; p.out_kept = out_kept;
+  return launch_stage<STAGE_V2>(p, nq, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int arb_rescore_khop(int64_t nq, int nc, const double* dense, const double* bm25, const double* focused,
+                                const double* cov, const double* cons, const double* prf_sim, const uint8_t* is_prf,
+                                const int32_t* group, const double* focused_w, const double* hop_mult,
+                                const int32_t* n_cand, double dense_weight, double bm25_weight, double cov_weight,
+                                double cons_weight, double rrf_lambda, int rrf_k, double* out_score, int32_t* out_order,
+                                void* stream) {
+  ARB_CHECK(dense && bm25 && focused_w && out_score && out_order, ARB_EINVAL, "arb_rescore_khop: NULL argument");
+  ARB_CHECK(!is_prf || prf_sim, ARB_EINVAL, "arb_rescore_khop: is_prf without prf_sim");
+  ARB_CHECK(rrf_k >= 0, ARB_EINVAL, "arb_rescore_khop: rrf_k < 0");
+  StageParams p{};
+  p.nc = nc; p.n_cand = n_cand; p.a = dense; p.b = bm25;
+  p.focused = focused; p.cov = cov; p.cons = cons; p.prf_sim = prf_sim; p.is_prf = is_prf; p.group = group;
+  p.focused_w = focused_w; p.hop_mult = hop_mult;
+  p.wa = dense_weight; p.wb = bm25_weight; p.cov_w = cov_weight; p.cons_w = cons_weight; p.rrf_lambda = rrf_lambda;
+  p.rrf_k = rrf_k;
+  p.out_score = out_score; p.out_order = out_order;
+  return launch_stage<STAGE_KHOP>(p, nq, static_cast<cudaStream_t>(stream));
+}
 
 extern "C" int arb_merge_topk_peers(int score_dtype, const void* const* part_scores, const int64_t* const* part_ids,
                                     int parts, int64_t row0, int64_t nq, int k, void* out_scores, int64_t* out_ids,

@@ -232,6 +232,40 @@ ARB_API int arb_rescore_candidates(int method, int64_t nq, int nc, const double*
                            const uint8_t* n_pred, double vector_weight, double bm25_weight, double rrf_k,
                            double* out_score, int32_t* out_order, void* stream);
 
+/* QueryProcessor._enhanced_hybrid_search_v2 (reference query/query_processor.py:1089-1143, without the optional
+ * ListT5 stage), batched: per candidate
+ *   f = dense_weight*dense + sparse_weight*sparse          (1.0 / 0.6 in the reference, :1109)
+ *   f *= section_mult; f *= lexical_mult                   (_apply_section_filtering :1235, _apply_lexical_fallback :1259)
+ *   if (f < noise_threshold && !satisfies_must) f = 0      (:1122-1123)
+ *   f *= entity_boost; f *= predicate_boost                (:1126-1132)
+ * candidates with f > 0 are kept and sorted by f, descending and stable (:1139-1142).  The multipliers come
+ * from note text and are computed by the host; a NULL multiplier array (or 1.0) skips the step, a NULL
+ * satisfies_must means "every candidate satisfies".  All arrays [nq, nc] device memory, nc <= 4096.
+ * out_score [nq, nc] in candidate order; out_order [nq, nc] = kept candidate indices in result order, -1
+ * beyond out_kept[q] (out_kept may be NULL). */
+ARB_API int arb_rescore_v2(int64_t nq, int nc, const double* dense, const double* sparse, const int32_t* n_cand,
+                   const double* section_mult, const double* lexical_mult, const uint8_t* satisfies_must,
+                   const double* entity_boost, const double* predicate_boost, double dense_weight,
+                   double sparse_weight, double noise_threshold, double* out_score, int32_t* out_order,
+                   int32_t* out_kept, void* stream);
+
+/* QueryProcessor._rerank_khop_candidates (reference query/query_processor.py:1549-1635) with _rrf_score
+ * (:854-861), batched: per candidate
+ *   final = dense_weight*dense + bm25_weight*bm25 + focused_w*focused + cov_weight*cov + cons_weight*cons
+ *           + rrf_lambda * (1/(rrf_k + rank_dense) + 1/(rrf_k + rank_bm25) [+ 1/(rrf_k + rank_prf)])
+ *   final *= hop_mult                                       (hop_decay ** (hop_no - 1), 1.0 when not applied)
+ * ranks are 1-based, stable, descending; rank_prf is taken inside the subset is_prf != 0, ordered by prf_sim.
+ * `group` (NULL = every candidate its own) carries the note id: candidates of one group share one RRF
+ * entry holding the largest rank of the group, as the reference's dict keyed by note_id does.  focused_w
+ * (per candidate, from hop_no) and hop_mult are computed by the host.  out_order: all n_cand[q] indices by
+ * descending final (stable), -1 beyond. */
+ARB_API int arb_rescore_khop(int64_t nq, int nc, const double* dense, const double* bm25, const double* focused,
+                     const double* cov, const double* cons, const double* prf_sim, const uint8_t* is_prf,
+                     const int32_t* group, const double* focused_w, const double* hop_mult,
+                     const int32_t* n_cand, double dense_weight, double bm25_weight, double cov_weight,
+                     double cons_weight, double rrf_lambda, int rrf_k, double* out_score, int32_t* out_order,
+                     void* stream);
+
 /* ------------------------------------------------------------------------- *
  * Multi-GPU merge (new design): `parts` per-shard top-k lists,
  * laid out [parts, nq, k] as an NCCL all-gather leaves them, merged to the global

@@ -208,6 +208,24 @@ def test_rescore_oracle_matches_reference_golden(golden_dir):
         assert score == [float.fromhex(v) for v in case["hybrid_score"]]
 
 
+def test_rescore_stage_oracles_match_reference_golden(golden_dir):
+    """_enhanced_hybrid_search_v2 (:1089-1143) and _rerank_khop_candidates (:1549-1635), bit-exact."""
+    from oracle import rescore
+    fh = float.fromhex
+    with open(os.path.join(golden_dir, "rescore_stages_golden.json")) as f:
+        golden = json.load(f)
+    assert len(golden["v2"]) >= 30 and len(golden["khop"]) >= 30
+    for c in golden["v2"]:
+        kept, score = rescore.enhanced_hybrid_search_v2([fh(v) for v in c["dense"]], [fh(v) for v in c["sparse"]], c["candidates"],
+                                                        c["settings"], c["must_have_terms"], c["boost_entities"], c["boost_predicates"])
+        assert kept == c["order"] and score == [fh(v) for v in c["all_scores"]]
+        assert [score[i] for i in kept] == [fh(v) for v in c["final_base_score"]]
+    for c in golden["khop"]:
+        order, score = rescore.rerank_khop([fh(v) for v in c["dense"]], [fh(v) for v in c["bm25"]], [fh(v) for v in c["focused"]],
+                                           c["candidates"], c["path_entities"], c["relation_focus"], c["fusion"], c["features"])
+        assert order == c["order"] and [score[i] for i in order] == [fh(v) for v in c["final_score"]]
+
+
 def test_ivf_oracle_is_consistent_with_flat_oracle():
     """IVF restatement: probing every list equals the flat search; fewer probes only ever drop rows; padding is -1."""
     from oracle import dense as od
