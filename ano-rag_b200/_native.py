@@ -55,6 +55,7 @@ _SIGS = {
     "arb_index_add": (c_int, [c_void_p, c_void_p, c_int, c_int64, c_int, c_void_p]),
     "arb_index_reset": (c_int, [c_void_p]),
     "arb_index_ntotal": (c_int64, [c_void_p]),
+    "arb_index_set_row_normalization": (c_int, [c_void_p, c_int]),
     "arb_index_dim": (c_int, [c_void_p]),
     "arb_index_reconstruct": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_int, c_void_p]),
     "arb_index_search": (c_int, [c_void_p, c_void_p, c_int, c_int64, c_int, c_int, c_int, c_int64,

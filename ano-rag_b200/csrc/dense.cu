@@ -714,6 +714,7 @@ using namespace arb;
 
 struct arb_index {
   int dim = 0, d_pad = 0, storage = 0, planes = 1, normalize = 1;
+  int normalize_rows = 1;        // rows of the next add calls (arb_index_set_row_normalization); queries follow `normalize`
   int device = 0;
   int64_t n = 0, cap = 0;
   __nv_bfloat16* rows = nullptr;       // [cap, planes*d_pad]
@@ -745,6 +746,12 @@ static int launch_prep(const void* src_dev, int dtype, int64_t n, int d, int d_p
 
 static int ivf_assign_rows(arb_index* ix, int64_t row0, int64_t n, cudaStream_t st);
 
+extern "C" int arb_index_set_row_normalization(arb_index* ix, int on) {
+  ARB_CHECK(ix, ARB_EINVAL, "arb_index_set_row_normalization: NULL index");
+  ix->normalize_rows = on ? 1 : 0;
+  return ARB_OK;
+}
+
 extern "C" int arb_index_create(arb_index** out, int dim, int storage, int normalize) {
   ARB_CHECK(out != nullptr, ARB_EINVAL, "arb_index_create: out is NULL");
   ARB_CHECK(dim > 0 && dim <= 8192, ARB_EINVAL, "arb_index_create: dim must be in [1, 8192]");
@@ -757,6 +764,7 @@ extern "C" int arb_index_create(arb_index** out, int dim, int storage, int norma
   ix->storage = storage;
   ix->planes = storage == ARB_STORE_BF16 ? 1 : 3;
   ix->normalize = normalize ? 1 : 0;
+  ix->normalize_rows = ix->normalize;
   ix->device = dev;
   *out = ix;
   return ARB_OK;
@@ -819,7 +827,7 @@ extern "C" int arb_index_add(arb_index* ix, const void* rows, int dtype, int64_t
   const size_t esz = dtype == ARB_F32 ? 4 : 2;
   __nv_bfloat16* dst = ix->rows + static_cast<size_t>(ix->n) * ix->row_elems();
   if (rows_is_device) {
-    int rc = launch_prep(rows, dtype, n, ix->dim, ix->d_pad, ix->planes, ix->normalize, dst, st);
+    int rc = launch_prep(rows, dtype, n, ix->dim, ix->d_pad, ix->planes, ix->normalize_rows, dst, st);
     if (rc) return rc;
   } else {
     // stage host rows through a bounded device buffer
@@ -830,7 +838,7 @@ extern "C" int arb_index_add(arb_index* ix, const void* rows, int dtype, int64_t
       const int64_t m = std::min(chunk, n - off);
       ARB_CUDA(cudaMemcpyAsync(stagebuf.p, static_cast<const char*>(rows) + off * ix->dim * esz,
                                static_cast<size_t>(m) * ix->dim * esz, cudaMemcpyHostToDevice, st));
-      int rc = launch_prep(stagebuf.p, dtype, m, ix->dim, ix->d_pad, ix->planes, ix->normalize,
+      int rc = launch_prep(stagebuf.p, dtype, m, ix->dim, ix->d_pad, ix->planes, ix->normalize_rows,
                            dst + static_cast<size_t>(off) * ix->row_elems(), st);
       if (rc) return rc;
     }

@@ -99,6 +99,14 @@ class DenseIndex:
     def reset(self):
         nat.check(nat.lib.arb_index_reset(self._h))
 
+    def add_prepared(self, rows) -> None:
+        """Append rows that are already pre-processed (a saved index holds them L2-normalised): stored as they are."""
+        nat.check(nat.lib.arb_index_set_row_normalization(self._h, 0))
+        try:
+            self.add(rows)
+        finally:
+            nat.check(nat.lib.arb_index_set_row_normalization(self._h, 1 if self.normalize else 0))
+
     def add(self, rows) -> None:
         f32 = (np.dtype(np.float32),)
         b = _Buf(rows, f32, (torch.float32, torch.bfloat16) if torch is not None else (), "rows")

@@ -29,6 +29,7 @@ import numpy as np
 from .._log import logger
 from ..config import config
 from .. import engine
+from . import faiss_io
 
 try:
     import torch
@@ -228,6 +229,8 @@ class VectorIndex:
 
     # ------------------------------------------------------------------ persistence
     def save_index(self, filename: str = None) -> str:
+        """Writes faiss's own on-disk format (``faiss_io``: IndexFlatIP, or IndexIVFFlat when the index holds
+        inverted lists) so the file is interchangeable with the reference's ``faiss.write_index`` (:300)."""
         if self.index is None:
             logger.error("No index to save")
             return ""
@@ -236,15 +239,16 @@ class VectorIndex:
             filepath = os.path.join(self.index_dir, filename)
             rows = self.index.reconstruct(0, self.index.ntotal) if self.index.ntotal else \
                 np.zeros((0, self.embedding_dim), np.float32)
-            extra = {}
             if self.index.nlist > 0:
-                extra["centroids"] = self.index.ivf_export()[0]
-            with open(filepath, "wb") as f:
-                np.savez(f, rows=rows, storage=np.array(self.storage), **extra)
+                centroids, assign = self.index.ivf_export()
+                faiss_io.write_ivf_flat(filepath, rows, centroids, assign, self.nprobe)
+            else:
+                faiss_io.write_flat(filepath, rows)
             metadata = {                                                                    # :303-311
                 "index_type": self.index_type, "embedding_dim": self.embedding_dim,
                 "similarity_metric": self.similarity_metric, "total_vectors": self.total_vectors,
                 "is_trained": self.is_trained, "nlist": self.nlist, "nprobe": self.nprobe,
+                "b200_storage": self.storage,                                               # extra key, ignored by the reference
             }
             with open(filepath.replace(".faiss", "_metadata.json"), "w", encoding="utf-8") as f:
                 json.dump(metadata, f, ensure_ascii=False, indent=2)
@@ -255,34 +259,44 @@ class VectorIndex:
             return ""
 
     def load_index(self, filename: str) -> bool:
+        """Reads an index written by ``save_index`` or by the reference's ``faiss.write_index`` (Flat / IVFFlat,
+        inner-product metric); the rows go to HBM as stored (they were normalised before they were added)."""
         try:
             filepath = os.path.join(self.index_dir, filename)
             if not os.path.exists(filepath):
                 logger.error(f"Index file not found: {filepath}")
                 return False
+            data = faiss_io.read_index(filepath)
+            if data.metric != faiss_io.METRIC_INNER_PRODUCT:
+                raise ValueError("only inner-product (cosine) indexes are served on the B200 path")
             metadata_file = filepath.replace(".faiss", "_metadata.json")
-            if os.path.exists(metadata_file):
+            self.embedding_dim = data.d
+            self.total_vectors = 0
+            if os.path.exists(metadata_file):                                               # :338-347
                 with open(metadata_file, "r", encoding="utf-8") as f:
                     metadata = json.load(f)
                 self.index_type = metadata.get("index_type", self.index_type)
                 self.embedding_dim = metadata.get("embedding_dim", self.embedding_dim)
                 self.similarity_metric = metadata.get("similarity_metric", self.similarity_metric)
+                self.total_vectors = metadata.get("total_vectors", 0)
+                self.is_trained = metadata.get("is_trained", True)
                 self.nlist = metadata.get("nlist", self.nlist)
                 self.nprobe = metadata.get("nprobe", self.nprobe)
-            with np.load(filepath, allow_pickle=False) as z:
-                rows = z["rows"]
-                self.storage = str(z["storage"])
-                centroids = z["centroids"] if "centroids" in z.files else None
+                self.storage = metadata.get("b200_storage", self.storage)
+            if self.embedding_dim != data.d:
+                raise ValueError(f"metadata says dimension {self.embedding_dim}, the index file holds {data.d}")
             if self.index is not None:
                 self.index.close()
-            # stored rows are already normalised; normalising again on add is idempotent to 1 ulp
-            self.index = engine.DenseIndex(self.embedding_dim, storage=self.storage, normalize=True)
-            if centroids is not None:
-                self.index.set_centroids(centroids)
-            if len(rows):
-                self.index.add(rows)
-            self.total_vectors = len(rows)
-            self.is_trained = True
+            self.index = engine.DenseIndex(data.d, storage=self.storage, normalize=self.similarity_metric == "cosine")
+            if data.kind == "IVFFlat" and self.ivf_mode == "lists" and data.centroids is not None:
+                self.index.set_centroids(data.centroids)          # rows are re-assigned on the device while they are added
+                self.nlist = self.index.nlist
+            chunk = max(1, (256 << 20) // (4 * data.d))
+            for lo in range(0, data.ntotal, chunk):
+                self.index.add_prepared(np.ascontiguousarray(data.rows[lo: lo + chunk]))
+            if not os.path.exists(metadata_file):
+                self.total_vectors = data.ntotal
+                self.is_trained = data.is_trained
             logger.info(f"Index loaded from {filepath}, vectors: {self.total_vectors}")
             return True
         except Exception as e:

@@ -102,6 +102,10 @@ ARB_API int arb_index_destroy(arb_index* index);
  * (row-major, `dtype` ARB_F32 or ARB_BF16).  Row order is the id (:194-196). */
 ARB_API int arb_index_add(arb_index* index, const void* rows, int dtype, int64_t n,
                   int rows_is_device, void* stream);
+/* Rows of the following add calls are (on != 0) / are not L2-normalised on the device; queries keep the
+ * setting of arb_index_create.  load_index (vector_index.py:323-364) uses it to take rows that a saved
+ * index already holds normalised bit for bit, as faiss.read_index does. */
+ARB_API int arb_index_set_row_normalization(arb_index* index, int on);
 ARB_API int arb_index_reset(arb_index* index);                    /* :409-421 reset_index */
 ARB_API int64_t arb_index_ntotal(const arb_index* index);         /* faiss ntotal (:381)   */
 ARB_API int arb_index_dim(const arb_index* index);

@@ -145,6 +145,13 @@ def test_vector_index_dropin_matches_oracle_shaping(tmp_path):
     assert vi2.load_index(path.split("/")[-1]) and vi2.total_vectors == 2000
     again = vi2.search(q, top_k=7)
     assert [[r["index"] for r in g] for g in again] == [[r["index"] for r in g] for g in got]
+    assert [[r["score"] for r in g] for g in again] == [[r["score"] for r in g] for g in got]   # rows restored bit for bit
+    # the file is faiss's own IndexFlatIP format (what the reference's faiss.write_index leaves, :300)
+    from ano_rag_b200.vector_store import faiss_io
+    assert open(path, "rb").read(4) == b"IxFI"
+    disk = faiss_io.read_index(path)
+    assert disk.ntotal == 2000 and np.allclose(np.linalg.norm(np.asarray(disk.rows), axis=1), 1.0, atol=1e-6)
+    assert np.allclose(np.asarray(disk.rows), od.preprocess_vectors(x), rtol=0, atol=3e-7)   # the reference's normalised rows
     # small training set shrinks nlist exactly like the reference (:140-155)
     vi3 = VectorIndex(96)
     vi3.create_index("IVFFlat")

@@ -109,8 +109,13 @@ def test_vector_index_ivf_lists_mode(tmp_path):
     best = vi.optimize_search_params(q, truth, target_recall=0.9)            # sweep of :437-462
     assert best["nprobe"] in (1, 5, 10, 20) and best["recall"] >= 0.9 and vi.nprobe == best["nprobe"]
     path = vi.save_index()
+    assert open(path, "rb").read(4) == b"IwFl"                               # faiss IndexIVFFlat container
+    from ano_rag_b200.vector_store import faiss_io
+    disk = faiss_io.read_index(path)
+    assert disk.kind == "IVFFlat" and disk.nlist == 32 and np.array_equal(disk.assign, vi.index.ivf_export()[1])
     vi2 = VectorIndex(48)
     assert vi2.load_index(path.split("/")[-1]) and vi2.index.nlist == 32
+    assert np.array_equal(vi2.index.ivf_export()[1], disk.assign)            # same lists after the device re-assignment
     vi2.nprobe = vi.nprobe
     assert [[r["index"] for r in g] for g in vi2.search(q, top_k=5)] == [[r["index"] for r in g] for g in vi.search(q, top_k=5)]
     vi3 = VectorIndex(48)
