@@ -7,8 +7,12 @@ Workload (N=1): BASELINE.json configs[2], which contains configs[1] as its dense
 stage -- 1M synthetic atomic notes x 768-d bf16 (exact IP top-100) + BM25 over 1M
 docs (Zipf vocab 50k, ~40 tokens) + RRF(k=60) fusion to the top-100, 4096-query
 batch.  One "step" = one batch through dense top-k -> BM25 top-k -> fusion.
-N>1: the same corpus row-sharded over N ranks (strong scaling): local top-k per
-source, NCCL all-gather, merge, fuse.
+N>1 (strong scaling, same corpus and batch): N GPUs = R row shards x N/R query groups.  The
+default picks the fewest row shards that fit one GPU's HBM -- for this 1M-note corpus R = 1: every
+GPU holds the corpus and serves 1/N of the batch, nothing to exchange -- and ALSO measures the
+fully row-sharded layout (R = N: local top-k per source, candidates exchanged over NVLink by the
+merge kernel's peer loads, merge, fuse), reported in the same line under "row_sharded".
+`--row-shards R` forces a layout; `--workload cfg4` is the corpus that only fits row-sharded.
 
 `value`  = queries/s with the batch already resident in HBM (device-timed, max over ranks).
 `e2e`    = same metric through the public API with HOST buffers (H2D of the batch and D2H
@@ -47,6 +51,11 @@ def parse_args():
     ap.add_argument("--queries", type=int, default=None)
     ap.add_argument("--topk", type=int, default=100)
     ap.add_argument("--vocab", type=int, default=50_000)
+    ap.add_argument("--row-shards", default="auto",
+                    help="N GPUs = R row shards x N/R query groups.  'auto' (default): the fewest row shards whose share of "
+                         "the corpus fits one GPU's HBM budget (cfg3: 1 -> the corpus is replicated and the batch is split; "
+                         "cfg4: N); an integer dividing N forces R (R = N is the fully row-sharded layout)")
+    ap.add_argument("--hbm-budget-gb", type=float, default=140.0, help="per-GPU budget for index data when choosing R")
     ap.add_argument("--cpu-sample", type=int, default=64, help="queries per CPU-baseline step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
@@ -65,19 +74,38 @@ def resolve_workload(a):
     return a
 
 
-def workload_config(a, n_gpus):
+def choose_row_shards(a, world):
+    """R row shards x (world / R) query groups."""
+    if a.row_shards != "auto":
+        r = int(a.row_shards)
+        if r < 1 or world % r:
+            raise SystemExit(f"--row-shards {r} must divide the number of GPUs ({world})")
+        return r
+    if a.workload == "cfg4":
+        return world
+    corpus_gb = (a.notes * a.dim * 2 + a.notes * 40 * 12) / 1e9          # bf16 rows + postings, planes and build scratch
+    for r in range(1, world + 1):
+        if world % r == 0 and corpus_gb / r <= a.hbm_budget_gb:
+            return r
+    return world
+
+
+def workload_config(a, n_gpus, row_shards=None):
+    row_shards = row_shards or n_gpus
+    groups = n_gpus // row_shards
+    layout = "none" if n_gpus == 1 else f"{row_shards} row shard(s) x {groups} query group(s)"
     if a.workload == "cfg4":
         return {"workload": f"cfg4 dense: {a.notes} notes x {a.dim}-d bf16 row-sharded over {n_gpus} GPU(s) "
                             f"({a.notes // n_gpus} rows each), exact IP local top-{a.topk} + all-gather merge, {a.queries}-query batch",
                 "notes": a.notes, "dim": a.dim, "queries": a.queries, "top_k": a.topk,
-                "sharding": f"rows/{n_gpus}" if n_gpus > 1 else "none",
+                "sharding": layout,
                 "l2": "inputs larger than L2 (corpus shard 25.6 GB bf16 vs 126 MB L2)"}
     return {
         "workload": f"cfg3 hybrid: {a.notes} notes x {a.dim}-d bf16 flat-IP top-{a.topk} + BM25 (Zipf vocab {a.vocab}, "
                     f"~40 tok/doc, okapi fp64) + RRF k=60 -> fused top-{a.topk}, {a.queries}-query batch",
         "notes": a.notes, "dim": a.dim, "queries": a.queries, "top_k": a.topk, "vocab": a.vocab,
         "fusion": "rrf", "rrf_k": 60, "weights": {"dense": 1.0, "bm25": 1.0},
-        "sharding": f"rows/{n_gpus}" if n_gpus > 1 else "none",
+        "sharding": layout,
         "l2": "inputs larger than L2 (corpus 1.5 GB bf16 + 138 MB postings vs 126 MB L2)",
     }
 
@@ -240,32 +268,15 @@ def run_b200(a):
         dist.init_process_group("nccl", device_id=dev)
     n_gpus = world
 
-    # ---- build the (sharded) corpus
-    per = (a.notes + world - 1) // world
-    row0, row1 = min(a.notes, rank * per), min(a.notes, (rank + 1) * per)
-    dense = engine.DenseIndex(a.dim, storage="bf16", normalize=False)
-    for _, rows in synth.dense_rows(row0, row1 - row0, a.dim, dev):
-        dense.add(rows)
-    q_emb = synth.dense_queries(a.queries, a.dim, dev, n_rows=a.notes)              # bf16, resident
     hybrid = a.workload == "cfg3"
-    bm25 = None
-    q_terms_h = None
+    q_emb_all = synth.dense_queries(a.queries, a.dim, dev, n_rows=a.notes)          # bf16, resident
+    doc_ptr = doc_tok = q_terms_all = full = None
     if hybrid:
         doc_ptr, doc_tok = synth.bm25_corpus(a.notes, a.vocab)
-        q_terms_h = synth.bm25_queries(a.queries, doc_ptr, doc_tok, a.vocab)
+        q_terms_all = synth.bm25_queries(a.queries, doc_ptr, doc_tok, a.vocab)
         full = bb.build_arrays(doc_ptr, doc_tok, a.vocab, variant="okapi")
-        if world > 1:
-            sptr = doc_ptr[row0:row1 + 1] - doc_ptr[row0]
-            arr = bb.build_arrays(sptr, doc_tok[doc_ptr[row0]:doc_ptr[row1]], a.vocab, stats=full.stats)
-        else:
-            arr = full
-        bm25 = engine.BM25Index(row1 - row0, arr.term_ptr, arr.post_doc, arr.post_gcode, arr.stats.idf, arr.gtab)
     searcher = HybridSearcher({"retrieval": {"candidate_pool": a.topk, "hybrid": {
         "fusion_method": "rrf", "rrf_k": 60, "weights": {"dense": 1.0, "bm25": 1.0}}}})
-    pipe = HybridPipeline(dense, bm25, searcher, k_dense=a.topk, k_bm25=a.topk, pool=a.topk, id_base=row0,
-                          query_planes=1, device=dev)
-    q_terms = torch.from_numpy(q_terms_h).to(dev) if hybrid else None
-    local_postings = bm25.query_postings(q_terms_h) if hybrid else 0
 
     def barrier():
         if world > 1:
@@ -279,73 +290,128 @@ def run_b200(a):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
-    # ---- device-resident throughput (clock sampler runs from the warm-up on: nvidia-smi needs ~0.5 s to start)
+    def build_layout(n_shards):
+        """world = n_shards row shards x n_groups query groups: rank r holds row shard r % n_shards and serves the
+        query slice of group r // n_shards; the ranks of one group exchange and merge their candidates."""
+        n_groups = world // n_shards
+        shard, grp = rank % n_shards, rank // n_shards
+        per = (a.notes + n_shards - 1) // n_shards
+        row0, row1 = min(a.notes, shard * per), min(a.notes, (shard + 1) * per)
+        qper = (a.queries + n_groups - 1) // n_groups
+        q0, q1 = min(a.queries, grp * qper), min(a.queries, (grp + 1) * qper)
+        dense = engine.DenseIndex(a.dim, storage="bf16", normalize=False)
+        for _, rows in synth.dense_rows(row0, row1 - row0, a.dim, dev):
+            dense.add(rows)
+        bm25 = None
+        if hybrid:
+            if n_shards > 1:
+                sptr = doc_ptr[row0:row1 + 1] - doc_ptr[row0]
+                arr = bb.build_arrays(sptr, doc_tok[doc_ptr[row0]:doc_ptr[row1]], a.vocab, stats=full.stats)
+            else:
+                arr = full
+            bm25 = engine.BM25Index(row1 - row0, arr.term_ptr, arr.post_doc, arr.post_gcode, arr.stats.idf, arr.gtab)
+        sub = None
+        if world > 1 and n_shards > 1:
+            subs = [dist.new_group(list(range(g * n_shards, (g + 1) * n_shards))) for g in range(n_groups)]
+            sub = subs[grp]
+        pipe = HybridPipeline(dense, bm25, searcher, k_dense=a.topk, k_bm25=a.topk, pool=a.topk, id_base=row0,
+                              query_planes=1, group=sub, device=dev)
+        if n_shards == 1:
+            pipe.world, pipe.rank = 1, 0                                            # replicated corpus: nothing to exchange
+        q_terms_h = q_terms_all[q0:q1] if hybrid else None
+        return {"pipe": pipe, "dense": dense, "bm25": bm25, "n_shards": n_shards, "n_groups": n_groups, "rows": (row0, row1),
+                "queries": (q0, q1), "q_emb": q_emb_all[q0:q1].contiguous(), "q_terms_h": q_terms_h,
+                "q_terms": torch.from_numpy(np.ascontiguousarray(q_terms_h)).to(dev) if hybrid else None,
+                "local_postings": bm25.query_postings(q_terms_h) if hybrid and q1 > q0 else 0}
+
+    def measure(lay, sampler=None):
+        pipe, q_emb, q_terms = lay["pipe"], lay["q_emb"], lay["q_terms"]
+        n_warm = max(3, a.warmup)
+        for _ in range(n_warm):
+            pipe.search_device(q_emb, q_terms)
+        barrier()
+        # a fresh box keeps paging driver / library code in for the first steps (launch gaps of several ms): keep warming,
+        # untimed, until two consecutive steps agree within 10 % (at most 12 extra steps); the count is reported
+        prev = None
+        for _ in range(12):
+            w0, w1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            w0.record()
+            pipe.search_device(q_emb, q_terms)
+            w1.record()
+            barrier()
+            n_warm += 1
+            cur = max_over_ranks(w0.elapsed_time(w1))
+            if prev is not None and abs(cur - prev) <= 0.1 * min(cur, prev):
+                break
+            prev = cur
+        nat.launch_count(reset=True)
+        nat.profile(True)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(a.steps):
+            pipe.search_device(q_emb, q_terms)
+        e1.record()
+        barrier()
+        launches = nat.launch_count(reset=True)
+        prof = nat.profile_collect()
+        nat.profile(False)
+        ms_step = max_over_ranks(e0.elapsed_time(e1)) / a.steps
+        clocks = sampler.stop() if sampler is not None else None
+        # ---- end to end: pinned host inputs, host outputs
+        q_emb_h = q_emb.to(torch.float32).cpu().pin_memory()                          # encoder output is fp32 on the host
+        q_terms_p = torch.from_numpy(np.ascontiguousarray(lay["q_terms_h"])).pin_memory() if hybrid else None
+        for _ in range(3):
+            pipe.search_host(q_emb_h, q_terms_p)
+        barrier()
+        e0.record()
+        for _ in range(a.steps):
+            res = pipe.search_host(q_emb_h, q_terms_p)
+        e1.record()
+        barrier()
+        e2e_ms = max_over_ranks(e0.elapsed_time(e1)) / a.steps
+        h2d = q_emb_h.numel() * 4 + (q_terms_p.numel() * 4 if hybrid else 0)
+        d2h = sum(int(r.nbytes) for r in res)
+        return {"ms_step": ms_step, "value": a.queries / (ms_step * 1e-3), "warmup": n_warm, "launches": int(launches),
+                "prof": prof, "clocks": clocks, "res": res,
+                "e2e": {"value": a.queries / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
+                        "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms}}
+
+    # ---- the headline layout (clock sampler runs from the warm-up on: nvidia-smi needs ~0.5 s to start)
+    n_shards = choose_row_shards(a, world)
+    lay = build_layout(n_shards)
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    n_warm = max(3, a.warmup)
-    for _ in range(n_warm):
-        pipe.search_device(q_emb, q_terms)
-    barrier()
-    # a fresh box keeps paging driver / library code in for the first steps (launch gaps of several ms): keep warming,
-    # untimed, until two consecutive steps agree within 10 % (at most 12 extra steps); the count is reported
-    prev = None
-    for _ in range(12):
-        w0, w1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        w0.record()
-        pipe.search_device(q_emb, q_terms)
-        w1.record()
-        barrier()
-        n_warm += 1
-        cur = max_over_ranks(w0.elapsed_time(w1))
-        if prev is not None and abs(cur - prev) <= 0.1 * min(cur, prev):
-            break
-        prev = cur
-    nat.launch_count(reset=True)
-    nat.profile(True)
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(a.steps):
-        out = pipe.search_device(q_emb, q_terms)
-    e1.record()
-    barrier()
-    launches = nat.launch_count(reset=True)
-    prof = nat.profile_collect()
-    nat.profile(False)
-    ms_total = max_over_ranks(e0.elapsed_time(e1))
-    clocks = sampler.stop() if rank == 0 else None
-    ms_step = ms_total / a.steps
-    value = a.queries / (ms_step * 1e-3)
+    m = measure(lay, sampler if rank == 0 else None)
+    pipe, prof, res, e2e, clocks = lay["pipe"], m["prof"], m["res"], m["e2e"], m["clocks"]
+    ms_step, value, n_warm, launches = m["ms_step"], m["value"], m["warmup"], m["launches"]
+    row0, row1 = lay["rows"]
+    q_local = lay["queries"][1] - lay["queries"][0]
+    local_postings, q_terms_h, q_emb = lay["local_postings"], q_terms_all, q_emb_all
+    lo, hi = pipe.query_slice(q_local)
+    lo, hi = lo + lay["queries"][0], hi + lay["queries"][0]
 
-    # ---- end to end: pinned host inputs, host outputs
-    q_emb_h = q_emb.to(torch.float32).cpu().pin_memory()                              # encoder output is fp32 on the host
-    q_terms_p = torch.from_numpy(q_terms_h).pin_memory() if hybrid else None
-    for _ in range(3):
-        pipe.search_host(q_emb_h, q_terms_p)
-    barrier()
-    t0 = time.perf_counter()
-    e0.record()
-    for _ in range(a.steps):
-        res = pipe.search_host(q_emb_h, q_terms_p)
-    e1.record()
-    barrier()
-    e2e_ms = max_over_ranks(e0.elapsed_time(e1)) / a.steps
-    lo, hi = pipe.query_slice(a.queries)
-    h2d = q_emb_h.numel() * 4 + (q_terms_p.numel() * 4 if hybrid else 0)
-    d2h = sum(int(r.nbytes) for r in res)
-    e2e = {"value": a.queries / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-           "ms_per_step": e2e_ms}
+    # ---- the fully row-sharded layout beside it when the headline replicates the corpus (SURVEY 8(e) exchange + merge)
+    row_sharded = None
+    if world > 1 and n_shards != world and a.row_shards == "auto":
+        lay["dense"].close()
+        if lay["bm25"] is not None:
+            lay["bm25"].close()
+        lay2 = build_layout(world)
+        m2 = measure(lay2)
+        row_sharded = {"row_shards": world, "query_groups": 1, "value": m2["value"], "unit": UNIT, "ms_per_step": m2["ms_step"],
+                       "e2e": m2["e2e"], "gpu_launches": m2["launches"], "exchange": lay2["pipe"].exchange}
 
     # ---- roofline of the dominant kernel (timed live, CUDA events on the launch stream)
     peaks = load_peaks()
     d_ms = prof["dense_topk"][0] / max(1, prof["dense_topk"][1])
     b_ms = prof["bm25_topk"][0] / max(1, prof["bm25_topk"][1])
     n_local = row1 - row0
-    dense_tflops = 2.0 * a.queries * n_local * a.dim / (d_ms * 1e-3) / 1e12 if d_ms > 0 else 0.0
+    dense_tflops = 2.0 * q_local * n_local * a.dim / (d_ms * 1e-3) / 1e12 if d_ms > 0 else 0.0
     # SURVEY 8(d): bytes/query = sum over query tokens of df(t) * (4 B doc id + 4 B impact) + k * 8 B of output.
     # (The index itself stores 4 B per posting and the batched pipeline re-uses term planes across the
     # queries of a batch from shared memory, so DRAM traffic is far below this figure: see `traffic`.)
-    bm25_bytes = local_postings * 8 + a.queries * a.topk * 8
+    bm25_bytes = local_postings * 8 + q_local * a.topk * 8
     bm25_gbs = bm25_bytes / (b_ms * 1e-3) / 1e9 if b_ms > 0 else 0.0
 
     def per_launch(kind):
@@ -357,10 +423,10 @@ def run_b200(a):
             traffic = json.load(f)
     stages = {
         "dense_topk": {"ms": d_ms, "bound": "tensor", "achieved": dense_tflops, "peak": peaks["tflops"], "unit": "TFLOP/s",
-                       "frac": dense_tflops / peaks["tflops"], "algorithmic_flops": 2.0 * a.queries * n_local * a.dim},
+                       "frac": dense_tflops / peaks["tflops"], "algorithmic_flops": 2.0 * q_local * n_local * a.dim},
         "bm25_topk": {"ms": b_ms, "bound": "hbm", "achieved": bm25_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                       "frac": bm25_gbs / peaks["hbm_gbs"], "algorithmic_bytes": bm25_bytes,
-                      "postings_per_query": local_postings / a.queries,
+                      "postings_per_query": local_postings / max(1, q_local),
                       "kernels_ms": {"sparse_pass": per_launch("bm25_sparse"), "plane_pass": per_launch("bm25_planes"),
                                      "final_merge_and_fallback": per_launch("bm25_final")}},
         "fuse": {"ms": prof["fuse"][0] / max(1, prof["fuse"][1])},
@@ -369,7 +435,7 @@ def run_b200(a):
     dom = "bm25_topk" if b_ms >= d_ms else "dense_topk"
     roofline = {"kernel": dom, "bound": stages[dom]["bound"], "achieved": stages[dom]["achieved"],
                 "peak": stages[dom]["peak"], "unit": stages[dom]["unit"], "frac": stages[dom]["frac"],
-                "traffic": traffic.get(dom), "peak_source": peaks["source"], "launch_ms": stages[dom]["ms"]}
+                "traffic": traffic.get(dom) if world == 1 else None, "peak_source": peaks["source"], "launch_ms": stages[dom]["ms"]}
 
     # ---- CPU baseline beside it (rank 0, N=1, bounded sample)
     cpu_baseline = None
@@ -395,9 +461,9 @@ def run_b200(a):
     if rank == 0:
         line = {"metric": METRIC if hybrid else "dense_queries_per_sec_top100", "value": value, "unit": UNIT, "n_gpus": n_gpus, "steps": a.steps, "warmup": n_warm,
                 "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong" if hybrid else "weak", "vs_baseline": None,
-                "dtype": "bf16", "data": "synthetic", "config": workload_config(a, n_gpus), "e2e": e2e,
+                "dtype": "bf16", "data": "synthetic", "config": workload_config(a, n_gpus, n_shards), "e2e": e2e,
                 "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "stages": stages,
-                "cpu_baseline": cpu_baseline, "impl": "b200",
+                "cpu_baseline": cpu_baseline, "row_sharded": row_sharded, "impl": "b200",
                 "dtype_note": "dense: bf16 operands, fp32 accumulate on tcgen05; BM25 and fusion: fp64"}
         sys.stdout.flush()
         os.dup2(saved_stdout, 1)
