@@ -79,7 +79,7 @@ struct DenseParams {
 // ----------------------------------------------------------------------------
 // Warp-cooperative selection: keep the k largest of list[0..cnt) (cnt <= 32*EPL)
 // in list[0..k), return the k-th largest key.  Exact ties at the k-th key are
-// filled in list order.  All 32 lanes participate.
+// resolved towards the smaller row index.  All 32 lanes participate.
 // ----------------------------------------------------------------------------
 __device__ __forceinline__ uint2 ld_volatile_u2(const uint2* p) {
   uint2 v;
@@ -121,11 +121,30 @@ __device__ __forceinline__ uint32_t warp_select(uint2* list, int cnt, int k, int
     if (gt) list[base + __popc(m & lt)] = make_uint2(idx[i], key[i]);
     base += __popc(m);
   }
-  int need = k - base;
+  const int need = k - base;
+  // entries equal to the k-th key: keep the `need` smallest row indices, so the survivors are the top-k by
+  // (key descending, index ascending) whatever order the list was filled in
+  int ties = 0;
+#pragma unroll
+  for (int i = 0; i < EPL; ++i) ties += ((key[i] == T) && (T != 0u)) ? 1 : 0;
+  ties = __reduce_add_sync(0xffffffffu, ties);
+  uint32_t imax = 0xFFFFFFFFu;                       // largest index that is kept
+  if (ties > need) {
+    imax = 0;                                        // -> the need-th smallest index among the ties
+#pragma unroll 1
+    for (int bit = 31; bit >= 0; --bit) {
+      const uint32_t cand = imax | (1u << bit);
+      int c = 0;
+#pragma unroll
+      for (int i = 0; i < EPL; ++i) c += (key[i] == T && idx[i] < cand) ? 1 : 0;
+      c = __reduce_add_sync(0xffffffffu, c);
+      if (c < need) imax = cand;
+    }
+  }
   int tbase = 0;
 #pragma unroll
   for (int i = 0; i < EPL; ++i) {
-    bool eq = (key[i] == T) && (T != 0u);
+    bool eq = (key[i] == T) && (T != 0u) && idx[i] <= imax;
     uint32_t m = __ballot_sync(0xffffffffu, eq);
     int r = tbase + __popc(m & lt);
     if (eq && r < need) list[base + r] = make_uint2(idx[i], key[i]);
@@ -536,41 +555,94 @@ dense_topk_pair_kernel(const __grid_constant__ CUtensorMap tmap_a,
 
 // ----------------------------------------------------------------------------
 // Merge the per-item candidate lists of each query into its final top-k.
-// One warp per query.
+// One CTA of MERGE_WARPS warps per query: the lists are dealt round-robin to the warps, every list is fetched
+// whole (its count one list ahead) so a warp pays one memory round trip per list instead of one per 32 entries
+// (a query has n_splits * EPI_HALVES lists -- 10 at 4096 queries, 74 at 512 -- and the serial version was
+// latency-bound: ~1 ms of a 1.45 ms dense stage at 512 queries).  Warp 0 then folds the other warps' survivors.
 // ----------------------------------------------------------------------------
+constexpr int MERGE_WARPS = 4;
 template <int EPL, bool IVF>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(32 * MERGE_WARPS)
 dense_merge_kernel(const DenseParams p, int64_t id_base, float* __restrict__ out_scores,
                    int64_t* __restrict__ out_ids) {
   constexpr int C = 32 * EPL;
   extern __shared__ uint8_t msmem[];
+  __shared__ uint32_t s_thr;
+  __shared__ int s_cnt[MERGE_WARPS];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int q = blockIdx.x * (blockDim.x >> 5) + warp;
-  if (q >= p.nq) return;
+  const int q = blockIdx.x;
   uint2* buf = reinterpret_cast<uint2*>(msmem) + static_cast<size_t>(warp) * C;
   const int qt = q / BLOCK_M, row = q % BLOCK_M;
   const uint32_t lt = (1u << lane) - 1u;
-  uint32_t thr_key = p.gthr[q];
+  if (threadIdx.x == 0) s_thr = p.gthr[q];
+  __syncthreads();
+  uint32_t thr_key = s_thr;
   int cnt = 0;
-  const int n_parts = IVF ? p.nprobe : p.n_splits;
-  for (int sp = 0; sp < n_parts; ++sp) {
+  const int n_lists = (IVF ? p.nprobe : p.n_splits) * EPI_HALVES;
+  // list li -> its index in p.lists / p.counts, or -1 (IVF pair without a gathered row)
+  auto list_of = [&](int li) -> long long {
+    const int sp = li / EPI_HALVES, hb = li % EPI_HALVES;
     size_t slot;
     if (IVF) {
       const int pos = p.pair_pos[static_cast<size_t>(q) * p.nprobe + sp];
-      if (pos < 0) continue;
+      if (pos < 0) return -1;
       slot = static_cast<size_t>(pos);
     } else {
       slot = (static_cast<size_t>(sp) * p.n_qtiles + qt) * BLOCK_M + row;
     }
-    for (int hb = 0; hb < EPI_HALVES; ++hb) {
-    const uint2* L = p.lists + (slot * EPI_HALVES + hb) * C;
-    const int n = p.counts[slot * EPI_HALVES + hb];
+    return static_cast<long long>(slot * EPI_HALVES + hb);
+  };
+  long long cur = warp < n_lists ? list_of(warp) : -1;
+  int n_cur = cur >= 0 ? p.counts[cur] : 0;
+  for (int li = warp; li < n_lists; li += MERGE_WARPS) {
+    const long long nxt = li + MERGE_WARPS < n_lists ? list_of(li + MERGE_WARPS) : -1;
+    const int n_nxt = nxt >= 0 ? p.counts[nxt] : 0;          // in flight while this list is merged
+    const int n = n_cur;
+    if (n > 0) {
+      const uint2* L = p.lists + static_cast<size_t>(cur) * C;
+      uint2 e[EPL];
+#pragma unroll
+      for (int i = 0; i < EPL; ++i) {
+        e[i] = make_uint2(0u, 0u);
+        if (32 * i + lane < n) e[i] = __ldcg(L + 32 * i + lane);
+      }
+      if (IVF) {
+#pragma unroll
+        for (int i = 0; i < EPL; ++i)      // rank and tie-break by the original row, not the list slot
+          if (32 * i + lane < n) e[i].x = static_cast<uint32_t>(p.row_ids[e[i].x]);
+      }
+      thr_key = max(thr_key, *reinterpret_cast<volatile uint32_t*>(&s_thr));
+#pragma unroll
+      for (int i = 0; i < EPL; ++i) {
+        if (32 * i < n) {                                     // warp-uniform
+          const bool pass = (32 * i + lane < n) && e[i].y >= thr_key;
+          const uint32_t m = __ballot_sync(0xffffffffu, pass);
+          if (pass) buf[cnt + __popc(m & lt)] = e[i];
+          cnt += __popc(m);
+          if (cnt > C - 32) {
+            const uint32_t T = warp_select<EPL, false>(buf, cnt, p.k, lane);
+            cnt = p.k;
+            thr_key = max(thr_key, T);
+            if (lane == 0) atomicMax(&s_thr, T);
+          }
+        }
+      }
+    }
+    cur = nxt; n_cur = n_nxt;
+  }
+  __syncwarp();
+  if (cnt > p.k) { warp_select<EPL, false>(buf, cnt, p.k, lane); cnt = p.k; }
+  if (lane == 0) s_cnt[warp] = cnt;
+  __syncthreads();
+  if (warp != 0) return;
+  // fold the survivors of warps 1.. into warp 0's buffer (each holds at most k <= C - 32 entries)
+  thr_key = max(thr_key, *reinterpret_cast<volatile uint32_t*>(&s_thr));
+  for (int w = 1; w < MERGE_WARPS; ++w) {
+    const uint2* B = reinterpret_cast<const uint2*>(msmem) + static_cast<size_t>(w) * C;
+    const int n = s_cnt[w];
     for (int b = 0; b < n; b += 32) {
       uint2 e = make_uint2(0u, 0u);
-      if (b + lane < n) {
-        e = L[b + lane];
-        if (IVF) e.x = static_cast<uint32_t>(p.row_ids[e.x]);   // rank and tie-break by the original row, not the list slot
-      }
+      if (b + lane < n) e = B[b + lane];
       const bool pass = (b + lane < n) && e.y >= thr_key;
       const uint32_t m = __ballot_sync(0xffffffffu, pass);
       if (pass) buf[cnt + __popc(m & lt)] = e;
@@ -580,7 +652,6 @@ dense_merge_kernel(const DenseParams p, int64_t id_base, float* __restrict__ out
         cnt = p.k;
         thr_key = max(thr_key, T);
       }
-    }
     }
   }
   __syncwarp();
@@ -999,7 +1070,7 @@ static int run_dense_rows(const arb_index* ix, int64_t n_rows, const uint32_t* t
   ARB_LAUNCH_OK();
   const int wpb = 4;
   {
-    dense_merge_kernel<EPL, false><<<static_cast<unsigned>((nq + wpb - 1) / wpb), wpb * 32, wpb * C * sizeof(uint2), st>>>(
+    dense_merge_kernel<EPL, false><<<static_cast<unsigned>(nq), MERGE_WARPS * 32, MERGE_WARPS * C * sizeof(uint2), st>>>(
         p, id_base, d_scores, d_ids);
   }
   ARB_LAUNCH_OK();
@@ -1485,7 +1556,7 @@ static int run_ivf(arb_index* ix, const __nv_bfloat16* qplanes, int q_planes, in
   const int wpb = 4;
   {
     ProfileScope ps(PROF_DENSE_MERGE, st);
-    dense_merge_kernel<EPL, true><<<static_cast<unsigned>((nq + wpb - 1) / wpb), wpb * 32, wpb * C * sizeof(uint2), st>>>(
+    dense_merge_kernel<EPL, true><<<static_cast<unsigned>(nq), MERGE_WARPS * 32, MERGE_WARPS * C * sizeof(uint2), st>>>(
         p, id_base, d_scores, d_ids);
   }
   ARB_LAUNCH_OK();
