@@ -67,6 +67,13 @@ struct DenseParams {
   uint2* lists;             // [n_items, 128, C] {row index, ordered score key}
   int* counts;              // [n_items, 128]
   uint32_t* gthr;           // [n_qtiles*128] shared per-query threshold key
+  // Cross-list bound (flat scan, small batches): a query's rows are split over n_lists = n_splits * EPI_HALVES
+  // candidate lists.  Every list tracks the rank2-th best key it has met (rank2 = ceil(k / n_lists) <= 8) and
+  // publishes it once per tile; as soon as all lists have one, at least n_lists * rank2 >= k scores reach the
+  // smallest published key, so the query's threshold can be raised to it long before any single list has seen k
+  // good rows.  Without it a list of a 512-query batch (74 lists per query) never gets a selective threshold.
+  uint32_t* sthr;           // [n_lists, n_qtiles*128] published keys, 0 = none yet; NULL = off
+  int n_lists, rank2;
   // IVF list scan (template flag IVF): work items come from a device-built table
   const IvfItem* items;     // [n_items] A-tile of gathered queries x one inverted list
   const int* n_items_ptr;   // number of items (known only on the device)
@@ -157,7 +164,7 @@ __device__ __forceinline__ uint32_t warp_select(uint2* list, int cnt, int k, int
 // ----------------------------------------------------------------------------
 // The fused GEMM + threshold-select kernel.
 // ----------------------------------------------------------------------------
-template <int EPL, bool IVF>
+template <int EPL, bool IVF, int CROSS = 0>      // CROSS: 0 = off, else how many best keys a list tracks (4 or 8)
 __global__ void __launch_bounds__(DENSE_THREADS, 1)
 dense_topk_kernel(const __grid_constant__ CUtensorMap tmap_a,
                   const __grid_constant__ CUtensorMap tmap_b, const DenseParams p) {
@@ -271,7 +278,25 @@ dense_topk_kernel(const __grid_constant__ CUtensorMap tmap_a,
       int cnt = 0;
       uint32_t thr_key = KEY_NEG_INF;
       float thr = valid ? -INFINITY : INFINITY;
+      constexpr bool cross = CROSS > 0 && !IVF;
+      constexpr int NB = CROSS > 0 ? CROSS : 1;
+      const size_t q_pad = static_cast<size_t>(p.n_qtiles) * BLOCK_M;
+      const int li = IVF ? 0 : (item / p.n_qtiles) * EPI_HALVES + half;
+      uint32_t best[NB], b_pub = 0;                         // the NB best keys this list has met, descending
+#pragma unroll
+      for (int i = 0; i < NB; ++i) best[i] = 0;
       for (int t = t0; t < t1; ++t) {
+        if (cross && valid) {
+          uint32_t br = best[NB - 1];
+#pragma unroll
+          for (int i = 0; i < NB - 1; ++i) if (p.rank2 == i + 1) br = best[i];
+          if (br != b_pub) { b_pub = br; *reinterpret_cast<volatile uint32_t*>(p.sthr + li * q_pad + q) = br; }
+          if ((t - t0) % p.n_lists == li % p.n_lists || t == t0 + 2) {   // the lists of a query take turns (warp-uniform)
+            uint32_t mn = 0xFFFFFFFFu;
+            for (int i = 0; i < p.n_lists; ++i) mn = min(mn, i == li ? br : __ldcg(p.sthr + i * q_pad + q));
+            if (mn > KEY_NEG_INF + 1u) atomicMax(p.gthr + q, mn - 1u);   // "score > threshold" keeps scores equal to mn
+          }
+        }
         if (valid) {
           uint32_t g = __ldcg(p.gthr + q);
           if (g > thr_key) { thr_key = g; thr = key_f32(g); }
@@ -306,7 +331,16 @@ dense_topk_kernel(const __grid_constant__ CUtensorMap tmap_a,
 #pragma unroll
                 for (int j = 8 * g8; j < 8 * g8 + 8; ++j) {
                   float s = __uint_as_float(v[j]);
-                  if (s > thr) { list[cnt] = make_uint2(idx0 + j, f32_key(s)); ++cnt; }
+                  if (s > thr) {
+                    const uint32_t key = f32_key(s);
+                    list[cnt] = make_uint2(idx0 + j, key); ++cnt;
+                    if (cross && key > best[NB - 1]) {       // sorted insert into the NB best
+                      best[NB - 1] = key;
+#pragma unroll
+                      for (int i = NB - 1; i > 0; --i)
+                        if (best[i] > best[i - 1]) { const uint32_t x = best[i - 1]; best[i - 1] = best[i]; best[i] = x; }
+                    }
+                  }
                 }
               }
             }
@@ -945,8 +979,9 @@ extern "C" int arb_index_reconstruct(const arb_index* ix, int64_t row0, int64_t 
 
 // choose how many corpus splits each query tile is cut into so that the persistent
 // grid finishes in the fewest n-tile steps (ties: fewer splits = fewer lists)
-static void plan_splits(int n_qtiles, int n_ntiles, int grid, int* n_splits, int* tiles_per_split) {
-  long best_cost = -1; int best_s = 1;
+static void plan_splits(int n_qtiles, int n_ntiles, int grid, int* n_splits, int* tiles_per_split, int* n_rounds = nullptr) {
+  long best_cost = -1; int best_s = 1; long best_rounds = 1;
+  long one_cost = -1; int one_s = 1;                    // best plan whose items all run at once (one round)
   const int max_s = std::max(1, std::min(n_ntiles, 64 * std::max(1, grid / std::max(1, n_qtiles)) + 8));
   for (int s = 1; s <= max_s; ++s) {
     const int tps = (n_ntiles + s - 1) / s;
@@ -954,11 +989,16 @@ static void plan_splits(int n_qtiles, int n_ntiles, int grid, int* n_splits, int
     const long items = static_cast<long>(s_eff) * n_qtiles;
     const long rounds = (items + grid - 1) / grid;
     const long cost = rounds * tps * 64 + s_eff;       // makespan first, then fewer lists
-    if (best_cost < 0 || cost < best_cost) { best_cost = cost; best_s = s_eff; }
+    if (best_cost < 0 || cost < best_cost) { best_cost = cost; best_s = s_eff; best_rounds = rounds; }
+    if (rounds == 1 && (one_cost < 0 || cost < one_cost)) { one_cost = cost; one_s = s_eff; }
   }
+  // All lists of a query being live at the same time lets them share one tight threshold (DenseParams::sthr), which is
+  // worth more than a few percent of makespan: take the one-round plan unless it is clearly longer.
+  if (n_rounds && one_cost >= 0 && one_cost <= best_cost + best_cost / 8) { best_s = one_s; best_rounds = 1; }
   *n_splits = best_s;
   *tiles_per_split = (n_ntiles + best_s - 1) / best_s;
   *n_splits = (n_ntiles + *tiles_per_split - 1) / *tiles_per_split;
+  if (n_rounds) *n_rounds = static_cast<int>(best_rounds);
 }
 
 // (query plane, corpus plane) pairs, smallest magnitude first
@@ -991,9 +1031,49 @@ __global__ void prepass_bound_kernel(const float* __restrict__ scores, const int
 
 // one scan of rows [0, n_rows) of the index; thr_init (device, [nq] keys or NULL) pre-loads the shared thresholds
 template <int EPL>
+static int run_dense_chunk(const arb_index* ix, int64_t n_rows, const uint32_t* thr_init, const __nv_bfloat16* qplanes,
+                           int q_planes, int64_t nq, int k, int64_t id_base, float* d_scores, int64_t* d_ids,
+                           cudaStream_t st);
+
+// A batch whose (query tile x corpus split) items cannot all be resident at once is scanned in query chunks that can:
+// with every list of a query live at the same time the lists share one tight threshold (DenseParams::sthr) and the
+// epilogue stops being the bottleneck (cfg3: 4096 queries as 2 x 2048 run at ~1.3 PFLOP/s instead of ~1.2).  Each
+// chunk streams the corpus again, which costs nothing while the scan is compute-bound; long scans (>= 8192 corpus
+// tiles, cfg4) warm their thresholds anyway and keep the single multi-round launch.
+template <int EPL>
 static int run_dense_rows(const arb_index* ix, int64_t n_rows, const uint32_t* thr_init, const __nv_bfloat16* qplanes,
                           int q_planes, int64_t nq, int k, int64_t id_base, float* d_scores, int64_t* d_ids,
                           cudaStream_t st) {
+  const int sms = num_sms();
+  const int64_t n_qtiles = (nq + BLOCK_M - 1) / BLOCK_M;
+  const int64_t n_ntiles = (n_rows + BLOCK_N - 1) / BLOCK_N;
+  // the most query tiles one chunk may hold: items = qtiles * floor(sms / qtiles) splits all resident, and the lists of a
+  // query (2 per split) must reach k with at most 8 keys each
+  int64_t max_qt = 0;
+  for (int64_t qt = 1; qt <= sms; ++qt) {
+    const int64_t splits = sms / qt;
+    if (splits >= 1 && (k + 2 * splits - 1) / (2 * splits) <= 8) max_qt = qt;
+  }
+  int mode = -1;                                                  // ARB_DENSE_CHUNK: 0 never, 1 always, default auto
+  if (const char* v = std::getenv("ARB_DENSE_CHUNK")) mode = atoi(v);
+  const bool chunked = max_qt > 0 && n_qtiles > max_qt && (mode == 1 || (mode != 0 && n_ntiles < 8192));
+  if (!chunked) return run_dense_chunk<EPL>(ix, n_rows, thr_init, qplanes, q_planes, nq, k, id_base, d_scores, d_ids, st);
+  const int64_t n_chunks = (n_qtiles + max_qt - 1) / max_qt;
+  const int64_t per = ((n_qtiles + n_chunks - 1) / n_chunks) * BLOCK_M;       // balanced, whole query tiles
+  for (int64_t q0 = 0; q0 < nq; q0 += per) {
+    const int64_t m = std::min<int64_t>(per, nq - q0);
+    int rc = run_dense_chunk<EPL>(ix, n_rows, thr_init ? thr_init + q0 : nullptr,
+                                  qplanes + static_cast<size_t>(q0) * q_planes * ix->d_pad, q_planes, m, k, id_base,
+                                  d_scores + static_cast<size_t>(q0) * k, d_ids + static_cast<size_t>(q0) * k, st);
+    if (rc) return rc;
+  }
+  return ARB_OK;
+}
+
+template <int EPL>
+static int run_dense_chunk(const arb_index* ix, int64_t n_rows, const uint32_t* thr_init, const __nv_bfloat16* qplanes,
+                           int q_planes, int64_t nq, int k, int64_t id_base, float* d_scores, int64_t* d_ids,
+                           cudaStream_t st) {
   constexpr int C = 32 * EPL;
   DenseParams p;
   memset(&p, 0, sizeof(p));
@@ -1009,7 +1089,7 @@ static int run_dense_rows(const arb_index* ix, int64_t n_rows, const uint32_t* t
   // (measured slower than the single-CTA kernel on cfg3 -- 6.2 vs 5.9 ms -- so it is opt-in: ARB_DENSE_PAIR=1)
   bool use_pair = false;
   if (const char* v = std::getenv("ARB_DENSE_PAIR")) use_pair = atoi(v) != 0 && nq >= 2 * BLOCK_M && sms >= 2;
-  int grid;
+  int grid, rounds = 0;
   if (use_pair) {
     p.n_qtiles = (p.n_qtiles + 1) & ~1;                  // whole 256-query super tiles (the odd one is padding)
     const int clusters = sms / 2;
@@ -1017,13 +1097,23 @@ static int run_dense_rows(const arb_index* ix, int64_t n_rows, const uint32_t* t
     p.n_items = p.n_splits * (p.n_qtiles / 2);
     grid = 2 * std::min(clusters, p.n_items);
   } else {
-    plan_splits(p.n_qtiles, p.n_ntiles, sms, &p.n_splits, &p.tiles_per_split);
+    plan_splits(p.n_qtiles, p.n_ntiles, sms, &p.n_splits, &p.tiles_per_split, &rounds);
     p.n_items = p.n_splits * p.n_qtiles;
     grid = std::min(sms, p.n_items);
   }
   const size_t n_slots = static_cast<size_t>(p.n_splits) * p.n_qtiles;   // candidate lists per query row
 
-  AsyncBuf lists, counts, gthr;
+  AsyncBuf lists, counts, gthr, sthr;
+  bool cross_off = false;                                         // ARB_DENSE_CROSS=0: A/B switch for the probes
+  if (const char* v = std::getenv("ARB_DENSE_CROSS")) cross_off = atoi(v) == 0;
+  p.n_lists = p.n_splits * EPI_HALVES;
+  p.rank2 = (k + p.n_lists - 1) / p.n_lists;
+  if (!use_pair && !cross_off && rounds == 1 && p.n_items <= grid && p.n_lists > 1 && p.rank2 <= 8) {
+    const size_t bytes = static_cast<size_t>(p.n_qtiles) * BLOCK_M * p.n_lists * sizeof(uint32_t);
+    ARB_CUDA(sthr.alloc(bytes, st));
+    ARB_CUDA(cudaMemsetAsync(sthr.p, 0, bytes, st));
+    p.sthr = sthr.as<uint32_t>();
+  }
   ARB_CUDA(lists.alloc(n_slots * BLOCK_M * EPI_HALVES * C * sizeof(uint2), st));
   ARB_CUDA(counts.alloc(n_slots * BLOCK_M * EPI_HALVES * sizeof(int), st));
   ARB_CUDA(gthr.alloc(static_cast<size_t>(p.n_qtiles) * BLOCK_M * sizeof(uint32_t), st));
@@ -1046,6 +1136,10 @@ static int run_dense_rows(const arb_index* ix, int64_t n_rows, const uint32_t* t
   std::call_once(attr_once, [] {
     attr_err = cudaFuncSetAttribute(dense_topk_kernel<EPL, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, DENSE_SMEM);
     if (attr_err == cudaSuccess)
+      attr_err = cudaFuncSetAttribute(dense_topk_kernel<EPL, false, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, DENSE_SMEM);
+    if (attr_err == cudaSuccess)
+      attr_err = cudaFuncSetAttribute(dense_topk_kernel<EPL, false, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, DENSE_SMEM);
+    if (attr_err == cudaSuccess)
       attr_err = cudaFuncSetAttribute(dense_topk_pair_kernel<EPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, PAIR_SMEM);
   });
   ARB_CUDA(attr_err);
@@ -1064,7 +1158,9 @@ static int run_dense_rows(const arb_index* ix, int64_t n_rows, const uint32_t* t
       cfg.numAttrs = 1;
       ARB_CUDA(cudaLaunchKernelEx(&cfg, dense_topk_pair_kernel<EPL>, ta, tb, p));
     } else {
-      dense_topk_kernel<EPL, false><<<grid, DENSE_THREADS, DENSE_SMEM, st>>>(ta, tb, p);
+      if (p.sthr && p.rank2 <= 4) dense_topk_kernel<EPL, false, 4><<<grid, DENSE_THREADS, DENSE_SMEM, st>>>(ta, tb, p);
+      else if (p.sthr)            dense_topk_kernel<EPL, false, 8><<<grid, DENSE_THREADS, DENSE_SMEM, st>>>(ta, tb, p);
+      else                        dense_topk_kernel<EPL, false><<<grid, DENSE_THREADS, DENSE_SMEM, st>>>(ta, tb, p);
     }
   }
   ARB_LAUNCH_OK();
