@@ -1038,15 +1038,14 @@ static int run_dense_chunk(const arb_index* ix, int64_t n_rows, const uint32_t* 
 // A batch whose (query tile x corpus split) items cannot all be resident at once is scanned in query chunks that can:
 // with every list of a query live at the same time the lists share one tight threshold (DenseParams::sthr) and the
 // epilogue stops being the bottleneck (cfg3: 4096 queries as 2 x 2048 run at ~1.3 PFLOP/s instead of ~1.2).  Each
-// chunk streams the corpus again, which costs nothing while the scan is compute-bound; long scans (>= 8192 corpus
-// tiles, cfg4) warm their thresholds anyway and keep the single multi-round launch.
+// chunk streams the corpus again, which costs nothing while the scan is compute-bound (cfg4 shard, 12.5M x 1024-d,
+// 8192 queries as 4 x 2048: 167.8 -> 159.8 ms; the re-reads are 102 GB per step = 0.64 TB/s).
 template <int EPL>
 static int run_dense_rows(const arb_index* ix, int64_t n_rows, const uint32_t* thr_init, const __nv_bfloat16* qplanes,
                           int q_planes, int64_t nq, int k, int64_t id_base, float* d_scores, int64_t* d_ids,
                           cudaStream_t st) {
   const int sms = num_sms();
   const int64_t n_qtiles = (nq + BLOCK_M - 1) / BLOCK_M;
-  const int64_t n_ntiles = (n_rows + BLOCK_N - 1) / BLOCK_N;
   // the most query tiles one chunk may hold: items = qtiles * floor(sms / qtiles) splits all resident, and the lists of a
   // query (2 per split) must reach k with at most 8 keys each
   int64_t max_qt = 0;
@@ -1054,9 +1053,9 @@ static int run_dense_rows(const arb_index* ix, int64_t n_rows, const uint32_t* t
     const int64_t splits = sms / qt;
     if (splits >= 1 && (k + 2 * splits - 1) / (2 * splits) <= 8) max_qt = qt;
   }
-  int mode = -1;                                                  // ARB_DENSE_CHUNK: 0 never, 1 always, default auto
-  if (const char* v = std::getenv("ARB_DENSE_CHUNK")) mode = atoi(v);
-  const bool chunked = max_qt > 0 && n_qtiles > max_qt && (mode == 1 || (mode != 0 && n_ntiles < 8192));
+  bool off = false;                                               // ARB_DENSE_CHUNK=0: A/B switch for the probes
+  if (const char* v = std::getenv("ARB_DENSE_CHUNK")) off = atoi(v) == 0;
+  const bool chunked = !off && max_qt > 0 && n_qtiles > max_qt;
   if (!chunked) return run_dense_chunk<EPL>(ix, n_rows, thr_init, qplanes, q_planes, nq, k, id_base, d_scores, d_ids, st);
   const int64_t n_chunks = (n_qtiles + max_qt - 1) / max_qt;
   const int64_t per = ((n_qtiles + n_chunks - 1) / n_chunks) * BLOCK_M;       // balanced, whole query tiles
