@@ -1,5 +1,6 @@
 """Host-side logic that runs without a GPU: index-build arithmetic against the oracle,
 config shim, tokeniser, query encoding."""
+import os
 import random
 
 import numpy as np
@@ -88,3 +89,25 @@ def test_tokenizer_matches_oracle():
     from ano_rag_b200.utils.bm25_search import tokenize_text
     for s in ["The quick-brown fox_1 jumps!", "", "ÀÉ ünïcode 42x", "a.b,c;d"]:
         assert tokenize_text(s) == obm.tokenize_text(s)
+
+
+def test_bench_layout_choice():
+    """bench.py: N GPUs = R row shards x N/R query groups; 'auto' takes the fewest shards that fit the HBM budget."""
+    import importlib.util
+    import types
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    a = types.SimpleNamespace(row_shards="auto", workload="cfg3", notes=1_000_000, dim=768, hbm_budget_gb=140.0)
+    assert [bench.choose_row_shards(a, w) for w in (1, 2, 4, 8)] == [1, 1, 1, 1]          # replicated corpus, split batch
+    a.notes, a.dim = 100_000_000, 1024                                                    # 205 GB of rows + postings
+    assert bench.choose_row_shards(a, 8) == 2 and bench.choose_row_shards(a, 1) == 1
+    a.workload = "cfg4"
+    assert bench.choose_row_shards(a, 8) == 8
+    a.row_shards = "4"
+    assert bench.choose_row_shards(a, 8) == 4
+    a.row_shards = "3"
+    with pytest.raises(SystemExit):
+        bench.choose_row_shards(a, 8)
+    cfg = bench.workload_config(types.SimpleNamespace(workload="cfg3", notes=10, dim=4, queries=2, topk=1, vocab=5), 8, 2)
+    assert cfg["sharding"] == "2 row shard(s) x 4 query group(s)"
