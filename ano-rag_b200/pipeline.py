@@ -91,6 +91,8 @@ class HybridPipeline:
         # "nccl" = all-to-all of query slices followed by the merge
         self.exchange = os.environ.get("ARB_EXCHANGE", "peer" if self.world <= 16 else "nccl")
         self._peer: Optional[PeerLists] = None
+        self._copy_stream = None
+        self._host_out, self._host_turn = {}, {}
 
     # ------------------------------------------------------------------ device-resident inputs
     def _exchange(self, t: torch.Tensor, pad) -> torch.Tensor:
@@ -106,7 +108,23 @@ class HybridPipeline:
         torch.distributed.all_to_all_single(recv, send.contiguous(), group=self.group)
         return recv
 
-    def search_device(self, q_emb: torch.Tensor, q_terms: Optional[torch.Tensor]):
+    def _dense(self, q_emb: torch.Tensor, out, emb_ready):
+        """Dense local top-k into ``out`` (or fresh tensors).  ``emb_ready`` = [(lo, hi, event), ...]: rows [lo, hi) of
+        q_emb are valid once ``event`` (None = already) has happened -- lets the scan of the first rows of a batch
+        start while the rest is still on its way from the host (search_host)."""
+        nq = q_emb.shape[0]
+        if out is None:
+            out = (torch.empty((nq, self.k_dense), dtype=torch.float32, device=q_emb.device),
+                   torch.empty((nq, self.k_dense), dtype=torch.int64, device=q_emb.device))
+        for lo, hi, ev in (emb_ready or [(0, nq, None)]):
+            if ev is not None:
+                torch.cuda.current_stream(q_emb.device).wait_event(ev)
+            if hi > lo:
+                self.dense.search(q_emb[lo:hi], self.k_dense, query_planes=self.query_planes, id_base=self.id_base,
+                                  out=(out[0][lo:hi], out[1][lo:hi]))
+        return out
+
+    def search_device(self, q_emb: torch.Tensor, q_terms: Optional[torch.Tensor], emb_ready=None):
         """q_emb [nq, d] CUDA (fp32 or bf16), q_terms [nq, max_qt] CUDA int32 (or None: dense only).
         -> (ids [nq,pool] int64, final [nq,pool] fp64, src [nq,pool,4] fp64, count [nq] int32) on the device.
         With world > 1 every rank returns the rows of its own query slice
@@ -116,8 +134,7 @@ class HybridPipeline:
         if self.world > 1 and self.exchange == "peer":
             peer = self._peer_lists(nq)
             lo, hi = self.query_slice(nq)
-            self.dense.search(q_emb, self.k_dense, query_planes=self.query_planes, id_base=self.id_base,
-                              out=peer.dense_out(nq))
+            self._dense(q_emb, peer.dense_out(nq), emb_ready)
             if with_bm25:
                 self.bm25.search(q_terms, self.k_bm25, id_base=self.id_base, out=peer.bm25_out(nq))
             peer.barrier()                       # every rank's lists are written and visible
@@ -130,7 +147,7 @@ class HybridPipeline:
             peer.flip()
             return self.searcher.fuse_tensors(dense=(d_id, d_sc), bm25=(b_id, b_sc) if with_bm25 else None,
                                               pool=self.pool)
-        d_sc, d_id = self.dense.search(q_emb, self.k_dense, query_planes=self.query_planes, id_base=self.id_base)
+        d_sc, d_id = self._dense(q_emb, None, emb_ready)
         b_sc = b_id = None
         if with_bm25:
             b_sc, b_id = self.bm25.search(q_terms, self.k_bm25, id_base=self.id_base)
@@ -159,12 +176,46 @@ class HybridPipeline:
 
     # ------------------------------------------------------------------ host buffers (the end-to-end call)
     def search_host(self, q_emb_host, q_terms_host, return_src: bool = False):
-        """Host (ideally pinned) inputs -> host numpy outputs (ids, final, count[, src]); the H2D copy of
-        the batch and the D2H copy of the fused result are part of the call."""
-        q_emb = torch.as_tensor(q_emb_host).to(self.device, non_blocking=True)
-        q_terms = None
-        if q_terms_host is not None:
-            q_terms = torch.as_tensor(q_terms_host).to(self.device, non_blocking=True)
-        ids, fin, src, cnt = self.search_device(q_emb, q_terms)
-        out = (ids.cpu().numpy(), fin.cpu().numpy(), cnt.cpu().numpy())
-        return out + (src.cpu().numpy(),) if return_src else out
+        """Host inputs -> host numpy outputs (ids, final, count[, src]); the H2D copy of the batch and the D2H copy of
+        the fused result are part of the call.  With pinned inputs the second half of the embeddings travels on a
+        copy stream while the dense scan of the first half runs; the results land in pinned buffers (one
+        synchronisation).  The returned arrays are views of two alternating buffer sets: copy them if they must
+        outlive the next call but one."""
+        dev = self.device
+        h_emb = torch.as_tensor(q_emb_host)
+        nq = h_emb.shape[0]
+        with torch.cuda.device(dev):
+            main = torch.cuda.current_stream(dev)
+            q_emb = torch.empty(h_emb.shape, dtype=h_emb.dtype, device=dev)
+            half = ((nq // 2 + 127) // 128) * 128
+            emb_ready = None
+            if h_emb.is_pinned() and nq >= 1024 and 0 < half < nq:
+                if self._copy_stream is None:
+                    self._copy_stream = torch.cuda.Stream(device=dev)
+                side = self._copy_stream
+                side.wait_stream(main)                      # q_emb's memory may still be in use by earlier work
+                q_emb[:half].copy_(h_emb[:half], non_blocking=True)
+                ev = torch.cuda.Event()
+                with torch.cuda.stream(side):
+                    q_emb[half:].copy_(h_emb[half:], non_blocking=True)
+                    ev.record(side)
+                emb_ready = [(0, half, None), (half, nq, ev)]
+            else:
+                q_emb.copy_(h_emb, non_blocking=True)
+            q_terms = None
+            if q_terms_host is not None:
+                q_terms = torch.as_tensor(q_terms_host).to(dev, non_blocking=True)
+            res = self.search_device(q_emb, q_terms, emb_ready=emb_ready)
+            ids, fin, src, cnt = res
+            outs = [ids, fin, cnt] + ([src] if return_src else [])
+            key = tuple((tuple(t.shape), t.dtype) for t in outs)
+            sets = self._host_out.get(key)
+            if sets is None:
+                sets = self._host_out[key] = [[torch.empty(t.shape, dtype=t.dtype).pin_memory() for t in outs] for _ in range(2)]
+                self._host_turn[key] = 0
+            turn = self._host_turn[key]
+            self._host_turn[key] = turn ^ 1
+            for buf, t in zip(sets[turn], outs):
+                buf.copy_(t, non_blocking=True)
+            main.synchronize()
+            return tuple(buf.numpy() for buf in sets[turn])

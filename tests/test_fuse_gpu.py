@@ -82,3 +82,35 @@ def test_fuse_dict_semantics_duplicates_and_str_ids():
         want = ofu.HybridSearcherOracle(cfg).fuse(dense, bm25, None, path)
         assert got == want
     assert HybridSearcher(cfg).fuse() == []
+
+
+def test_pipeline_host_call_equals_device_call():
+    """HybridPipeline.search_host (split H2D on a copy stream, pinned double-buffered outputs) returns exactly what
+    search_device returns, for pinned and pageable inputs, on consecutive calls."""
+    import torch
+    import ano_rag_b200  # noqa: F401
+    from ano_rag_b200 import engine, synth
+    from ano_rag_b200.pipeline import HybridPipeline
+    from ano_rag_b200.retrieval.hybrid_search import HybridSearcher
+    from ano_rag_b200.utils.bm25_search import GpuBM25
+    dev = torch.device("cuda", 0)
+    n, d, v, k = 30_000, 64, 2000, 20
+    rng = np.random.default_rng(5)
+    ix = engine.DenseIndex(d, storage="bf16", normalize=True)
+    ix.add(rng.standard_normal((n, d)).astype(np.float32))
+    ptr, tok = synth.bm25_corpus(n, v, 20, seed=1)
+    g = GpuBM25.from_token_ids(ptr, tok, v, variant="okapi")
+    cfg = {"retrieval": {"candidate_pool": k, "hybrid": {"fusion_method": "rrf", "rrf_k": 60, "weights": {"dense": 1.0, "bm25": 1.0}}}}
+    pipe = HybridPipeline(ix, g.index, HybridSearcher(cfg), k_dense=k, k_bm25=k, pool=k, device=dev)
+    for nq in (1300, 70):                                        # split copy / single copy
+        q = rng.standard_normal((nq, d)).astype(np.float32)
+        qt = synth.bm25_queries(nq, ptr, tok, v, seed=nq)
+        want = [t.cpu().numpy() for t in pipe.search_device(torch.from_numpy(q).to(dev), torch.from_numpy(qt).to(dev))]
+        first = pipe.search_host(torch.from_numpy(q).pin_memory(), torch.from_numpy(qt).pin_memory(), return_src=True)
+        kept = [a.copy() for a in first]
+        again = pipe.search_host(q, qt, return_src=True)          # pageable numpy input, the other buffer set
+        for got in (kept, again):
+            assert np.array_equal(got[0], want[0]) and np.array_equal(got[1], want[1])
+            assert np.array_equal(got[2], want[3]) and np.array_equal(got[3], want[2], equal_nan=True)
+        assert np.array_equal(first[0], want[0])                  # the first call's views are still intact after one more call
+    g.close(); ix.close()
