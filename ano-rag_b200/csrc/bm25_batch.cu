@@ -788,11 +788,9 @@ bm25_h3_decide_kernel(const BatchScratch sc) {
 }
 
 // ----------------------------------------------------------------------------
-// 2b. plane pass over the (few) queries of h3_list.  HIST: histogram of the plane-only scores of their non-member
-// docs; otherwise: emission against the threshold that bm25_h3_threshold_kernel derived from the histogram.
-// All three launches return at once when the list is empty.
+// 2b. plane pass over the (few) queries of h3_list: emission against the threshold that bm25_h3_threshold_kernel
+// derived from the histogram the main sweep filled.  Returns at once when the list is empty.
 // ----------------------------------------------------------------------------
-template <bool HIST>
 __global__ void __launch_bounds__(PL_WARPS * 32, 1)
 bm25_plane_list_kernel(const Bm25Dev ix, const BatchScratch sc) {
   extern __shared__ __align__(16) double pll_smem[];           // [n_planes][256]
@@ -812,12 +810,9 @@ bm25_plane_list_kernel(const Bm25Dev ix, const BatchScratch sc) {
     __syncthreads();
     for (int idx = warp; idx < n3; idx += PL_WARPS) {
       const int64_t q = sc.h3_list[idx];
-      double thr_d = 0.0;
-      if (!HIST) {
-        const unsigned long long t = sc.thr[q];
-        if (t == THR_SKIP) continue;
-        thr_d = key_f64(t);
-      }
+      const unsigned long long t = sc.thr[q];
+      if (t == THR_SKIP) continue;
+      const double thr_d = key_f64(t);
       double acc[8];
 #pragma unroll
       for (int r = 0; r < 8; ++r) acc[r] = 0.0;
@@ -835,22 +830,17 @@ bm25_plane_list_kernel(const Bm25Dev ix, const BatchScratch sc) {
       const uint32_t mb = bm_bytes[(tile * sc.nq + q) * (PLANE_TILE / 8) + lane];
 #pragma unroll
       for (int r = 0; r < 8; ++r) {
-        const bool ok = acc[r] > 0.0 && !((mb >> r) & 1u);
-        if (HIST) {
-          if (ok) atomicAdd(&sc.hist[static_cast<size_t>(idx) * H3_BINS + h3_bin(acc[r])], 1u);
-        } else {
-          const bool p = ok && acc[r] >= thr_d;
-          const uint32_t m = __ballot_sync(0xffffffffu, p);
-          if (m == 0u) continue;
-          int base = 0;
-          if (lane == 0) base = atomicAdd(&sc.e_cnt[q], __popc(m));
-          base = __shfl_sync(0xffffffffu, base, 0);
-          if (p) {
-            const int pos = base + __popc(m & lt);
-            if (pos < E_CAP) {
-              sc.e_key[q * E_CAP + pos] = f64_key(acc[r]);
-              sc.e_doc[q * E_CAP + pos] = static_cast<uint32_t>(tile * PLANE_TILE + 8 * lane + r);
-            }
+        const bool p = acc[r] > 0.0 && !((mb >> r) & 1u) && acc[r] >= thr_d;
+        const uint32_t m = __ballot_sync(0xffffffffu, p);
+        if (m == 0u) continue;
+        int base = 0;
+        if (lane == 0) base = atomicAdd(&sc.e_cnt[q], __popc(m));
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (p) {
+          const int pos = base + __popc(m & lt);
+          if (pos < E_CAP) {
+            sc.e_key[q * E_CAP + pos] = f64_key(acc[r]);
+            sc.e_doc[q * E_CAP + pos] = static_cast<uint32_t>(tile * PLANE_TILE + 8 * lane + r);
           }
         }
       }
@@ -972,9 +962,7 @@ static int batch_set_attrs() {
     if (err == cudaSuccess)
       err = cudaFuncSetAttribute(bm25_plane_pass_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PL_SMEM_MAX);
     if (err == cudaSuccess)
-      err = cudaFuncSetAttribute(bm25_plane_list_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_PLANES * PLANE_TILE * 8);
-    if (err == cudaSuccess)
-      err = cudaFuncSetAttribute(bm25_plane_list_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_PLANES * PLANE_TILE * 8);
+      err = cudaFuncSetAttribute(bm25_plane_list_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_PLANES * PLANE_TILE * 8);
     if (err == cudaSuccess)
       err = cudaFuncSetAttribute(bm25_flag_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 4096 * 16);
     if (err == cudaSuccess)
@@ -1079,7 +1067,7 @@ static int batch_chunk(const Bm25Dev& ix, const int32_t* d_terms, int64_t nq, in
     // queries without a bound from list A: their score histogram was filled by the sweep above -> threshold -> emission
     bm25_h3_threshold_kernel<<<H3_MAX / 4, 128, 0, st>>>(k, sc);
     ARB_LAUNCH_OK();
-    bm25_plane_list_kernel<false><<<static_cast<unsigned>(sets), PL_WARPS * 32, plane_smem, st>>>(ix, sc);
+    bm25_plane_list_kernel<<<static_cast<unsigned>(sets), PL_WARPS * 32, plane_smem, st>>>(ix, sc);
     ARB_LAUNCH_OK();
   }
   {

@@ -253,3 +253,35 @@ def fi_restricted(qv, x, rows, k):
     s = x[rows] @ qv
     order = np.lexsort((rows, -s.astype(np.float64)))[:k]
     return rows[order]
+
+
+def _clustered(seed, n, d, n_clusters, spread):
+    rng = np.random.default_rng(seed)
+    cent = rng.standard_normal((n_clusters, d)).astype(np.float32)
+    x = cent[rng.integers(0, n_clusters, n)] + spread * rng.standard_normal((n, d)).astype(np.float32)
+    return x.astype(np.float32)
+
+
+def test_graph_similarity_oracle_matches_reference_golden(golden_dir):
+    """_find_embedding_candidates (graph/graph_retriever.py:153-170) and extract_semantic_similarity_relations
+    (graph/relation_extractor.py:591-633) restated; same numpy arithmetic, so bit-exact."""
+    import hashlib
+    from oracle import graph_sim
+    with open(os.path.join(golden_dir, "graph_sim_golden.json")) as f:
+        golden = json.load(f)
+    for c in golden["candidates"]:
+        x = _clustered(c["seed"], c["n"], c["d"], 12, 0.35)
+        q = (x[c["seed"]] + 0.1 * np.random.default_rng(c["seed"] + 100).standard_normal(c["d"]).astype(np.float32)).astype(np.float32)
+        got = graph_sim.find_embedding_candidates(x, q, {f"n{i}": i for i in range(c["n_ids"])}, c["top_k"])
+        assert got == c["result"]
+    for c in golden["relations"]:
+        x = _clustered(c["seed"], c["n"], c["d"], c["n_clusters"], c["spread"])
+        if c["zero_row"] is not None:
+            x[c["zero_row"]] = 0.0
+        rel = graph_sim.semantic_similarity_relations([{"note_id": f"n{i}"} for i in range(c["n"])], x, c["threshold"], 0.5)
+        assert len(rel) == c["count"]
+        text = "".join(f"{e['source_id']},{e['target_id']},{e['metadata']['similarity_rank']};" for e in rel)
+        assert hashlib.sha256(text.encode()).hexdigest() == c["digest"]
+        for e, want in zip(rel[::c["stride"]], c["pairs"]):
+            assert [int(e["source_id"][1:]), int(e["target_id"][1:])] == want[:2] and e["metadata"]["similarity_rank"] == want[3]
+            assert e["metadata"]["cosine_similarity"] == float.fromhex(want[2]) and float(e["weight"]) == float.fromhex(want[4])
