@@ -18,8 +18,7 @@
 namespace arb {
 
 constexpr int FUSE_THREADS = 256;
-constexpr int FUSE_MAXK = 256;                 // entries per source
-constexpr int FUSE_HASH = 2048;                // >= 2 * 4 * FUSE_MAXK / ... (load factor <= 0.5)
+constexpr int FUSE_MAXK = 256;                 // entries per source (largest instantiation)
 constexpr int FUSE_MAXU = 4 * FUSE_MAXK;       // union size bound (also sort size, power of two)
 
 struct FuseParams {
@@ -38,16 +37,21 @@ struct FuseParams {
   int32_t* out_count;
 };
 
+// Shared memory of one query, sized by the per-source capacity MAXK (128 or 256): 41 KB / 82 KB, i.e. five / two
+// CTAs per SM -- the kernel is latency-bound (barriers of a small sort), so residency is what it scales with.
+template <int MAXK>
 struct FuseSmem {
-  int64_t ids[4][FUSE_MAXK];
-  double sc[4][FUSE_MAXK];
-  short rank[4][FUSE_MAXK];          // 1-based stable descending rank inside the source (rrf)
-  unsigned long long hkey[FUSE_HASH];
-  short hpos[FUSE_HASH][4];          // position of the id in each source, -1 = absent
-  unsigned long long skey[FUSE_MAXU];
-  uint32_t sseq[FUSE_MAXU];
-  uint32_t sslot[FUSE_MAXU];
-  double hfin[FUSE_HASH];            // final score of the id in hash slot h
+  static constexpr int HASH = 8 * MAXK;        // hash slots: load factor <= 0.5 for 4 full sources
+  static constexpr int MAXU = 4 * MAXK;        // union size bound (also sort size, power of two)
+  int64_t ids[4][MAXK];
+  double sc[4][MAXK];
+  short rank[4][MAXK];               // 1-based stable descending rank inside the source (rrf)
+  unsigned long long hkey[HASH];
+  short hpos[HASH][4];               // position of the id in each source, -1 = absent
+  unsigned long long skey[MAXU];
+  uint32_t sseq[MAXU];
+  uint32_t sslot[MAXU];
+  double hfin[HASH];                 // final score of the id in hash slot h
   double maxv[4];
   int cnt[4];
   int n_union;
@@ -56,15 +60,20 @@ struct FuseSmem {
 
 constexpr unsigned long long HASH_EMPTY = 0xFFFFFFFFFFFFFFFFull;
 
+template <int HASH>
 __device__ __forceinline__ uint32_t hash_id(unsigned long long x) {
   x ^= x >> 33; x *= 0xff51afd7ed558ccdull; x ^= x >> 33; x *= 0xc4ceb9fe1a85ec53ull; x ^= x >> 33;
-  return static_cast<uint32_t>(x) & (FUSE_HASH - 1);
+  return static_cast<uint32_t>(x) & (HASH - 1);
 }
 
+template <int MAXK>
 __global__ void __launch_bounds__(FUSE_THREADS)
 fuse_kernel(const FuseParams p) {
   extern __shared__ __align__(16) uint8_t fsm_raw[];
-  FuseSmem& s = *reinterpret_cast<FuseSmem*>(fsm_raw);
+  using Smem = FuseSmem<MAXK>;
+  constexpr int FUSE_HASH = Smem::HASH;
+  constexpr int FUSE_MAXU = Smem::MAXU;
+  Smem& s = *reinterpret_cast<Smem*>(fsm_raw);
   const int tid = threadIdx.x;
   const int64_t q = blockIdx.x;
 
@@ -131,7 +140,7 @@ fuse_kernel(const FuseParams p) {
       const int64_t id = s.ids[src][j];
       if (id < 0) continue;
       const unsigned long long key = static_cast<unsigned long long>(id);
-      uint32_t h = hash_id(key);
+      uint32_t h = hash_id<FUSE_HASH>(key);
       while (true) {
         const unsigned long long prev = atomicCAS(&s.hkey[h], HASH_EMPTY, key);
         if (prev == HASH_EMPTY || prev == key) { s.hpos[h][src] = static_cast<short>(j); break; }
@@ -642,12 +651,18 @@ extern "C" int arb_fuse(int method, const double weights[4], double rrf_k, int p
   static std::once_flag once;
   static cudaError_t err = cudaSuccess;
   std::call_once(once, [] {
-    err = cudaFuncSetAttribute(fuse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sizeof(FuseSmem)));
+    err = cudaFuncSetAttribute(fuse_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sizeof(FuseSmem<128>)));
+    if (err == cudaSuccess)
+      err = cudaFuncSetAttribute(fuse_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sizeof(FuseSmem<256>)));
   });
   ARB_CUDA(err);
   {
     ProfileScope ps(PROF_FUSE, st);
-    fuse_kernel<<<static_cast<unsigned>(nq), FUSE_THREADS, sizeof(FuseSmem), st>>>(p);
+    const int kmax = std::max(std::max(p.k[0], p.k[1]), std::max(p.k[2], p.k[3]));
+    if (kmax <= 128 && pool <= FuseSmem<128>::MAXU)
+      fuse_kernel<128><<<static_cast<unsigned>(nq), FUSE_THREADS, sizeof(FuseSmem<128>), st>>>(p);
+    else
+      fuse_kernel<256><<<static_cast<unsigned>(nq), FUSE_THREADS, sizeof(FuseSmem<256>), st>>>(p);
   }
   ARB_LAUNCH_OK();
   if (!is_device) {
