@@ -89,6 +89,9 @@ _SIGS = {
     "arb_rescore_khop": (c_int, [c_int64, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                  c_void_p, c_void_p, c_void_p, c_void_p, c_double, c_double, c_double, c_double, c_double,
                                  c_int, c_void_p, c_void_p, c_void_p]),
+    "arb_tfidf_create": (c_int, [POINTER(c_void_p), c_int64, c_int64, c_void_p, c_void_p, c_void_p]),
+    "arb_tfidf_destroy": (c_int, [c_void_p]),
+    "arb_tfidf_search": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p]),
     "arb_merge_topk": (c_int, [c_int, c_void_p, c_void_p, c_int, c_int64, c_int, c_int, c_void_p, c_void_p,
                                c_void_p]),
     "arb_merge_topk_peers": (c_int, [c_int, POINTER(c_void_p), POINTER(c_void_p), c_int, c_int64, c_int64, c_int,

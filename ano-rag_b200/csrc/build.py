@@ -13,7 +13,7 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
-SOURCES = ["common.cu", "dense.cu", "bm25.cu", "bm25_batch.cu", "fuse.cu"]
+SOURCES = ["common.cu", "dense.cu", "bm25.cu", "bm25_batch.cu", "fuse.cu", "tfidf.cu"]
 HEADERS = ["common.cuh", "ptx.cuh", "bm25.cuh", os.path.join(ROOT, "include", "anorag_b200.h")]
 LIB = os.path.join(HERE, "libanorag_b200.so")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]

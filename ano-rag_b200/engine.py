@@ -411,3 +411,47 @@ def merge_topk(scores, ids):
         nat.check(nat.lib.arb_merge_topk(bs.code, bs.ptr, bi.ptr, parts, nq, k, 0, o_s.data_ptr(), o_i.data_ptr(),
                                          _stream_ptr(bs.device)))
     return o_s, o_i
+
+
+class TfidfIndex:
+    """Device-resident L2-normalised TF-IDF document matrix, term-major (see csrc/tfidf.cu): the cosine top-k of
+    the reference's "BM25 fallback" (vector_store/retriever.py:966-1002)."""
+
+    def __init__(self, matrix):
+        """``matrix``: scipy sparse [n_docs, n_terms] with rows already L2-normalised (sklearn ``normalize``)."""
+        csc = matrix.tocsc()
+        csc.sort_indices()
+        self.n_docs, self.n_terms = int(csc.shape[0]), int(csc.shape[1])
+        ptr = np.ascontiguousarray(csc.indptr, dtype=np.int64)
+        doc = np.ascontiguousarray(csc.indices, dtype=np.int32)
+        val = np.ascontiguousarray(csc.data, dtype=np.float64)
+        h = ctypes.c_void_p()
+        nat.check(nat.lib.arb_tfidf_create(ctypes.byref(h), self.n_docs, self.n_terms, ptr.ctypes.data, doc.ctypes.data,
+                                           val.ctypes.data))
+        self._h = h
+
+    def close(self):
+        if getattr(self, "_h", None):
+            nat.lib.arb_tfidf_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def search(self, queries, k: int):
+        """``queries``: scipy sparse [nq, n_terms], rows L2-normalised -> (scores fp64 [nq,k], ids int64 [nq,k]);
+        descending similarity, larger doc id first among equal ones, only similarities > 0 (id -1 beyond)."""
+        csr = queries.tocsr()
+        csr.sort_indices()
+        nq = int(csr.shape[0])
+        ptr = np.ascontiguousarray(csr.indptr, dtype=np.int64)
+        term = np.ascontiguousarray(csr.indices, dtype=np.int32)
+        val = np.ascontiguousarray(csr.data, dtype=np.float64)
+        scores = np.empty((nq, k), dtype=np.float64)
+        ids = np.empty((nq, k), dtype=np.int64)
+        nat.check(nat.lib.arb_tfidf_search(self._h, nq, ptr.ctypes.data, term.ctypes.data, val.ctypes.data, int(k),
+                                           scores.ctypes.data, ids.ctypes.data, _stream_ptr()))
+        return scores, ids

@@ -27,6 +27,7 @@ import numpy as np
 from .._log import logger
 from ..config import config
 from .vector_index import VectorIndex
+from .. import engine
 
 try:
     import torch
@@ -73,6 +74,11 @@ class VectorRetriever:
         self.hybrid_config = config.get("vector_store.hybrid_search", {}) or {}              # :85-87
         self.enable_hybrid_search = bool(self.hybrid_config.get("enable_hybrid_search", False))
         self.bm25_corpus = None
+        self.bm25_enabled = config.get("vector_store.bm25_fallback.enabled", True)           # :77
+        self.tfidf_vectorizer = None
+        self.tfidf_matrix = None
+        self.processed_texts: List[str] = []
+        self._tfidf_index = None
         if self.enable_hybrid_search:
             try:
                 from ..retrieval.hybrid_search import create_hybrid_searcher
@@ -108,6 +114,9 @@ class VectorRetriever:
             if not self.vector_index.add_vectors(self.note_embeddings, note_ids):
                 logger.error("Failed to add vectors to index")
                 return False
+            if self.bm25_enabled:                                                            # :162-164
+                logger.info("Building BM25 index for fallback retrieval")
+                self._build_bm25_index(atomic_notes)
             if self.enable_hybrid_search and self.hybrid_searcher:
                 try:
                     from ..utils.bm25_search import build_bm25_corpus
@@ -478,8 +487,93 @@ class VectorRetriever:
                 "index_stats": self.vector_index.get_index_stats(),
                 "top_k": self.top_k, "similarity_threshold": self.similarity_threshold}
 
+    # ------------------------------------------------------------------ TF-IDF "BM25 fallback" (:924-1032)
+    def _build_bm25_index(self, atomic_notes: List[Dict[str, Any]]) -> None:
+        """sklearn's TfidfVectorizer over the pre-processed contents, exactly as the reference configures it
+        (:941-946); the L2-normalised matrix goes to the device (``engine.TfidfIndex``)."""
+        try:
+            from sklearn.feature_extraction.text import TfidfVectorizer
+            from sklearn.preprocessing import normalize
+            texts = [self._preprocess_text(note.get("content", "")) if note.get("content", "") else "" for note in atomic_notes]
+            self.processed_texts = texts
+            self.tfidf_vectorizer = TfidfVectorizer(lowercase=True, stop_words="english", max_features=10000, ngram_range=(1, 2))
+            if texts:
+                self.tfidf_matrix = self.tfidf_vectorizer.fit_transform(texts)
+                if self._tfidf_index is not None:
+                    self._tfidf_index.close()
+                # cosine_similarity normalises its operands again (sklearn.metrics.pairwise): do it once here
+                self._tfidf_index = engine.TfidfIndex(normalize(self.tfidf_matrix, copy=True))
+                logger.info(f"BM25 index built with {len(texts)} documents")
+            else:
+                logger.warning("No valid texts found for BM25 indexing")
+        except Exception as e:
+            logger.error(f"Failed to build BM25 index: {e}")
+            self.bm25_enabled = False
+
+    @staticmethod
+    def _preprocess_text(text: str) -> str:
+        """:958-964"""
+        import re
+        text = re.sub(r"[^a-zA-Z0-9\s]", " ", text)
+        text = re.sub(r"\s+", " ", text)
+        return text.strip().lower()
+
+    def _bm25_search_batch(self, queries: List[str], top_k: int = 20) -> List[List[Dict[str, Any]]]:
+        """Many fallback queries through one device call (the reference answers them one by one, :966)."""
+        if not self.bm25_enabled or not self.tfidf_vectorizer or self._tfidf_index is None:
+            return [[] for _ in queries]
+        try:
+            from sklearn.preprocessing import normalize
+            qm = normalize(self.tfidf_vectorizer.transform([self._preprocess_text(q) for q in queries]), copy=True)
+            scores, ids = self._tfidf_index.search(qm, int(top_k))
+            out = []
+            for query, srow, irow in zip(queries, scores.tolist(), ids.tolist()):
+                results = []
+                for sim, idx in zip(srow, irow):
+                    if 0 <= idx < len(self.atomic_notes) and sim > 0:              # :985
+                        note = self.atomic_notes[idx].copy()
+                        note["retrieval_info"] = {"similarity": float(sim), "score": float(sim), "rank": len(results) + 1,
+                                                  "query": query, "retrieval_method": "bm25_fallback"}
+                        results.append(note)
+                logger.info(f"BM25 fallback search returned {len(results)} results")
+                out.append(results)
+            return out
+        except Exception as e:
+            logger.error(f"BM25 search failed: {e}")
+            return [[] for _ in queries]
+
+    def _bm25_search(self, query: str, top_k: int = 20) -> List[Dict[str, Any]]:
+        """:966-1002"""
+        return self._bm25_search_batch([query], top_k)[0]
+
+    def search_with_namespace_fallback(self, queries: List[str], dataset: str, qid: str, top_k: Optional[int] = None,
+                                       similarity_threshold: Optional[float] = None, include_metadata: bool = True,
+                                       namespace_filter: Optional[Callable] = None) -> List[List[Dict[str, Any]]]:
+        """:1004-1032.  ``namespace_filter(notes, dataset, qid)`` defaults to the reference's
+        ``utils.dataset_guard.filter_notes_by_namespace`` (imported at call time, as the reference does); the
+        queries whose vector results are all filtered away share one batched fallback call."""
+        if namespace_filter is None:
+            from utils.dataset_guard import filter_notes_by_namespace as namespace_filter
+        vector_results = self.search(queries, top_k, similarity_threshold, include_metadata)
+        final = [namespace_filter(res, dataset, qid) for res in vector_results]
+        need = [i for i, res in enumerate(final) if not res] if self.bm25_enabled else []
+        if need:
+            fallback = self._bm25_search_batch([queries[i] for i in need], top_k or self.top_k)
+            for i, res in zip(need, fallback):
+                logger.info(f"No namespace matches for query {i + 1}, trying BM25 fallback")
+                kept = namespace_filter(res, dataset, qid)
+                if kept:
+                    logger.info(f"BM25 fallback found {len(kept)} namespace matches")
+                    final[i] = kept
+                else:
+                    logger.warning(f"No results found for query '{queries[i]}' in namespace {dataset}/{qid}")
+        return final
+
     def cleanup(self):
         try:
+            if getattr(self, "_tfidf_index", None) is not None:
+                self._tfidf_index.close()
+                self._tfidf_index = None
             self.vector_index.cleanup()
             if self.bm25_corpus is not None and hasattr(self.bm25_corpus, "close"):
                 self.bm25_corpus.close()

@@ -271,6 +271,24 @@ ARB_API int arb_rescore_khop(int64_t nq, int nc, const double* dense, const doub
                      void* stream);
 
 /* ------------------------------------------------------------------------- *
+ * TF-IDF cosine "BM25 fallback" of VectorRetriever (reference vector_store/retriever.py:924-1002):
+ * cosine_similarity(query_vector, tfidf_matrix) (:977) + argsort top-k (:980) + `similarity > 0` (:985).
+ * The host keeps sklearn's TfidfVectorizer; the library holds the L2-normalised document matrix term-major
+ * (CSC of the doc x term matrix: for term t the postings term_ptr[t] .. term_ptr[t+1], doc ids strictly
+ * ascending) and accumulates exactly like scipy's sparse product: per doc, query_weight * doc_weight over the
+ * query's terms in ascending term order, every product and sum rounded separately.
+ * ------------------------------------------------------------------------- */
+typedef struct arb_tfidf arb_tfidf;
+ARB_API int arb_tfidf_create(arb_tfidf** out, int64_t n_docs, int64_t n_terms, const int64_t* term_ptr,
+                     const int32_t* post_doc, const double* post_val);          /* host arrays */
+ARB_API int arb_tfidf_destroy(arb_tfidf* index);
+/* nq sparse, L2-normalised queries in CSR form (q_term ascending inside a query); host arrays in and out.
+ * out_scores / out_ids [nq, k]: descending similarity; among EQUAL similarities the larger doc id first (the reference's
+ * np.argsort is an unstable sort, so it leaves that order unspecified); only similarities > 0; id -1 / score 0 beyond. */
+ARB_API int arb_tfidf_search(const arb_tfidf* index, int64_t nq, const int64_t* q_ptr, const int32_t* q_term,
+                     const double* q_val, int k, double* out_scores, int64_t* out_ids, void* stream);
+
+/* ------------------------------------------------------------------------- *
  * Multi-GPU merge (new design): `parts` per-shard top-k lists,
  * laid out [parts, nq, k] as an NCCL all-gather leaves them, merged to the global
  * top-k (descending score, ascending id; id < 0 = empty).  Device buffers.

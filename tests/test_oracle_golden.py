@@ -285,3 +285,24 @@ def test_graph_similarity_oracle_matches_reference_golden(golden_dir):
         for e, want in zip(rel[::c["stride"]], c["pairs"]):
             assert [int(e["source_id"][1:]), int(e["target_id"][1:])] == want[:2] and e["metadata"]["similarity_rank"] == want[3]
             assert e["metadata"]["cosine_similarity"] == float.fromhex(want[2]) and float(e["weight"]) == float.fromhex(want[4])
+
+
+def _tfidf_corpus(seed, n, vocab):
+    import random
+    rng = random.Random(seed)
+    words = [f"w{i}" for i in range(vocab)] + ["the", "and", "of"]
+    return [{"note_id": f"n{i}", "content": " ".join(rng.choices(words, k=rng.randint(0, 25))) + ("!" if i % 3 == 0 else "")}
+            for i in range(n)]
+
+
+def test_tfidf_fallback_oracle_matches_reference_golden(golden_dir):
+    """VectorRetriever._bm25_search (vector_store/retriever.py:966-1002): ids, ranks and similarities bit-exact."""
+    from oracle import tfidf
+    with open(os.path.join(golden_dir, "tfidf_golden.json")) as f:
+        golden = json.load(f)
+    for c in golden["cases"][:3]:
+        fb = tfidf.TfidfFallback(_tfidf_corpus(c["seed"], c["n"], c["vocab"]))
+        assert len(fb.vectorizer.vocabulary_) == c["features"]
+        for r in c["results"]:
+            got = fb.search(r["query"], c["top_k"])
+            assert [i for i, _ in got] == r["ids"] and [s for _, s in got] == [float.fromhex(v) for v in r["sims"]]
