@@ -17,6 +17,8 @@
 // blk_off[t*NB + b] is where block b of term t starts.
 #include "bm25.cuh"
 
+#include <cub/cub.cuh>
+
 #include <algorithm>
 #include <cstdlib>
 #include <mutex>
@@ -96,6 +98,59 @@ __global__ void bm25_plane_gmax_kernel(const double* __restrict__ tmax, int64_t 
   double m = 0.0;
   for (int64_t t = 0; t < n_tiles; ++t) m = fmax(m, tmax[t * n_planes + s]);
   gmax[s] = m;
+}
+
+// fp32 copy of the planes for the screening pass, rounded up (so fp32 sums with upward rounding bound the fp64 sums)
+__global__ void bm25_plane32_kernel(const double* __restrict__ planes, int64_t n_rows, float* __restrict__ planes32) {
+  const int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  if (i >= n_rows * PLANE_TILE) return;
+  const int64_t row = i >> PLANE_TILE_LOG2;
+  const uint32_t d = static_cast<uint32_t>(i) & (PLANE_TILE - 1);
+  planes32[row * PLANE_TILE + pos32(d)] = __double2float_ru(planes[row * PLANE_TILE + plane_pos(d)]);
+}
+
+// term owning posting i: the last t with term_ptr[t] <= i
+__device__ __forceinline__ int64_t term_of_posting(const int64_t* __restrict__ term_ptr, int64_t n_terms, int64_t i) {
+  int64_t lo = 0, hi = n_terms;                                  // answer in [lo, hi)
+  while (hi - lo > 1) {
+    const int64_t mid = (lo + hi) >> 1;
+    if (term_ptr[mid] <= i) lo = mid; else hi = mid;
+  }
+  return lo;
+}
+// doc-major rows, step 1: sort key of every posting = its doc (sparse term with idf != 0) or the sentinel n_docs
+__global__ void bm25_sparse_key_kernel(const int64_t* __restrict__ term_ptr, int64_t n_terms, const int32_t* __restrict__ doc,
+                                       const int* __restrict__ plane_slot, const double* __restrict__ idf, int64_t n_post,
+                                       uint32_t sentinel, uint32_t* __restrict__ key, uint32_t* __restrict__ val) {
+  const int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  if (i >= n_post) return;
+  const int64_t t = term_of_posting(term_ptr, n_terms, i);
+  key[i] = (plane_slot[t] >= 0 || idf[t] == 0.0) ? sentinel : static_cast<uint32_t>(doc[i]);
+  val[i] = static_cast<uint32_t>(i);
+}
+// step 2 (after a stable sort by key, which keeps a doc's postings in ascending term order): row offsets
+__global__ void bm25_drow_off_kernel(const uint32_t* __restrict__ sorted_key, int64_t n_post, int64_t n_docs,
+                                     uint32_t* __restrict__ drow_off) {
+  const int64_t d = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  if (d > n_docs) return;
+  int64_t lo = 0, hi = n_post;
+  while (lo < hi) {
+    const int64_t mid = (lo + hi) >> 1;
+    if (sorted_key[mid] < static_cast<uint32_t>(d)) lo = mid + 1; else hi = mid;
+  }
+  drow_off[d] = static_cast<uint32_t>(lo);
+}
+// step 3: term id and finished contribution idf * g of every row entry
+__global__ void bm25_drow_fill_kernel(const uint32_t* __restrict__ sorted_val, int64_t n_sp, const int64_t* __restrict__ term_ptr,
+                                      int64_t n_terms, const int32_t* __restrict__ gcode, const double* __restrict__ idf,
+                                      const double* __restrict__ gtab, uint32_t* __restrict__ drow_term,
+                                      double* __restrict__ drow_val) {
+  const int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  if (i >= n_sp) return;
+  const int64_t p = sorted_val[i];
+  const int64_t t = term_of_posting(term_ptr, n_terms, p);
+  drow_term[i] = static_cast<uint32_t>(t);
+  drow_val[i] = __dmul_rn(idf[t], gtab[gcode[p]]);
 }
 
 // ---------------------------------------------------------------- scoring core
@@ -650,10 +705,70 @@ extern "C" int arb_bm25_create(arb_bm25** out, int64_t n_docs, int64_t n_terms, 
         bm25_plane_gmax_kernel<<<(n_planes + 127) / 128, 128, 0, st>>>(bm->plane_tmax, n_tiles, n_planes, bm->plane_tmax + nt);
         count_launch(2);
       }
+      if (e == cudaSuccess && n_planes > 0) {
+        const int64_t n_rows = n_tiles * n_planes;
+        if (cudaMalloc(&bm->planes32, static_cast<size_t>(n_rows) * PLANE_TILE * 4) != cudaSuccess) {
+          cudaGetLastError(); set_error("arb_bm25_create: out of device memory (fp32 planes)"); return fail(ARB_ENOMEM);
+        }
+        bm25_plane32_kernel<<<static_cast<unsigned>((n_rows * PLANE_TILE + 255) / 256), 256, 0, st>>>(bm->planes, n_rows, bm->planes32);
+        count_launch();
+      }
       if (e == cudaSuccess) e = cudaStreamSynchronize(st);       // pslot dies at scope end
       if (e != cudaSuccess) return fail(cuda_fail(e, "bm25 term planes", __FILE__, __LINE__));
       bm->dev.n_planes = n_planes;
       bm->dev.n_tiles = n_tiles;
+    }
+    // doc-major rows of the sparse postings (the batched pipeline joins them with the batch's query-term index)
+    {
+      int64_t n_sp = 0;
+      if (cudaMalloc(&bm->drow_off, static_cast<size_t>(n_docs + 1) * 4) != cudaSuccess) {
+        cudaGetLastError(); set_error("arb_bm25_create: out of device memory (doc rows)"); return fail(ARB_ENOMEM);
+      }
+      if (n_post > 0) {
+        AsyncBuf k_in, k_out, v_in, v_out, tmp;
+        size_t tmp_bytes = 0;
+        const size_t np4 = static_cast<size_t>(n_post) * 4;
+        e = k_in.alloc(np4, st);
+        if (e == cudaSuccess) e = k_out.alloc(np4, st);
+        if (e == cudaSuccess) e = v_in.alloc(np4, st);
+        if (e == cudaSuccess) e = v_out.alloc(np4, st);
+        int end_bit = 1;
+        while ((int64_t(1) << end_bit) <= n_docs) ++end_bit;       // keys are in [0, n_docs]
+        if (e == cudaSuccess)
+          e = cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, k_in.as<uint32_t>(), k_out.as<uint32_t>(), v_in.as<uint32_t>(),
+                                              v_out.as<uint32_t>(), static_cast<int>(n_post), 0, end_bit, st);
+        if (e == cudaSuccess) e = tmp.alloc(tmp_bytes, st);
+        if (e != cudaSuccess) { cudaGetLastError(); set_error("arb_bm25_create: out of device memory (doc-row build)"); return fail(ARB_ENOMEM); }
+        bm25_sparse_key_kernel<<<static_cast<unsigned>((n_post + 255) / 256), 256, 0, st>>>(
+            d_ptr.as<int64_t>(), n_terms, d_doc.as<int32_t>(), bm->plane_slot, bm->idf, n_post, static_cast<uint32_t>(n_docs),
+            k_in.as<uint32_t>(), v_in.as<uint32_t>());
+        count_launch();
+        e = cub::DeviceRadixSort::SortPairs(tmp.p, tmp_bytes, k_in.as<uint32_t>(), k_out.as<uint32_t>(), v_in.as<uint32_t>(),
+                                            v_out.as<uint32_t>(), static_cast<int>(n_post), 0, end_bit, st);
+        if (e != cudaSuccess) return fail(cuda_fail(e, "bm25 doc-row sort", __FILE__, __LINE__));
+        bm25_drow_off_kernel<<<static_cast<unsigned>((n_docs + 1 + 255) / 256), 256, 0, st>>>(k_out.as<uint32_t>(), n_post, n_docs, bm->drow_off);
+        count_launch();
+        uint32_t h_nsp = 0;
+        e = cudaMemcpyAsync(&h_nsp, bm->drow_off + n_docs, 4, cudaMemcpyDeviceToHost, st);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+        if (e != cudaSuccess) return fail(cuda_fail(e, "bm25 doc-row offsets", __FILE__, __LINE__));
+        n_sp = h_nsp;
+        if (cudaMalloc(&bm->drow_term, std::max<size_t>(n_sp, 1) * 4) != cudaSuccess ||
+            cudaMalloc(&bm->drow_val, std::max<size_t>(n_sp, 1) * 8) != cudaSuccess) {
+          cudaGetLastError(); set_error("arb_bm25_create: out of device memory (doc rows)"); return fail(ARB_ENOMEM);
+        }
+        if (n_sp > 0) {
+          bm25_drow_fill_kernel<<<static_cast<unsigned>((n_sp + 255) / 256), 256, 0, st>>>(
+              v_out.as<uint32_t>(), n_sp, d_ptr.as<int64_t>(), n_terms, d_code.as<int32_t>(), bm->idf, bm->gtab, bm->drow_term, bm->drow_val);
+          count_launch();
+        }
+        e = cudaStreamSynchronize(st);
+        if (e != cudaSuccess) return fail(cuda_fail(e, "bm25 doc rows", __FILE__, __LINE__));
+      } else {
+        e = cudaMemsetAsync(bm->drow_off, 0, static_cast<size_t>(n_docs + 1) * 4, st);
+        if (e != cudaSuccess) return fail(cuda_fail(e, "bm25 doc rows", __FILE__, __LINE__));
+      }
+      bm->dev.n_sp = n_sp;
     }
     e = cudaGetLastError();
     if (e == cudaSuccess) e = cudaStreamSynchronize(st);
@@ -668,6 +783,8 @@ extern "C" int arb_bm25_create(arb_bm25** out, int64_t n_docs, int64_t n_terms, 
   bm->dev.plane_slot = bm->plane_slot; bm->dev.planes = bm->planes;
   bm->dev.plane_tmax = bm->plane_tmax;
   bm->dev.plane_gmax = bm->plane_tmax ? bm->plane_tmax + static_cast<size_t>(bm->dev.n_tiles) * bm->dev.n_planes : nullptr;
+  bm->dev.planes32 = bm->planes32;
+  bm->dev.drow_off = bm->drow_off; bm->dev.drow_term = bm->drow_term; bm->dev.drow_val = bm->drow_val;
   *out = bm;
   return ARB_OK;
 }
@@ -683,6 +800,10 @@ extern "C" int arb_bm25_destroy(arb_bm25* bm) {
   if (bm->plane_slot) cudaFree(bm->plane_slot);
   if (bm->planes) cudaFree(bm->planes);
   if (bm->plane_tmax) cudaFree(bm->plane_tmax);
+  if (bm->planes32) cudaFree(bm->planes32);
+  if (bm->drow_off) cudaFree(bm->drow_off);
+  if (bm->drow_term) cudaFree(bm->drow_term);
+  if (bm->drow_val) cudaFree(bm->drow_val);
   delete bm;
   return ARB_OK;
 }

@@ -49,7 +49,22 @@ struct Bm25Dev {
   const double* plane_tmax;     // [n_tiles * n_planes] largest value of each plane inside each tile (>= +0.0)
   const double* plane_gmax;     // [n_planes] largest value of each plane
   int64_t n_tiles;              // 256-doc tiles
+  // fp32 copy of the planes, every value rounded UP (screening pass: an fp32 sum with upward rounding bounds
+  // the in-order fp64 sum from above), tile-major with pos32() inside a row
+  const float* planes32;        // [n_tiles * n_planes * 256]
+  // doc-major rows of the non-plane ("sparse") postings with idf != 0, sorted by term inside a doc; the value is
+  // the posting's finished contribution idf * g (one fp64 rounding, as everywhere else)
+  int64_t n_sp;
+  const uint32_t* drow_off;     // [n_docs + 1]
+  const uint32_t* drow_term;    // [n_sp]
+  const double* drow_val;       // [n_sp]
 };
+
+// Position of doc d (0..255) inside a 256-entry fp32 plane-tile row: lane l owns docs 8l .. 8l+7 and reads them as
+// two 16-byte chunks; chunk j of all lanes is contiguous (conflict-free LDS.128):  d = 8l + 4j + e -> (j*32 + l)*4 + e.
+__host__ __device__ __forceinline__ uint32_t pos32(uint32_t d) {
+  return ((((d >> 2) & 1u) * 32u + (d >> 3)) << 2) | (d & 3u);
+}
 
 int merge_topk_device(int score_dtype, const void* scores, const int64_t* ids, int parts, int64_t nq, int k,
                       void* out_scores, int64_t* out_ids, cudaStream_t st);   // fuse.cu
@@ -77,5 +92,9 @@ struct arb_bm25 {
   int* plane_slot = nullptr;
   double* planes = nullptr;
   double* plane_tmax = nullptr;   // followed by plane_gmax
+  float* planes32 = nullptr;
+  uint32_t* drow_off = nullptr;
+  uint32_t* drow_term = nullptr;
+  double* drow_val = nullptr;
   std::vector<int64_t> df;      // host copy of per-term df (roofline accounting)
 };

@@ -1,55 +1,59 @@
-// Batched BM25 top-k (sm_100a): the plane / sparse pipeline behind arb_bm25_search.
+// Batched BM25 top-k (sm_100a): the tile-major join pipeline behind arb_bm25_search.
 //
 // Replaces corpus.get_scores() + top-k for a whole query batch (reference
 // utils/bm25_search.py:309 -> rank_bm25 BM25Okapi.get_scores / SimpleBM25.get_scores :43-63).
 //
-// Why two passes.  In a Zipf corpus a few dozen terms own almost all postings (cfg3: the 64
-// densest terms carry 98 % of the postings a query touches).  Scatter-adding those postings
-// into shared-memory accumulators costs three 64-bit shared accesses each; instead every such
-// term is stored as a doc-major fp64 "plane" of its finished contributions idf*g (+0.0 where
-// the term is absent), and a CTA that has staged one 256-doc tile of all planes in shared
-// memory scores that tile for EVERY query of the batch with register accumulators:
-// one conflict-free LDS + one DADD per (query token, doc).  The fp64 addition order of the
-// reference (query-token order per doc) is kept exactly:
+// In a Zipf corpus a few dozen terms own almost all postings (cfg3: the 96 densest terms carry 98 % of the
+// postings a query touches).  Every such term is stored as a doc-major fp64 "plane" of its finished
+// contributions idf*g (+0.0 where the term is absent); all other ("sparse") postings are stored twice: term-major
+// for the per-query kernel and doc-major ("doc rows": per doc its sparse terms, ascending, with the finished
+// contribution).  A batch is scored in doc order, 256-doc tiles at a time, where the tile of all planes sits in
+// shared memory:
 //
-//   1. sparse pass   (one warp per query)  docs that match at least one non-plane token
-//      ("members") get their complete score in query-token order: postings of the sparse tokens
-//      are scattered into a per-warp 1024-doc accumulator tile, plane tokens are looked up for the
-//      members only.  The members are recorded in a per-query bitmap; their top-k (list A) gives
-//      a lower bound on the final k-th score.
-//   2. plane pass    (one CTA per 256-doc tile, all queries)  every other doc has plane tokens
-//      only, so its score is the in-order sum of plane values; docs that reach A's k-th score
-//      and are not members are appended to the query's list E.
-//   3. final merge   A + E -> top-k by (score desc, doc asc).
-//   4. fallback      queries whose A holds fewer than k docs while they have plane tokens (no
-//      usable bound), or whose E overflowed, are re-scored by the per-query kernel (bm25.cu).
+//   0. query-term index   the batch's sparse query tokens grouped by term: bt_off[term] .. -> (query, position).
+//   1. member pass        every doc row of a tile is JOINED with that index: each (doc, sparse term) posting
+//      whose term occurs in the batch yields the (query, position) records that match it, one pair per thread
+//      (counts -> CTA-wide scan -> 512 independent pairs in flight).  The thread computes the COMPLETE score of
+//      its (query, doc) in the reference's order -- query tokens first to last, plane tokens from the staged
+//      tile, the query's other sparse tokens looked up in the doc's own row (a 384-bit two-hash Bloom filter of
+//      the row answers almost all of those look-ups; positives are deferred and scored together) -- and, when
+//      another sparse token of the query matches the doc at an earlier position, leaves the pair to that thread.  Scores
+//      above the query's running bound are appended to its candidate list.  The corpus is swept in a few rounds
+//      of growing size; between rounds a compaction kernel cuts every list back to its k best and publishes the
+//      k-th score as the bound of the next round (rounds go in ascending doc order, so a later doc that only
+//      ties the bound loses the tie).  The last compaction leaves list A = top-k of the docs that match at
+//      least one sparse token ("members").
+//   2. screening pass     every other doc has plane tokens only.  fp32 copies of the planes, rounded up, are
+//      summed with upward rounding: a rigorous upper bound of the in-order fp64 sum at half the shared-memory
+//      traffic.  Only (query, tile) pairs in which some bound reaches A's k-th score are recomputed in fp64
+//      (same token order); docs that reach it and are not members of the query go to list E.
+//   3. final merge        A + E -> top-k by (score desc, doc asc).
+//   4. fallback           queries whose A holds fewer than k docs while they have plane tokens take a histogram
+//      pass (threshold from the distribution of plane-only scores) or, like queries whose lists overflowed,
+//      the per-query kernel (bm25.cu).
 //
-// Adding +0.0 for absent terms is what the reference itself does (score += idf * 0), and an
-// accumulator that starts at +0.0 can never become -0.0, so the result is bit-identical.
+// Adding +0.0 for absent terms is what the reference itself does (score += idf * 0), and an accumulator that
+// starts at +0.0 can never become -0.0, so the result is bit-identical.
 #include "bm25.cuh"
 #include "ptx.cuh"
 
 #include <algorithm>
 #include <cstdlib>
 #include <mutex>
+#include <type_traits>
+#include <vector>
 
 namespace arb {
 
-constexpr int SP_MIN_BLOCK_LOG2 = 10;                // sparse-pass doc blocks: 1024 .. 16384 docs, chosen per query
-constexpr int SP_MAX_BLOCK_LOG2 = 14;
-constexpr int SP_MAXB = 1 << SP_MAX_BLOCK_LOG2;
-constexpr int SP_MAXM = 1024;                       // members per block visit (rank-compact accumulators)
-constexpr int SP_TARGET_M = 448;                    // block size aims at this many members per visit
-constexpr int SP_POOL = 1728;                       // fp64 pool: M accumulators + staged plane values
-constexpr int SP_PCAP = 1024;                       // postings staged per visit
-constexpr int SP_STAGED_PLANES = 4;                 // plane tokens whose member values are staged by cp.async
-constexpr int PL_WARPS = 16;
-constexpr int PL_SMEM_MAX = 227 * 1024 - 64;        // planes tile + per-query records (64 B left for the static mbarrier)
-constexpr int E_CAP = 1024;                         // plane-pass emissions kept per query
+constexpr int SC_WARPS = 32;                         // screening pass: warps per CTA (two fp32 plane tiles in flight)
+constexpr int PL_WARPS = 16;                         // fp64 plane kernels of the histogram path
+constexpr int SMEM_MAX = 227 * 1024 - 128;           // dynamic shared memory per CTA (128 B left for static barriers)
+constexpr int C_CAP = 4096;                          // candidate entries a query may collect between two compactions
+constexpr int E_CAP = 1024;                          // screening-pass emissions kept per query
+constexpr int RQ_CAP = 1 << 20;                      // queued fp64 rechecks per batch chunk (more: done in place)
 constexpr unsigned long long THR_SKIP = ~0ull;
-constexpr int H3_MAX = 1024;                        // queries per batch chunk that may take the histogram path
-constexpr int H3_BINS = 4096;                       // 128 bins per octave from 2^-12 up
-constexpr unsigned long long H3_TAG = 0xFFF8000000000000ull;   // qrec.x of a histogram query (a NaN pattern) | slot
+constexpr int H3_MAX = 1024;                         // queries per batch chunk that may take the histogram path
+constexpr int H3_BINS = 4096;                        // 128 bins per octave from 2^-12 up
 constexpr unsigned long long H3_BASE = (1ull << 18) | (static_cast<unsigned long long>(1023 - 12) << 7);
 // bin of a positive score: sign | exponent | 7 mantissa bits of its order-preserving key, clamped
 __device__ __forceinline__ int h3_bin(double v) {
@@ -60,60 +64,39 @@ __device__ __forceinline__ int h3_bin(double v) {
 __device__ __forceinline__ unsigned long long h3_edge(int b) {
   return b == 0 ? f64_key(0.0) + 1ull : (static_cast<unsigned long long>(b) + H3_BASE) << 45;
 }
-static_assert(SP_POOL >= SP_MAXM, "the pool holds at least the accumulators");
 
-// per-warp state of the sparse pass; CAP = candidate buffer (>= 2k + 32)
-template <int CAP>
-struct SpWarp {
-  double pool[SP_POOL];                  // [0, M): accumulator of member r (ranked by doc id inside the block);
-                                         // [M, ...): plane values of the members, staged by cp.async
-  unsigned long long ckey[CAP];
-  uint32_t cdoc[CAP];
-  uint32_t post[SP_PCAP];                // this visit's postings of all sparse tokens, staged by cp.async
-  uint32_t bm[SP_MAXB / 32];             // member bitmap of the block being visited
-  uint16_t prk[SP_PCAP];                 // member rank of each staged posting (0xFFFF: other sub-block)
-  uint16_t pref[SP_MAXB / 32];           // rank of the first member of each bitmap word
-  uint16_t mdoc[SP_MAXM];                // doc offset (inside the block) of member r
-};
-template <int CAP> constexpr int sp_warps() { return CAP <= 256 ? 8 : 7; }
-
-__device__ __forceinline__ void cp_async_4(void* smem_dst, const void* gsrc) {
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" :: "r"(static_cast<uint32_t>(__cvta_generic_to_shared(smem_dst))), "l"(gsrc) : "memory");
-}
-__device__ __forceinline__ void cp_async_8(void* smem_dst, const void* gsrc) {
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" :: "r"(static_cast<uint32_t>(__cvta_generic_to_shared(smem_dst))), "l"(gsrc) : "memory");
-}
-__device__ __forceinline__ void cp_async_wait_all() {
-  asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
-}
-
+struct MjDefer;
 struct BatchScratch {
-  unsigned long long* a_key;   // [nq, k]  sparse-pass top-k (list A), sorted
+  int64_t nq;
+  // ---- query-term index of the batch
+  int32_t* qinfo;              // [nq, qs] per query token: >= 0 sparse term id, -1 contributes nothing, <= -2 plane slot (-2 - slot)
+  int qs;                      // tokens per query rounded up to a multiple of 4 (16-byte rows)
+  uint32_t* bt_off;            // [n_terms + 1] pairs of term t: bt_pair[bt_off[t] .. bt_off[t + 1])
+  uint32_t* bt_cur;            // [n_terms] occurrence counts, then fill cursors
+  int4* bt_rec;                // [sparse tokens of the batch] records of 1 + qs/4 int4, grouped by term (bm25_bt_fill_kernel)
+  uint32_t* rec_of;            // [nq * qs] record of a sparse query token, else 0xFFFFFFFF
+  MjDefer* defer;       // [member-pass CTAs, MJ_DEF] set-aside pairs of the unit being joined
+  // ---- member pass
+  unsigned long long* c_key;   // [nq, C_CAP] candidates; [0, k) = running top-k after a compaction
+  uint32_t* c_doc;             // [nq, C_CAP]
+  int* c_cnt;                  // [nq] entries appended (may exceed C_CAP: overflow)
+  unsigned long long* gthr;    // [nq] bound of the current round: only scores strictly above it are candidates
+  int* n_nonpos;               // [nq] members whose complete score is not positive (never candidates)
+  uint8_t* ovf;                // [nq] a list overflowed: the per-query kernel takes the query
+  // ---- list A and the per-query state the later passes read
+  unsigned long long* a_key;   // [nq, k] top-k of the members, sorted
   uint32_t* a_doc;             // [nq, k]
   int* a_cnt;                  // [nq]
   unsigned long long* thr;     // [nq]  key of A's k-th score, or THR_SKIP
-  uint8_t* state;              // [nq]  0 = plane pass runs, 1 = no plane tokens (A is final), 2 = fallback
+  uint8_t* state;              // [nq]  0 = screening pass runs, 1 = no plane tokens (A is final), 2 = fallback, 3 = histogram path
   uint8_t* qd;                 // [nq, qd_stride] the query's plane slots in token order, 0xFF terminated/padded
   int qd_stride;               // mq rounded up to a multiple of 8 (<= 32)
-  uint32_t* bitmap;            // [bm_tiles, nq, 8] member bitmap, tile-major: the plane pass streams one tile's
-                               // 32-byte records of consecutive queries (NULL when the index has no planes)
-  int64_t bm_tiles;            // 256-doc tiles covered (whole 16K-doc blocks)
-  int64_t nq;
   unsigned long long* e_key;   // [nq, E_CAP]
   uint32_t* e_doc;             // [nq, E_CAP]
   int* e_cnt;                  // [nq]
   int* flag_list;              // [nq]
-  // the sparse pass cuts every query into `parts` doc ranges (whole 16K-doc blocks) scored by different
-  // warps, so that one heavy query cannot become the tail of the kernel; part lists are merged into A
-  int parts;
-  unsigned long long* pa_key;  // [nq, parts, k]
-  uint32_t* pa_doc;            // [nq, parts, k]
-  int* pa_cnt;                 // [nq, parts]  entries, or -1 if the part overflowed its staging areas
-  unsigned long long* gthr;    // [nq] largest k-th key any part of the query has reached so far (0 = none): a doc
-                               // strictly below it cannot be in the query's top-k, whichever part it lies in
-  int* counters;               // [0] next unit of the sparse pass, [1] number of flagged queries, [2] histogram queries
-  // queries whose list A holds fewer than k docs while they have plane tokens get their plane-pass threshold from
-  // a histogram of the plane-only scores of all their non-member docs (bm25_plane_list_kernel)
+  int* counters;               // [1] number of flagged queries, [2] histogram queries, [3] queued rechecks
+  uint2* rq;                   // [RQ_CAP] (query, tile) pairs the screening pass wants recomputed in fp64
   int* h3_list;                // [H3_MAX]
   uint32_t* hist;              // [H3_MAX, H3_BINS]
 };
@@ -157,363 +140,402 @@ __device__ __forceinline__ void cta_sort_desc(unsigned long long* key, IdT* id, 
   __syncthreads();
 }
 
+
+// two hash functions into a 384-bit filter; bit 383 is never set (record entries without a sparse term point at it)
+constexpr uint32_t BLOOM_MUL1 = 0x9E3779B1u, BLOOM_MUL2 = 0x85EBCA6Bu;
+constexpr uint32_t BLOOM_NONE = 383u, SLOT_NONE = 127u;
+__host__ __device__ __forceinline__ uint32_t bloom_bit(uint32_t t, uint32_t mul) { return (((t * mul) >> 23) * 383u) >> 9; }   // 0 .. 382
+
 // ----------------------------------------------------------------------------
-// 1. sparse pass: one warp per query (queries handed out by an atomic counter).
-//
-// The warp walks the corpus in doc blocks of B = 1024 .. 8192 docs (B chosen per query so that a
-// block holds ~SP_TARGET_M members on average).  The pass is bound by memory latency (a few hundred
-// scattered postings and plane values per visit), so every global read of a visit is issued as one
-// burst of cp.async copies into the warp's shared-memory staging areas:
-//  (1) the postings of all the query's sparse tokens in this block are staged, then mark the member
-//      bitmap;
-//  (2) members are ranked (bitmap word prefix sums): the fp64 accumulators are indexed by rank, so
-//      their footprint does not depend on B; every staged posting records its member's rank;
-//  (3) the plane values of the members are staged in one burst (member-major: one address
-//      computation per member);
-//  (4) tokens are applied in QUERY ORDER: a sparse token adds idf*g at the rank of each of its docs,
-//      a plane token adds its staged value for every member;
-//  (5) members are harvested in ascending doc order.
+// 0. query-term index of the batch
 // ----------------------------------------------------------------------------
-template <int CAP>
-__global__ void __launch_bounds__(sp_warps<CAP>() * 32, 1)
-bm25_sparse_pass_kernel(const Bm25Dev ix, const int32_t* __restrict__ q_terms_all, int mq, int64_t nq, int k,
-                        const BatchScratch sc) {
-  extern __shared__ __align__(16) uint8_t sp_smem[];
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  SpWarp<CAP>& W = reinterpret_cast<SpWarp<CAP>*>(sp_smem)[warp];
-  for (int i = lane; i < SP_MAXB / 32; i += 32) W.bm[i] = 0u;    // restored to zero after every block
-  __syncwarp();
-  const int nsl = ix.n_slices;
-  const uint32_t lt = (1u << lane) - 1u;
-  const unsigned long long key_zero = f64_key(0.0);
-  const int64_t tile_stride = static_cast<int64_t>(ix.n_planes) * PLANE_TILE;
-
-  while (true) {
-    int ui = 0;
-    if (lane == 0) ui = atomicAdd(&sc.counters[0], 1);
-    const int64_t unit = __shfl_sync(0xffffffffu, ui, 0);
-    if (unit >= nq * sc.parts) break;
-    // part-major order: the warps in flight work on the same doc range of different queries, so the term planes
-    // of that range (n_planes * 8 B per doc) stay in L2 for the scattered member look-ups
-    const int part = static_cast<int>(unit / nq);
-    const int64_t q = unit - static_cast<int64_t>(part) * nq;
-
-    // one query token per lane: kind 1 = plane term, 2 = sparse term with per-512-doc offsets,
-    // 3 = sparse term with per-16K-block offsets only, 0 = contributes nothing
-    int t = -1, kind = 0, slot = -1;
-    double idf = 0.0;
-    long long df = 0;
-    if (lane < mq) {
-      t = q_terms_all[q * mq + lane];
-      if (t >= 0 && t < ix.n_terms) {
-        idf = __ldg(ix.idf + t);
-        if (idf != 0.0) {                                      // (idf.get(q) or 0) == 0 adds +0.0: a no-op
-          const int ps = ix.n_planes > 0 ? __ldg(ix.plane_slot + t) : -1;
-          if (ps >= 0) { kind = 1; slot = ps; }
-          else {
-            const int fs = __ldg(ix.dense_slot + t);
-            if (fs >= 0) { kind = 2; slot = fs; } else kind = 3;
-            df = static_cast<long long>(__ldg(ix.blk_off + static_cast<int64_t>(t + 1) * ix.nb)) -
-                 static_cast<long long>(__ldg(ix.blk_off + static_cast<int64_t>(t) * ix.nb));
-          }
-        }
-      }
+// one thread per query: classify its tokens, count the sparse ones per term, pack its plane slots
+__global__ void __launch_bounds__(128)
+bm25_qclassify_kernel(const Bm25Dev ix, const int32_t* __restrict__ q_terms, int mq, int64_t nq, const BatchScratch sc) {
+  const int64_t q = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  if (q >= nq) return;
+  int np = 0;
+  for (int p = 0; p < sc.qs; ++p) {
+    int code = -1;
+    const int t = p < mq ? q_terms[q * mq + p] : -1;
+    if (t >= 0 && t < ix.n_terms && __ldg(ix.idf + t) != 0.0) {        // (idf.get(q) or 0) == 0 adds +0.0: a no-op
+      const int ps = ix.n_planes > 0 ? __ldg(ix.plane_slot + t) : -1;
+      if (ps >= 0) { code = -2 - ps; sc.qd[q * sc.qd_stride + np++] = static_cast<uint8_t>(ps); }
+      else { code = t; atomicAdd(sc.bt_cur + t, 1u); }
     }
-    const uint32_t plane_mask = __ballot_sync(0xffffffffu, kind == 1);
-    const uint32_t sparse_mask = __ballot_sync(0xffffffffu, kind >= 2);
-    const int np = __popc(plane_mask);
-    // the plane pass reads the query's plane slots in token order, packed at the front of an 8-byte-aligned row
-    if (part == 0) {
-      if (kind == 1) sc.qd[q * sc.qd_stride + __popc(plane_mask & lt)] = static_cast<uint8_t>(slot);
-      if (lane >= np && lane < sc.qd_stride) sc.qd[q * sc.qd_stride + lane] = 0xFF;
+    sc.qinfo[q * sc.qs + p] = code;
+  }
+  for (int i = np; i < sc.qd_stride; ++i) sc.qd[q * sc.qd_stride + i] = 0xFF;
+  sc.gthr[q] = f64_key(0.0);                                            // only positive scores are candidates
+}
+
+// exclusive scan of the per-term counts (one CTA: the table is small and L2 resident); the counts become cursors
+__global__ void __launch_bounds__(1024)
+bm25_bt_scan_kernel(int64_t n_terms, const BatchScratch sc) {
+  __shared__ uint32_t warp_tot[32];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int64_t chunk = (n_terms + 1023) / 1024;
+  const int64_t lo = min(n_terms, static_cast<int64_t>(tid) * chunk), hi = min(n_terms, lo + chunk);
+  uint32_t sum = 0;
+  for (int64_t i = lo; i < hi; ++i) sum += sc.bt_cur[i];
+  uint32_t incl = sum;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) { const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
+  if (lane == 31) warp_tot[warp] = incl;
+  __syncthreads();
+  if (warp == 0) {
+    uint32_t w = warp_tot[lane], wi = w;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const uint32_t v = __shfl_up_sync(0xffffffffu, wi, o); if (lane >= o) wi += v; }
+    warp_tot[lane] = wi - w;
+  }
+  __syncthreads();
+  uint32_t run = warp_tot[warp] + incl - sum;
+  for (int64_t i = lo; i < hi; ++i) { const uint32_t c = sc.bt_cur[i]; sc.bt_off[i] = run; sc.bt_cur[i] = 0u; run += c; }
+  if (tid == 1023) sc.bt_off[n_terms] = run;
+}
+
+// One record per sparse query token, grouped by term: everything the member pass needs to score the token's query
+// against a doc arrives with ONE load -- {query << 5 | position, -, bound of the current round (8 B)} followed by
+// one entry per query token: plane slot (bits 0-6, 127 = none) | the two filter bit positions of a sparse term
+// (bits 7-15 and 16-24, 383 = none; the record's OWN token carries none: its value arrives with the posting).  The
+// member pass evaluates every entry the same way, without branching on the token kind; the exact path reads the term
+// ids from qinfo.  rec_of remembers where a query's records went (the compaction updates their bound).
+__global__ void __launch_bounds__(256)
+bm25_bt_fill_kernel(int64_t n, const BatchScratch sc) {
+  const int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  if (i >= n) return;
+  const int code = sc.qinfo[i];
+  if (code < 0) { sc.rec_of[i] = 0xFFFFFFFFu; return; }
+  const int64_t q = i / sc.qs;
+  const uint32_t at = __ldg(sc.bt_off + code) + atomicAdd(sc.bt_cur + code, 1u);
+  sc.rec_of[i] = at;
+  const int rs4 = 1 + (sc.qs >> 2);
+  int4* rec = sc.bt_rec + static_cast<size_t>(at) * rs4;
+  const unsigned long long b0 = f64_key(0.0);
+  rec[0] = make_int4(static_cast<int>(static_cast<uint32_t>(q << 5) | static_cast<uint32_t>(i - q * sc.qs)), 0,
+                     static_cast<int>(static_cast<uint32_t>(b0)), static_cast<int>(static_cast<uint32_t>(b0 >> 32)));
+  const int* src = sc.qinfo + q * sc.qs;
+  for (int j = 0; j < (sc.qs >> 2); ++j) {
+    int f[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int c = src[4 * j + e];
+      uint32_t slot = SLOT_NONE, b1 = BLOOM_NONE, b2 = BLOOM_NONE;
+      if (c <= -2) slot = static_cast<uint32_t>(-2 - c);
+      else if (c >= 0 && 4 * j + e != static_cast<int>(i - q * sc.qs)) {
+        b1 = bloom_bit(static_cast<uint32_t>(c), BLOOM_MUL1);
+        b2 = bloom_bit(static_cast<uint32_t>(c), BLOOM_MUL2);
+      }
+      f[e] = static_cast<int>(slot | (b1 << 7) | (b2 << 16));
     }
-    // plane offsets (slot * 256) of the first plane tokens, for the member-major staging loop
-    int64_t pso[SP_STAGED_PLANES];
-#pragma unroll
-    for (int p = 0; p < SP_STAGED_PLANES; ++p) {
-      const int jl = p < np ? static_cast<int>(__fns(plane_mask, 0, p + 1)) : 0;
-      pso[p] = static_cast<int64_t>(__shfl_sync(0xffffffffu, slot, jl)) * PLANE_TILE;
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) df += __shfl_xor_sync(0xffffffffu, df, o);
-    // block size: the largest power of two in [1024, 8192] with (expected members per block) <= SP_TARGET_M
-    int bl2 = SP_MAX_BLOCK_LOG2;
-    while (bl2 > SP_MIN_BLOCK_LOG2 && (df << bl2) > static_cast<long long>(SP_TARGET_M) * ix.n_docs) --bl2;
-    const int nblk_all = static_cast<int>((ix.n_docs + (int64_t(1) << bl2) - 1) >> bl2);
-    // this part's blocks: 16K-doc blocks [part * nb / parts, (part + 1) * nb / parts)
-    const int b_first = static_cast<int>((static_cast<int64_t>(part) * ix.nb / sc.parts) << (DOC_BLOCK_LOG2 - bl2));
-    const int nblk = min(nblk_all, static_cast<int>((static_cast<int64_t>(part + 1) * ix.nb / sc.parts) << (DOC_BLOCK_LOG2 - bl2)));
-    const int nwords = 1 << (bl2 - 5);
-    const int wpl = nwords >> 5;                               // bitmap words ranked by each lane (contiguous)
-    const uint32_t sub_mask = (1u << (DOC_BLOCK_LOG2 - bl2)) - 1u;
-    const uint32_t in_mask = (1u << bl2) - 1u;
-    const int spb = 1 << (bl2 - SLICE_LOG2);                   // 512-doc slices per block
-
-    unsigned long long thr_key = key_zero;                     // only positive scores are candidates
-    unsigned long long floor_key = *reinterpret_cast<volatile unsigned long long*>(sc.gthr + q);   // other parts' bound
-    int cnt = 0;
-    bool overflow = false;
-    // word w of this query's member bitmap lives at bitmap[((w >> 3) * nq + q) * 8 + (w & 7)]
-    uint32_t* bm_row = sc.bitmap ? sc.bitmap + q * 8 : nullptr;
-    const int64_t bm_tile_stride = sc.nq * 8;
-
-    auto compact = [&]() {
-      __syncwarp();
-      int n2 = 32;
-      while (n2 < cnt) n2 <<= 1;
-      for (int i = cnt + lane; i < n2; i += 32) { W.ckey[i] = 0ull; W.cdoc[i] = 0xFFFFFFFFu; }
-      warp_sort_desc(W.ckey, W.cdoc, n2, lane);
-      if (cnt >= k) {
-        cnt = k; thr_key = W.ckey[k - 1];
-        if (lane == 0 && thr_key > floor_key) atomicMax(sc.gthr + q, thr_key);
-      }
-      __syncwarp();
-    };
-    // posting range of this lane's token in block b (kind 3: the enclosing 16K block, fetched once per 16K docs)
-    auto fetch_range = [&](int b, uint32_t& lo, uint32_t& hi) {
-      if (b >= nblk) return;
-      if (kind == 2) {
-        const uint32_t* fo = ix.fine_off + static_cast<int64_t>(slot) * (nsl + 1);
-        lo = __ldg(fo + min(b * spb, nsl));
-        hi = __ldg(fo + min(b * spb + spb, nsl));
-      } else if (kind == 3 && (static_cast<uint32_t>(b) & sub_mask) == 0u) {
-        const int64_t o = static_cast<int64_t>(t) * ix.nb + (b >> (DOC_BLOCK_LOG2 - bl2));
-        lo = __ldg(ix.blk_off + o);
-        hi = __ldg(ix.blk_off + o + 1);
-      }
-    };
-
-    uint32_t lo = 0u, hi = 0u, nlo = 0u, nhi = 0u;
-    if (sparse_mask) fetch_range(b_first, nlo, nhi);
-    for (int b = b_first; b < nblk && sparse_mask; ++b) {
-      lo = nlo; hi = nhi;
-      fetch_range(b + 1, nlo, nhi);                            // in flight during this visit
-      const uint32_t sub = static_cast<uint32_t>(b) & sub_mask;
-      const uint32_t ne = __ballot_sync(0xffffffffu, hi > lo) & sparse_mask;
-      if (ne == 0u) {
-        if (bm_row)
-          for (int i = lane; i < nwords; i += 32) {
-            const int64_t w = static_cast<int64_t>(b) * nwords + i;
-            bm_row[(w >> 3) * bm_tile_stride + (w & 7)] = 0u;
-          }
-        continue;
-      }
-
-      floor_key = max(floor_key, *reinterpret_cast<volatile unsigned long long*>(sc.gthr + q));
-
-      // ---- (1) the active tokens are packed into lanes 0..na-1; their postings are staged back to back
-      const int na = __popc(ne);
-      const int src = lane < na ? static_cast<int>(__fns(ne, 0, lane + 1)) : 0;
-      const uint32_t c_lo = __shfl_sync(0xffffffffu, lo, src);
-      const uint32_t c_hi = __shfl_sync(0xffffffffu, hi, src);
-      const uint32_t c_len = lane < na ? c_hi - c_lo : 0u;
-      uint32_t c_end = c_len;
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        const uint32_t v = __shfl_up_sync(0xffffffffu, c_end, o);
-        if (lane >= o) c_end += v;
-      }
-      const uint32_t c_st = c_end - c_len;
-      const uint32_t L = __shfl_sync(0xffffffffu, c_end, 31);
-      if (L > SP_PCAP) { overflow = true; break; }
-      for (int a = 0; a < na; ++a) {
-        const uint32_t l = __shfl_sync(0xffffffffu, c_lo, a), n = __shfl_sync(0xffffffffu, c_len, a);
-        const uint32_t st = __shfl_sync(0xffffffffu, c_st, a);
-#pragma unroll 2
-        for (uint32_t i = lane; i < n; i += 32) cp_async_4(&W.post[st + i], ix.post + l + i);
-      }
-      cp_async_wait_all();
-      __syncwarp();
-      for (uint32_t f = lane; f < L; f += 32) {
-        const uint32_t d16 = post_doc(W.post[f]);
-        if ((d16 >> bl2) == sub) atomicOr(&W.bm[(d16 & in_mask) >> 5], 1u << (d16 & 31));
-      }
-      __syncwarp();
-
-      // ---- (2) rank the members
-      int c = 0;
-      for (int i = 0; i < wpl; ++i) c += __popc(W.bm[lane * wpl + i]);
-      int incl = c;
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        const int v = __shfl_up_sync(0xffffffffu, incl, o);
-        if (lane >= o) incl += v;
-      }
-      const int M = __shfl_sync(0xffffffffu, incl, 31);
-      if (bm_row)
-        for (int i = lane; i < nwords; i += 32) {
-          const int64_t w = static_cast<int64_t>(b) * nwords + i;
-          bm_row[(w >> 3) * bm_tile_stride + (w & 7)] = W.bm[i];
-        }
-      if (M == 0) continue;                                    // the 16K block's postings lie in other sub-blocks
-      if (M > SP_MAXM) {                                       // denser than the staging areas allow: fallback
-        overflow = true;
-        for (int i = lane; i < nwords; i += 32) W.bm[i] = 0u;
-        __syncwarp();
-        break;
-      }
-      {
-        int r = incl - c;
-        for (int i = 0; i < wpl; ++i) {
-          const int wi = lane * wpl + i;
-          W.pref[wi] = static_cast<uint16_t>(r);
-          r += __popc(W.bm[wi]);
-        }
-      }
-      __syncwarp();
-      for (uint32_t f = lane; f < L; f += 32) {
-        const uint32_t d16 = post_doc(W.post[f]);
-        uint32_t rk = 0xFFFFu;
-        if ((d16 >> bl2) == sub) {
-          const uint32_t d = d16 & in_mask;
-          rk = W.pref[d >> 5] + __popc(W.bm[d >> 5] & ((1u << (d & 31)) - 1u));
-          W.mdoc[rk] = static_cast<uint16_t>(d);               // every posting of the doc writes the same value
-        }
-        W.prk[f] = static_cast<uint16_t>(rk);
-      }
-      for (int i = lane; i < M; i += 32) W.pool[i] = 0.0;
-      __syncwarp();
-      const int64_t doc0 = static_cast<int64_t>(b) << bl2;
-
-      // ---- (3) stage the plane values of the members (first SP_STAGED_PLANES plane tokens, pool permitting)
-      const int n_staged = min(min(np, SP_STAGED_PLANES), (SP_POOL - M) / M);
-      if (n_staged > 0) {
-#pragma unroll 2
-        for (int i = lane; i < M; i += 32) {
-          const int64_t doc = doc0 + W.mdoc[i];
-          const double* src_p = ix.planes + (doc >> PLANE_TILE_LOG2) * tile_stride + plane_pos(static_cast<uint32_t>(doc) & (PLANE_TILE - 1));
-          double* dst = W.pool + M + i;
-#pragma unroll
-          for (int p = 0; p < SP_STAGED_PLANES; ++p)
-            if (p < n_staged) cp_async_8(dst + p * M, src_p + pso[p]);
-        }
-        cp_async_wait_all();
-        __syncwarp();
-      }
-
-      // ---- (4) accumulate in query-token order
-      int p_seen = 0;
-      for (uint32_t m = ne | plane_mask; m; m &= m - 1) {
-        const int jl = __ffs(m) - 1;
-        if ((plane_mask >> jl) & 1u) {
-          if (p_seen < n_staged) {
-            const double* stg = W.pool + static_cast<size_t>(p_seen + 1) * M;
-            for (int i = lane; i < M; i += 32) W.pool[i] = __dadd_rn(W.pool[i], stg[i]);
-          } else {
-            const double* pp = ix.planes + static_cast<int64_t>(__shfl_sync(0xffffffffu, slot, jl)) * PLANE_TILE;
-            for (int i0 = 0; i0 < M; i0 += 128) {
-              double v[4];
-#pragma unroll
-              for (int r = 0; r < 4; ++r) {
-                const int i = i0 + r * 32 + lane;
-                v[r] = 0.0;
-                if (i < M) {
-                  const int64_t doc = doc0 + W.mdoc[i];
-                  v[r] = __ldg(pp + (doc >> PLANE_TILE_LOG2) * tile_stride + plane_pos(static_cast<uint32_t>(doc) & (PLANE_TILE - 1)));
-                }
-              }
-#pragma unroll
-              for (int r = 0; r < 4; ++r) {
-                const int i = i0 + r * 32 + lane;
-                if (i < M) W.pool[i] = __dadd_rn(W.pool[i], v[r]);
-              }
-            }
-          }
-          ++p_seen;
-        } else {
-          const int a = __popc(ne & ((1u << jl) - 1u));         // index of this token among the active ones
-          const uint32_t st = __shfl_sync(0xffffffffu, c_st, a), en = __shfl_sync(0xffffffffu, c_end, a);
-          const double w_idf = __shfl_sync(0xffffffffu, idf, jl);
-          for (uint32_t f = st + lane; f < en; f += 32) {
-            const uint32_t rk = W.prk[f];
-            if (rk != 0xFFFFu)
-              W.pool[rk] = __dadd_rn(W.pool[rk], __dmul_rn(w_idf, __ldg(ix.gtab + post_code(W.post[f]))));
-          }
-        }
-        __syncwarp();
-      }
-
-      // ---- (5) harvest the members (ascending doc id, so a tie with the k-th score loses: strict >)
-      for (int i0 = 0; i0 < M; i0 += 32) {
-        const int i = i0 + lane;
-        const bool valid = i < M;
-        double v = 0.0;
-        uint32_t d = 0u;
-        if (valid) { v = W.pool[i]; d = W.mdoc[i]; }
-        const unsigned long long key = f64_key(v);
-        const bool pass = valid && key > thr_key && key >= floor_key;
-        const uint32_t pm = __ballot_sync(0xffffffffu, pass);
-        if (pass) {
-          const int pos = cnt + __popc(pm & lt);
-          W.ckey[pos] = key;
-          W.cdoc[pos] = static_cast<uint32_t>(doc0) + d;
-        }
-        cnt += __popc(pm);
-        if (cnt > CAP - 32) compact();
-      }
-      for (int i = lane; i < nwords; i += 32) W.bm[i] = 0u;
-      __syncwarp();
-    }
-    if (bm_row && !sparse_mask)
-      for (int64_t w = static_cast<int64_t>(b_first) * nwords + lane; w < static_cast<int64_t>(nblk) * nwords; w += 32)
-        bm_row[(w >> 3) * bm_tile_stride + (w & 7)] = 0u;
-
-    compact();
-    cnt = min(cnt, k);
-    const int64_t po = (q * sc.parts + part) * k;
-    for (int i = lane; i < cnt; i += 32) { sc.pa_key[po + i] = W.ckey[i]; sc.pa_doc[po + i] = W.cdoc[i]; }
-    if (lane == 0) sc.pa_cnt[q * sc.parts + part] = overflow ? -1 : cnt;
-    __syncwarp();
+    rec[1 + j] = make_int4(f[0], f[1], f[2], f[3]);
   }
 }
 
 // ----------------------------------------------------------------------------
-// 1b. merge the part lists of every query into list A (sorted top-k of the members), and derive the
-// plane-pass threshold / the query's state.  One CTA per query.
+// 1. member pass
 // ----------------------------------------------------------------------------
-__global__ void __launch_bounds__(128)
-bm25_a_merge_kernel(int64_t nq, int k, const int A_MERGE_CAP, const BatchScratch sc) {
-  extern __shared__ __align__(16) uint8_t am_smem[];             // A_MERGE_CAP x 12 B (a power of two >= parts * k)
-  const int64_t q = blockIdx.x;
-  const int tid = threadIdx.x;
-  __shared__ int s_n, s_ovf, s_total;
-  __shared__ unsigned long long s_floor;
-  if (tid == 0) {
-    // Every part list is sorted; a full part's k-th key is a lower bound of the merged k-th key, so only
-    // entries at or above the largest such bound can be in the merged top-k.
-    int ovf = 0, total = 0;
-    unsigned long long fl = 0ull;
-    for (int p = 0; p < sc.parts; ++p) {
-      const int c = sc.pa_cnt[q * sc.parts + p];
-      if (c < 0) { ovf = 1; continue; }
-      total += c;
-      if (c >= k) fl = max(fl, sc.pa_key[(q * sc.parts + p) * k + k - 1]);
-    }
-    s_n = 0; s_ovf = ovf; s_floor = fl; s_total = total;
+constexpr int MJ_THREADS = 768;
+constexpr int MJ_CH = 2048;                          // postings joined per chunk
+constexpr int MJ_BLOOM_W = 12;                       // 384-bit filter per doc, two hash functions
+constexpr int MJ_DEF = 32768;                        // set-aside pairs per CTA and unit, in global scratch (more: finished in place)
+constexpr int MJ_PSTRIDE = PLANE_TILE + 2;           // padded plane rows: threads of a warp mostly read the SAME doc of
+                                                     // different planes; 258 * 8 B keeps bulk copies 16-byte aligned
+struct MjShared {
+  uint32_t pscan[MJ_CH + 4];             // exclusive scan of the chunk's pair counts; [n_ch] = total
+  uint32_t cbase[MJ_CH];                 // first record of each posting's term
+  uint32_t bloom[PLANE_TILE * MJ_BLOOM_W];
+  uint32_t doff[PLANE_TILE + 4];         // row offsets of the unit's docs
+  uint32_t wsum[32];
+  uint8_t pdoc[MJ_CH];                   // doc (inside the unit) of each posting
+  int n_def;
+};
+static_assert(MAX_PLANES * MJ_PSTRIDE * 8 + sizeof(MjShared) <= SMEM_MAX, "member pass: plane tile + join state must fit one CTA");
+// index of term c in the ascending list dt[0, n), or -1
+__device__ __forceinline__ int row_find(const uint32_t* __restrict__ dt, int n, uint32_t c) {
+  int lo = 0, hi = n;
+  while (lo < hi) { const int mid = (lo + hi) >> 1; if (__ldg(dt + mid) < c) lo = mid + 1; else hi = mid; }
+  return (lo < n && __ldg(dt + lo) == c) ? lo : -1;
+}
+// does doc d match one of query q's sparse tokens?  (rare path: screening emissions only)
+__device__ __forceinline__ bool is_member(const uint32_t* __restrict__ drow_off, const uint32_t* __restrict__ drow_term,
+                                          const int32_t* __restrict__ qinfo, int qs, int64_t q, int64_t d) {
+  const uint32_t o0 = __ldg(drow_off + d);
+  const int n = static_cast<int>(__ldg(drow_off + d + 1) - o0);
+  if (n == 0) return false;
+  for (int p = 0; p < qs; ++p) {
+    const int c = __ldg(qinfo + q * qs + p);
+    if (c >= 0 && row_find(drow_term + o0, n, static_cast<uint32_t>(c)) >= 0) return true;
   }
-  __syncthreads();
-  const unsigned long long fl = s_floor;
-  unsigned long long* key = reinterpret_cast<unsigned long long*>(am_smem);
-  uint32_t* doc = reinterpret_cast<uint32_t*>(am_smem + static_cast<size_t>(A_MERGE_CAP) * 8);
-  for (int i = tid; i < sc.parts * k; i += blockDim.x) {
-    const int p = i / k, j = i - p * k;
-    if (j < sc.pa_cnt[q * sc.parts + p]) {
-      const unsigned long long kk = sc.pa_key[(q * sc.parts + p) * k + j];
-      if (kk >= fl) {
-        const int pos = atomicAdd(&s_n, 1);
-        if (pos < A_MERGE_CAP) { key[pos] = kk; doc[pos] = sc.pa_doc[(q * sc.parts + p) * k + j]; }
+  return false;
+}
+// largest i in [0, n) with off[i] <= x (off ascending, off[0] <= x < off[n])
+__device__ __forceinline__ int seg_of(const uint32_t* off, int n, uint32_t x) {
+  int lo = 0, hi = n;
+  while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (off[mid] <= x) lo = mid; else hi = mid; }
+  return lo;
+}
+
+// append (key, doc) to query q's candidates if it beats the round's bound; count members that can never be candidates
+__device__ __forceinline__ void member_emit(const BatchScratch& sc, int64_t q, double acc, unsigned long long bound, int64_t d) {
+  const unsigned long long key = f64_key(acc);
+  if (key > bound) {
+    const int at = atomicAdd(sc.c_cnt + q, 1);
+    if (at < C_CAP) { sc.c_key[q * C_CAP + at] = key; sc.c_doc[q * C_CAP + at] = static_cast<uint32_t>(d); }
+  } else if (!(acc > 0.0)) {
+    atomicAdd(sc.n_nonpos + q, 1);
+  }
+}
+
+// grid: persistent CTAs over the units of tiles [tile_lo, tile_hi); a unit is 1/sub of a tile's docs.  Per unit:
+// stage the tile of all planes (bulk copy), build the per-doc filters, then join the unit's doc rows with the batch's
+// query-term index 2048 postings at a time: record counts -> CTA-wide exclusive scan -> every thread scores a contiguous
+// run of (posting, record) pairs, keeping the posting's state in registers.  The complete score of a pair's (query, doc)
+// is summed in query-token order: plane tokens from the staged tile, the pair's own token from the posting, +0.0 for
+// every other sparse token of the query -- unless the doc's filter says one of them may be present: those pairs are
+// set aside with the positions in question and finished after the last chunk (doc row searched; a pair whose query
+// matches the doc at an EARLIER position belongs to that position's pair and is dropped).
+struct MjDefer { uint32_t posting, rec, hits; };
+__global__ void __launch_bounds__(MJ_THREADS, 1)
+bm25_member_kernel(const Bm25Dev ix, const BatchScratch sc, int64_t tile_lo, int64_t tile_hi, int sub) {
+  extern __shared__ __align__(16) uint8_t mj_smem[];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int P = ix.n_planes;
+  const double* pl = reinterpret_cast<const double*>(mj_smem);                     // [P][MJ_PSTRIDE]
+  MjShared& S = *reinterpret_cast<MjShared*>(mj_smem + static_cast<size_t>(P) * MJ_PSTRIDE * 8);
+  MjDefer* defer = sc.defer + static_cast<size_t>(blockIdx.x) * MJ_DEF;
+  __shared__ __align__(8) uint64_t fill_bar;
+  if (tid == 0) { ptx::mbar_init(&fill_bar, 1); ptx::fence_barrier_init(); }
+  uint32_t fill_phase = 0;
+  const int dps = PLANE_TILE / sub;
+  const int64_t units = (tile_hi - tile_lo) * sub;
+  const int rs4 = 1 + (sc.qs >> 2);
+  for (int64_t u = blockIdx.x; u < units; u += gridDim.x) {
+    const int64_t tile = tile_lo + u / sub;
+    const int part = static_cast<int>(u % sub);
+    __syncthreads();                                           // the previous unit is done; fill_bar is initialised
+    if (tid == 0) {
+      S.n_def = 0;
+      if (P > 0) {
+        const uint32_t bytes = static_cast<uint32_t>(P) * PLANE_TILE * 8u;
+        const char* src = reinterpret_cast<const char*>(ix.planes + tile * P * PLANE_TILE);
+        ptx::fence_proxy_async_smem();
+        ptx::mbar_expect_tx(&fill_bar, bytes);
+        for (int r = 0; r < P; ++r)                             // one 2 KB row at a time into the padded rows
+          ptx::bulk_load_1d(mj_smem + static_cast<size_t>(r) * MJ_PSTRIDE * 8, src + static_cast<size_t>(r) * PLANE_TILE * 8,
+                            PLANE_TILE * 8u, &fill_bar);
       }
     }
+    const int64_t d0 = tile * PLANE_TILE + static_cast<int64_t>(part) * dps;
+    const int nd = static_cast<int>(max(static_cast<int64_t>(0), min(static_cast<int64_t>(dps), ix.n_docs - d0)));
+    // row offsets and empty filters while the tile is on its way
+    for (int i = tid; i <= nd && nd > 0; i += MJ_THREADS) S.doff[i] = __ldg(ix.drow_off + d0 + i);
+    for (int i = tid; i < nd * MJ_BLOOM_W; i += MJ_THREADS) S.bloom[i] = 0u;
+    __syncthreads();
+    const uint32_t o_lo = nd > 0 ? S.doff[0] : 0u, o_hi = nd > 0 ? S.doff[nd] : 0u;
+    for (uint32_t i = o_lo + tid; i < o_hi; i += MJ_THREADS) {
+      const uint32_t t = __ldg(ix.drow_term + i);
+      const int dl = seg_of(S.doff, nd, i);
+      const uint32_t b1 = bloom_bit(t, BLOOM_MUL1), b2 = bloom_bit(t, BLOOM_MUL2);
+      atomicOr(&S.bloom[dl * MJ_BLOOM_W + (b1 >> 5)], 1u << (b1 & 31));
+      atomicOr(&S.bloom[dl * MJ_BLOOM_W + (b2 >> 5)], 1u << (b2 & 31));
+    }
+    if (P > 0) { ptx::mbar_wait(&fill_bar, fill_phase); fill_phase ^= 1u; }
+    __syncthreads();
+    for (uint32_t c0 = o_lo; c0 < o_hi; c0 += MJ_CH) {
+      const int n_ch = static_cast<int>(min(static_cast<uint32_t>(MJ_CH), o_hi - c0));
+      // ---- counts of matching records per posting (thread t owns postings 4t .. 4t+3) and their exclusive scan
+      uint32_t cnt[4];
+      uint32_t tsum = 0u;
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int i = tid * 4 + e;
+        cnt[e] = 0u;
+        if (i < n_ch) {
+          const uint32_t t = __ldg(ix.drow_term + c0 + i);
+          const uint32_t b0 = __ldg(sc.bt_off + t);
+          cnt[e] = __ldg(sc.bt_off + t + 1) - b0;
+          S.cbase[i] = b0;
+          S.pdoc[i] = static_cast<uint8_t>(seg_of(S.doff, nd, c0 + i));
+        }
+        tsum += cnt[e];
+      }
+      uint32_t incl = tsum;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) { const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
+      if (lane == 31) S.wsum[warp] = incl;
+      __syncthreads();
+      if (warp == 0) {
+        const uint32_t w = lane < MJ_THREADS / 32 ? S.wsum[lane] : 0u;
+        uint32_t wi = w;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const uint32_t v = __shfl_up_sync(0xffffffffu, wi, o); if (lane >= o) wi += v; }
+        S.wsum[lane] = wi - w;
+        if (lane == 31) S.pscan[n_ch] = wi;
+      }
+      __syncthreads();
+      {
+        uint32_t run = S.wsum[warp] + incl - tsum;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int i = tid * 4 + e;
+          if (i < n_ch) S.pscan[i] = run;
+          run += cnt[e];
+        }
+      }
+      __syncthreads();
+      // ---- pairs: thread t scores pairs [t * R, (t + 1) * R) of the chunk
+      const uint32_t T = S.pscan[n_ch];
+      const uint32_t R = (T + MJ_THREADS - 1) / MJ_THREADS;
+      uint32_t j = tid * R;
+      const uint32_t j_end = min(T, j + R);
+      if (j < j_end) {
+        int p = seg_of(S.pscan, n_ch, j);                      // pscan[p] <= j < pscan[p + 1]
+        uint32_t p_end = 0u;                                   // forces the posting state to be loaded
+        const double* pl_doc = pl;
+        const uint32_t* brow = S.bloom;
+        double myval = 0.0;
+        uint32_t rbase = 0u;
+        int64_t d = 0;
+        --p;
+        for (; j < j_end; ++j) {
+          if (j >= p_end) {                                    // next posting with records (skips postings without)
+            do { ++p; p_end = S.pscan[p + 1]; } while (j >= p_end);
+            const int dl = S.pdoc[p];
+            d = d0 + dl;
+            pl_doc = pl + plane_pos(static_cast<uint32_t>(d) & (PLANE_TILE - 1));
+            brow = S.bloom + dl * MJ_BLOOM_W;
+            myval = __ldg(ix.drow_val + c0 + p);
+            rbase = S.cbase[p] - S.pscan[p];
+            if (p + 1 < n_ch) ptx::prefetch_l1(sc.bt_rec + static_cast<size_t>(S.cbase[p + 1]) * rs4);   // likely the next posting
+          }
+          const uint32_t r = rbase + j;
+          const int4* rec = sc.bt_rec + static_cast<size_t>(r) * rs4;
+          ptx::prefetch_l1(reinterpret_cast<const char*>(rec) + 128);   // the records of a term are contiguous
+          const int4 hd = __ldg(rec);
+          const int pos = hd.x & 31;
+          double acc = 0.0;
+          uint32_t hits = 0u;
+          for (int p4 = 0; p4 < rs4 - 1; ++p4) {
+            const int4 c4 = __ldg(rec + 1 + p4);
+            const uint32_t ee[4] = {static_cast<uint32_t>(c4.x), static_cast<uint32_t>(c4.y), static_cast<uint32_t>(c4.z), static_cast<uint32_t>(c4.w)};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const uint32_t f = ee[e];
+              const uint32_t slot = f & 127u, b1 = (f >> 7) & 511u, b2 = (f >> 16) & 511u;
+              double v = 0.0;                                  // adding +0.0 changes nothing (the sum is never -0.0)
+              if (slot != SLOT_NONE) v = pl_doc[slot * MJ_PSTRIDE];
+              if (p4 * 4 + e == pos) v = myval;
+              acc = __dadd_rn(acc, v);
+              hits |= ((brow[b1 >> 5] >> (b1 & 31)) & (brow[b2 >> 5] >> (b2 & 31)) & 1u) << (p4 * 4 + e);
+            }
+          }
+          if (hits != 0u) {
+            const int at = atomicAdd(&S.n_def, 1);
+            if (at < MJ_DEF) { defer[at].posting = c0 + p; defer[at].rec = r; defer[at].hits = hits; continue; }
+            // (a full list cannot happen with MJ_DEF pairs per unit; if it does the pair is finished in place below)
+            bool dup = false;
+            const int64_t q = static_cast<uint32_t>(hd.x) >> 5;
+            const uint32_t r0 = S.doff[S.pdoc[p]];
+            const int row_n = static_cast<int>(S.doff[S.pdoc[p] + 1] - r0);
+            acc = 0.0;
+            for (int pp = 0; pp < sc.qs; ++pp) {
+              const uint32_t f = static_cast<uint32_t>(reinterpret_cast<const int*>(rec + 1)[pp]);
+              const uint32_t slot = f & 127u;
+              double v = 0.0;
+              if (slot != SLOT_NONE) v = pl_doc[slot * MJ_PSTRIDE];
+              if (pp == pos) v = myval;
+              if ((hits >> pp) & 1u) {
+                const int idx = row_find(ix.drow_term + r0, row_n, static_cast<uint32_t>(__ldg(sc.qinfo + q * sc.qs + pp)));
+                if (idx >= 0) { if (pp < pos) dup = true; else v = __ldg(ix.drow_val + r0 + idx); }
+              }
+              acc = __dadd_rn(acc, v);
+            }
+            if (!dup) member_emit(sc, q, acc, (static_cast<unsigned long long>(static_cast<uint32_t>(hd.w)) << 32) | static_cast<uint32_t>(hd.z), d);
+            continue;
+          }
+          member_emit(sc, static_cast<uint32_t>(hd.x) >> 5, acc,
+                      (static_cast<unsigned long long>(static_cast<uint32_t>(hd.w)) << 32) | static_cast<uint32_t>(hd.z), d);
+        }
+      }
+      __syncthreads();                                         // pscan / cbase / pdoc are rewritten by the next chunk
+    }
+    // ---- the set-aside pairs of the unit: same sum, the positions in question looked up in the doc's row
+    const int n_def = min(S.n_def, MJ_DEF);
+    for (int i = tid; i < n_def; i += MJ_THREADS) {
+      const MjDefer de = defer[i];
+      const int dl = seg_of(S.doff, nd, de.posting);
+      const int64_t d = d0 + dl;
+      const double* pl_doc = pl + plane_pos(static_cast<uint32_t>(d) & (PLANE_TILE - 1));
+      const double myval = __ldg(ix.drow_val + de.posting);
+      const uint32_t r0 = S.doff[dl];
+      const int row_n = static_cast<int>(S.doff[dl + 1] - r0);
+      const int4* rec = sc.bt_rec + static_cast<size_t>(de.rec) * rs4;
+      const int4 hd = __ldg(rec);
+      const int64_t q = static_cast<uint32_t>(hd.x) >> 5;
+      const int pos = hd.x & 31;
+      double acc = 0.0;
+      bool dup = false;
+      for (int pp = 0; pp < sc.qs; ++pp) {
+        const uint32_t f = static_cast<uint32_t>(__ldg(reinterpret_cast<const int*>(rec + 1) + pp));
+        const uint32_t slot = f & 127u;
+        double v = 0.0;
+        if (slot != SLOT_NONE) v = pl_doc[slot * MJ_PSTRIDE];
+        if (pp == pos) v = myval;
+        if ((de.hits >> pp) & 1u) {
+          const int idx = row_find(ix.drow_term + r0, row_n, static_cast<uint32_t>(__ldg(sc.qinfo + q * sc.qs + pp)));
+          if (idx >= 0) { if (pp < pos) dup = true; else v = __ldg(ix.drow_val + r0 + idx); }
+        }
+        acc = __dadd_rn(acc, v);
+      }
+      if (!dup) member_emit(sc, q, acc, (static_cast<unsigned long long>(static_cast<uint32_t>(hd.w)) << 32) | static_cast<uint32_t>(hd.z), d);
+    }
   }
-  __syncthreads();
-  if (s_n > A_MERGE_CAP) { if (tid == 0) s_ovf = 1; }
-  const int n = min(s_n, A_MERGE_CAP);
-  __syncthreads();
+}
+
+// Between rounds: cut a query's candidate list back to its k best and publish the k-th key as the next bound.
+// After the last round: list A, the screening threshold and the query's state.  One CTA per query.
+__global__ void __launch_bounds__(256)
+bm25_compact_kernel(int64_t nq, int k, int last, const BatchScratch sc) {
+  extern __shared__ __align__(16) uint8_t cp_smem[];             // C_CAP x 12 B
+  const int64_t q = blockIdx.x;
+  const int tid = threadIdx.x;
+  const int raw = sc.c_cnt[q];
+  const bool ovf = sc.ovf[q] != 0 || raw > C_CAP;
+  auto publish = [&](unsigned long long bound) {              // the next round reads the bound from the query's records
+    const int rs4 = 1 + (sc.qs >> 2);
+    if (tid < sc.qs) {
+      const uint32_t r = sc.rec_of[q * sc.qs + tid];
+      if (r != 0xFFFFFFFFu)
+        *reinterpret_cast<unsigned long long*>(reinterpret_cast<int*>(sc.bt_rec + static_cast<size_t>(r) * rs4) + 2) = bound;
+    }
+  };
+  if (!last) {
+    if (ovf) {
+      if (tid == 0) { sc.ovf[q] = 1; sc.gthr[q] = ~0ull; sc.c_cnt[q] = 0; }
+      publish(~0ull);
+      return;
+    }
+    if (raw <= k) return;
+  }
+  const int n = ovf ? 0 : raw;
+  unsigned long long* key = reinterpret_cast<unsigned long long*>(cp_smem);
+  uint32_t* doc = reinterpret_cast<uint32_t*>(cp_smem + static_cast<size_t>(C_CAP) * 8);
   int n2 = 2;
   while (n2 < n) n2 <<= 1;
-  for (int i = n + tid; i < n2; i += blockDim.x) { key[i] = 0ull; doc[i] = 0xFFFFFFFFu; }
+  for (int i = tid; i < n2; i += blockDim.x) {
+    key[i] = i < n ? sc.c_key[q * C_CAP + i] : 0ull;
+    doc[i] = i < n ? sc.c_doc[q * C_CAP + i] : 0xFFFFFFFFu;
+  }
   cta_sort_desc(key, doc, n2);
   const int cnt = min(n, k);
+  if (!last) {
+    for (int i = tid; i < cnt; i += blockDim.x) { sc.c_key[q * C_CAP + i] = key[i]; sc.c_doc[q * C_CAP + i] = doc[i]; }
+    if (tid == 0) { sc.c_cnt[q] = cnt; if (cnt >= k) sc.gthr[q] = key[k - 1]; }
+    if (cnt >= k) publish(key[k - 1]);
+    return;
+  }
   for (int i = tid; i < k; i += blockDim.x) {
     sc.a_key[q * k + i] = i < cnt ? key[i] : 0ull;
     sc.a_doc[q * k + i] = i < cnt ? doc[i] : 0xFFFFFFFFu;
@@ -522,9 +544,9 @@ bm25_a_merge_kernel(int64_t nq, int k, const int A_MERGE_CAP, const BatchScratch
     const bool has_planes = sc.qd[q * sc.qd_stride] != 0xFF;
     sc.a_cnt[q] = cnt;
     int h3 = H3_MAX;
-    if (!has_planes && !s_ovf)   { sc.state[q] = 1; sc.thr[q] = THR_SKIP; }
-    else if (cnt >= k && !s_ovf) { sc.state[q] = 0; sc.thr[q] = key[k - 1]; }
-    else if (!s_ovf && (h3 = atomicAdd(&sc.counters[2], 1)) < H3_MAX) {
+    if (!has_planes && !ovf)    { sc.state[q] = 1; sc.thr[q] = THR_SKIP; }
+    else if (cnt >= k && !ovf)  { sc.state[q] = 0; sc.thr[q] = key[k - 1]; }
+    else if (!ovf && (h3 = atomicAdd(&sc.counters[2], 1)) < H3_MAX) {
       sc.state[q] = 3; sc.thr[q] = THR_SKIP; sc.h3_list[h3] = static_cast<int>(q);
     } else {
       sc.state[q] = 2; sc.thr[q] = THR_SKIP;
@@ -533,246 +555,193 @@ bm25_a_merge_kernel(int64_t nq, int k, const int A_MERGE_CAP, const BatchScratch
   }
 }
 
-// 1b'. the same merge for the common shapes (parts * k keys fit 20 KB): one WARP per query.  The part lists are
-// sorted, so the merged k-th key is found by a bitwise search in which lane p counts, by binary search in its
-// own list (held in shared memory), how many of part p's keys reach the candidate; only the <= k (+ ties)
-// entries at or above that key are gathered and sorted.
-constexpr int AMW_WARPS = 4;
-constexpr int AMW_KEYS = 2560;                      // keys per warp (20 KB)
-constexpr int AMW_OUT = 512;                        // gathered entries per warp
-struct AmWarp { unsigned long long keys[AMW_KEYS]; unsigned long long okey[AMW_OUT]; uint32_t odoc[AMW_OUT]; };
-__global__ void __launch_bounds__(AMW_WARPS * 32)
-bm25_a_merge_warp_kernel(int64_t nq, int k, const BatchScratch sc) {
-  extern __shared__ __align__(16) uint8_t amw_smem[];
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int64_t q = blockIdx.x * static_cast<int64_t>(AMW_WARPS) + warp;
-  if (q >= nq) return;
-  AmWarp& W = reinterpret_cast<AmWarp*>(amw_smem)[warp];
-  const int parts = sc.parts;
-  int my_cnt = 0;
-  bool ovf = false;
-  if (lane < parts) { my_cnt = sc.pa_cnt[q * parts + lane]; if (my_cnt < 0) { ovf = true; my_cnt = 0; } }
-  ovf = __any_sync(0xffffffffu, ovf);
-  for (int p = 0; p < parts; ++p) {
-    const int c = __shfl_sync(0xffffffffu, my_cnt, p);
-    for (int j = lane; j < c; j += 32) W.keys[p * k + j] = sc.pa_key[(q * parts + p) * k + j];
-  }
-  __syncwarp();
-  const int total = __reduce_add_sync(0xffffffffu, my_cnt);
-  // number of keys of this lane's part that are >= cand (the list is sorted descending)
-  auto count_ge = [&](unsigned long long cand) {
-    int lo = 0, hi = my_cnt;
-    const unsigned long long* L = W.keys + lane * k;
-    while (lo < hi) { const int mid = (lo + hi) >> 1; if (L[mid] >= cand) lo = mid + 1; else hi = mid; }
-    return lo;
-  };
-  unsigned long long T = 0ull;
-  if (total > k) {
-    for (int bit = 63; bit >= 0; --bit) {
-      const unsigned long long cand = T | (1ull << bit);
-      const int c = __reduce_add_sync(0xffffffffu, lane < parts ? count_ge(cand) : 0);
-      if (c >= k) T = cand;                                    // at least k keys reach cand: the k-th key does too
-    }
-  }
-  // gather everything at or above the k-th key (exactly k entries unless keys tie there)
-  const int mine = lane < parts ? (total > k ? count_ge(T) : my_cnt) : 0;
-  int incl = mine;
+// ----------------------------------------------------------------------------
+// 2. screening pass: grid (tile sets, query groups), one CTA per SM, two fp32 plane tiles in flight.
+// ----------------------------------------------------------------------------
+// append the docs of one tile whose in-order fp64 plane score reaches thr_d and that are not members of q
+struct RecheckArgs {
+  const double* planes; const uint32_t* drow_off; const uint32_t* drow_term; const int32_t* qinfo; const uint8_t* qd;
+  int* e_cnt; unsigned long long* e_key; uint32_t* e_doc; int P, qs, qd_stride;
+};
+__device__ __noinline__ void screen_recheck(const RecheckArgs ra, int64_t q, int64_t tile, double thr_d, int lane) {
+  const int P = ra.P;
+  double acc[8];
 #pragma unroll
-  for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
-  const int n = __shfl_sync(0xffffffffu, incl, 31);
-  const bool too_many = n > AMW_OUT;
-  if (!too_many) {
-    for (int p = 0; p < parts; ++p) {
-      const int c = __shfl_sync(0xffffffffu, mine, p), base = __shfl_sync(0xffffffffu, incl - mine, p);
-      for (int j = lane; j < c; j += 32) { W.okey[base + j] = W.keys[p * k + j]; W.odoc[base + j] = sc.pa_doc[(q * parts + p) * k + j]; }
+  for (int r = 0; r < 8; ++r) acc[r] = 0.0;
+  for (int i = 0; i < ra.qd_stride; ++i) {
+    const uint32_t ps = ra.qd[q * ra.qd_stride + i];
+    if (ps == 0xFFu) break;
+    const double2* row = reinterpret_cast<const double2*>(ra.planes + (tile * P + ps) * PLANE_TILE) + lane;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const double2 v = __ldg(row + j * 32);
+      acc[2 * j] = __dadd_rn(acc[2 * j], v.x);
+      acc[2 * j + 1] = __dadd_rn(acc[2 * j + 1], v.y);
     }
   }
-  int n2 = 32;
-  while (n2 < n && n2 < AMW_OUT) n2 <<= 1;
-  const int nn = too_many ? 0 : n;
-  for (int i = nn + lane; i < n2; i += 32) { W.okey[i] = 0ull; W.odoc[i] = 0xFFFFFFFFu; }
-  warp_sort_desc(W.okey, W.odoc, n2, lane);
-  const int cnt = min(nn, k);
-  for (int i = lane; i < k; i += 32) {
-    sc.a_key[q * k + i] = i < cnt ? W.okey[i] : 0ull;
-    sc.a_doc[q * k + i] = i < cnt ? W.odoc[i] : 0xFFFFFFFFu;
-  }
-  if (lane == 0) {
-    const bool has_planes = sc.qd[q * sc.qd_stride] != 0xFF;
-    const bool bad = ovf || too_many;
-    sc.a_cnt[q] = cnt;
-    int h3 = H3_MAX;
-    if (!has_planes && !bad)   { sc.state[q] = 1; sc.thr[q] = THR_SKIP; }
-    else if (cnt >= k && !bad) { sc.state[q] = 0; sc.thr[q] = W.okey[k - 1]; }
-    else if (!bad && (h3 = atomicAdd(&sc.counters[2], 1)) < H3_MAX) {
-      sc.state[q] = 3; sc.thr[q] = THR_SKIP; sc.h3_list[h3] = static_cast<int>(q);
-    } else {
-      sc.state[q] = 2; sc.thr[q] = THR_SKIP;
-      sc.flag_list[atomicAdd(&sc.counters[1], 1)] = static_cast<int>(q);
+  const uint32_t lt = (1u << lane) - 1u;
+#pragma unroll
+  for (int r = 0; r < 8; ++r) {
+    const int64_t d = tile * PLANE_TILE + 8 * lane + r;
+    bool p = acc[r] >= thr_d && acc[r] > 0.0;
+    if (p) p = !is_member(ra.drow_off, ra.drow_term, ra.qinfo, ra.qs, q, d);
+    const uint32_t m = __ballot_sync(0xffffffffu, p);
+    if (m == 0u) continue;
+    int base = 0;
+    if (lane == 0) base = atomicAdd(&ra.e_cnt[q], __popc(m));
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (p) {
+      const int at = base + __popc(m & lt);
+      if (at < E_CAP) { ra.e_key[q * E_CAP + at] = f64_key(acc[r]); ra.e_doc[q * E_CAP + at] = static_cast<uint32_t>(d); }
     }
   }
 }
 
-// ----------------------------------------------------------------------------
-// 2. plane pass: grid (tile sets, query groups).  The CTA stages one 256-doc tile of every
-// plane in shared memory; each warp then scores that tile for its queries with 8 register
-// accumulators per lane (lane l owns docs 8l .. 8l+7; see plane_pos()).
-// ----------------------------------------------------------------------------
-__global__ void __launch_bounds__(PL_WARPS * 32, 1)
-bm25_plane_pass_kernel(const Bm25Dev ix, int64_t nq, int64_t q_per_group, const BatchScratch sc) {
-  extern __shared__ __align__(16) double pl_smem[];            // [n_planes][256]
+__global__ void __launch_bounds__(SC_WARPS * 32, 1)
+bm25_screen_kernel(const Bm25Dev ix, int64_t nq, int64_t q_per_group, const BatchScratch sc) {
+  extern __shared__ __align__(16) uint8_t sn_smem[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int P = ix.n_planes;
+  const int P = ix.n_planes, Pp = (P + 1) & ~1;
+  const uint32_t tile_bytes = static_cast<uint32_t>(P) * PLANE_TILE * 4u;
+  double* tmax_s = reinterpret_cast<double*>(sn_smem + 2 * static_cast<size_t>(tile_bytes));       // [2][Pp]
+  ulonglong2* qrec = reinterpret_cast<ulonglong2*>(tmax_s + 2 * Pp);                               // [q_per_group]
+  int* qidx = reinterpret_cast<int*>(qrec + q_per_group);                                          // [q_per_group]
+  __shared__ __align__(8) uint64_t bar[2];
+  __shared__ int n_active;
+  __shared__ int next_a[2];                                    // next active query of the tile in buffer b (warps take turns)
   const int64_t q0 = blockIdx.y * q_per_group;
   const int64_t q1 = min(nq, q0 + q_per_group);
-  const uint32_t lt = (1u << lane) - 1u;
   const int qw = sc.qd_stride >> 3;                            // 8-byte words of packed plane slots per query
   const unsigned long long* qd64 = reinterpret_cast<const unsigned long long*>(sc.qd);
-  const uint8_t* bm_bytes = reinterpret_cast<const uint8_t*>(sc.bitmap);
-  double* tmax_s = pl_smem + static_cast<size_t>(P) * PLANE_TILE;                                    // [P] this tile's plane maxima
-  ulonglong2* qrec = reinterpret_cast<ulonglong2*>(tmax_s + ((P + 1) & ~1));                         // [q_per_group]
+  if (threadIdx.x == 0) { n_active = 0; ptx::mbar_init(&bar[0], 1); ptx::mbar_init(&bar[1], 1); ptx::fence_barrier_init(); }
+  __syncthreads();
   // Upper bounds: fp64 addition is monotone, so adding the plane maxima in the query's token order bounds the
   // in-order score of every doc that matches plane tokens only.  A query whose bound over the whole corpus is
-  // below its threshold needs no plane pass at all; the per-tile bound prunes most (query, tile) pairs of the rest.
-  for (int64_t q = q0 + threadIdx.x; q < q1; q += PL_WARPS * 32) {
+  // below its threshold needs no screening at all; the per-tile bound prunes (query, tile) pairs of the rest.
+  for (int64_t q = q0 + threadIdx.x; q < q1; q += SC_WARPS * 32) {
     const unsigned long long t = __ldg(sc.thr + q);
-    ulonglong2 rec = make_ulonglong2(0ull, ~0ull);
-    if (sc.state[q] == 3) {                                    // no bound yet: this sweep fills its score histogram
-      int slot = 0;
-      const int n3 = min(sc.counters[2], H3_MAX);
-      while (slot < n3 && sc.h3_list[slot] != static_cast<int>(q)) ++slot;
-      if (slot < n3) rec = make_ulonglong2(H3_TAG | static_cast<unsigned long long>(slot), __ldg(qd64 + q * qw));
-    } else if (t != THR_SKIP) {
-      const double thr_d = key_f64(t);
-      double ub = 0.0;
-      for (int i = 0; i < sc.qd_stride; ++i) {
-        const uint32_t ps = sc.qd[q * sc.qd_stride + i];
-        if (ps == 0xFFu) break;
-        ub = __dadd_rn(ub, __ldg(ix.plane_gmax + ps));
-      }
-      if (ub >= thr_d) rec = make_ulonglong2(static_cast<unsigned long long>(__double_as_longlong(thr_d)), __ldg(qd64 + q * qw));
+    if (sc.state[q] != 0 || t == THR_SKIP) continue;
+    const double thr_d = key_f64(t);
+    double ub = 0.0;
+    for (int i = 0; i < sc.qd_stride; ++i) {
+      const uint32_t ps = sc.qd[q * sc.qd_stride + i];
+      if (ps == 0xFFu) break;
+      ub = __dadd_rn(ub, __ldg(ix.plane_gmax + ps));
     }
-    qrec[q - q0] = rec;
+    if (ub >= thr_d) {
+      const int a = atomicAdd(&n_active, 1);
+      qrec[a] = make_ulonglong2(static_cast<unsigned long long>(__double_as_longlong(thr_d)), __ldg(qd64 + q * qw));
+      qidx[a] = static_cast<int>(q);
+    }
   }
-  // The tile of all planes is one contiguous block of P * 2 KB: one thread hands it to the bulk-copy engine in 32 KB
-  // pieces and everybody waits on the mbarrier (a 512-thread LDG/STS loop needed six dependent round trips, ~9 us per
-  // tile with nothing else resident on the SM to hide them).
-  __shared__ __align__(8) uint64_t fill_bar;
-  if (threadIdx.x == 0) { ptx::mbar_init(&fill_bar, 1); ptx::fence_barrier_init(); }
-  uint32_t fill_phase = 0;
-  for (int64_t tile = blockIdx.x; tile < ix.n_tiles; tile += gridDim.x) {
-    __syncthreads();                                           // the previous tile is no longer read; fill_bar is initialised
-    if (threadIdx.x == 0) {
-      const uint32_t bytes = static_cast<uint32_t>(P) * PLANE_TILE * 8u;
-      const char* src = reinterpret_cast<const char*>(ix.planes + tile * P * PLANE_TILE);
-      ptx::fence_proxy_async_smem();
-      ptx::mbar_expect_tx(&fill_bar, bytes);
-      for (uint32_t off = 0; off < bytes; off += 32768u)
-        ptx::bulk_load_1d(reinterpret_cast<char*>(pl_smem) + off, src + off, min(32768u, bytes - off), &fill_bar);
-    }
-    if (threadIdx.x < P) tmax_s[threadIdx.x] = __ldg(ix.plane_tmax + tile * P + threadIdx.x);
-    ptx::mbar_wait(&fill_bar, fill_phase);
-    fill_phase ^= 1u;
+  __syncthreads();
+  const int na = n_active;
+  if (na == 0) return;
+  auto issue = [&](int64_t tile, int b) {                      // thread 0: hand one fp32 tile to the bulk-copy engine
+    const char* src = reinterpret_cast<const char*>(ix.planes32 + tile * P * PLANE_TILE);
+    uint8_t* dst = sn_smem + static_cast<size_t>(b) * tile_bytes;
+    ptx::fence_proxy_async_smem();
+    ptx::mbar_expect_tx(&bar[b], tile_bytes);
+    for (uint32_t off = 0; off < tile_bytes; off += 32768u)
+      ptx::bulk_load_1d(dst + off, src + off, min(32768u, tile_bytes - off), &bar[b]);
+  };
+  int64_t tile = blockIdx.x;
+  if (threadIdx.x == 0 && tile < ix.n_tiles) issue(tile, 0);
+  uint32_t phases = 0u;
+  for (int b = 0; tile < ix.n_tiles; tile += gridDim.x, b ^= 1) {
+    // the other buffer was last read in the previous iteration, which ended with a CTA barrier
+    if (threadIdx.x == 0 && tile + gridDim.x < ix.n_tiles) issue(tile + gridDim.x, b ^ 1);
+    if (threadIdx.x < P) tmax_s[b * Pp + threadIdx.x] = __ldg(ix.plane_tmax + tile * P + threadIdx.x);
+    if (threadIdx.x == 0) next_a[b] = 0;
+    ptx::mbar_wait(&bar[b], (phases >> b) & 1u);
+    phases ^= 1u << b;
     __syncthreads();
-    // Per-query inputs: {threshold, packed plane slots} come from shared memory (staged once per CTA); the member
-    // byte is streamed from HBM (this tile's 32-byte records of consecutive queries).  Four queries are processed
-    // per outer iteration so that the loads of the next four are in flight, in their own registers, meanwhile.
-    const uint8_t* bm_tile = bm_bytes + tile * sc.nq * (PLANE_TILE / 8) + lane;   // + q * 32: this lane's 8 member bits
-    auto process = [&](const int64_t q, const uint32_t mb) {
-      const ulonglong2 rec = qrec[q - q0];                   // {k-th score of A as fp64 bits, packed plane slots}
-      unsigned long long pk = rec.y;
-        uint32_t ps = static_cast<uint32_t>(pk) & 0xFFu;
-        if (ps == 0xFFu) return;                             // skipped query (no plane tokens / fallback / bounded out)
-        const bool hist = (rec.x & H3_TAG) == H3_TAG;
-        const double thr_d = hist ? 0.0 : __longlong_as_double(static_cast<long long>(rec.x));
-        if (!hist) {
-          // this tile's bound for the query (same token order); all lanes read the same shared-memory words
-          double ub = tmax_s[ps];
-          unsigned long long pb = pk;
-          for (int i = 1; i < sc.qd_stride; ++i) {
-            if ((i & 7) == 0) pb = __ldg(qd64 + q * qw + (i >> 3)); else pb >>= 8;
-            const uint32_t s2 = static_cast<uint32_t>(pb) & 0xFFu;
-            if (s2 == 0xFFu) break;
-            ub = __dadd_rn(ub, tmax_s[s2]);
-          }
-          if (ub < thr_d) return;
+    const float* T = reinterpret_cast<const float*>(sn_smem + static_cast<size_t>(b) * tile_bytes);
+    const double* tm = tmax_s + b * Pp;
+    while (true) {                                             // warps take 32 active queries at a time
+      int a0 = 0;
+      if (lane == 0) a0 = atomicAdd(&next_a[b], 32);
+      a0 = __shfl_sync(0xffffffffu, a0, 0);
+      if (a0 >= na) break;
+      // this tile's bound for 32 queries at once, one query per lane (same token order as the scores)
+      const int a = a0 + lane;
+      ulonglong2 rec = make_ulonglong2(0ull, ~0ull);
+      int q_mine = 0;
+      bool alive = false;
+      if (a < na) {
+        rec = qrec[a];                                         // {k-th score of A as fp64 bits, packed plane slots}
+        q_mine = qidx[a];
+        double ub = tm[static_cast<uint32_t>(rec.y) & 0xFFu];
+        unsigned long long pb = rec.y;
+        for (int i = 1; i < sc.qd_stride; ++i) {
+          if ((i & 7) == 0) pb = __ldg(qd64 + static_cast<int64_t>(q_mine) * qw + (i >> 3)); else pb >>= 8;
+          const uint32_t s2 = static_cast<uint32_t>(pb) & 0xFFu;
+          if (s2 == 0xFFu) break;
+          ub = __dadd_rn(ub, tm[s2]);
         }
-        // first plane token: 0.0 + x == x (plane values are never -0.0), so the accumulators start as its row
-        double acc[8];
+        alive = ub >= __longlong_as_double(static_cast<long long>(rec.x));
+      }
+      uint32_t todo = __ballot_sync(0xffffffffu, alive);
+      while (todo != 0u) {
+        const int src = __ffs(todo) - 1;
+        todo &= todo - 1u;
+        const double thr_d = __longlong_as_double(static_cast<long long>(__shfl_sync(0xffffffffu, rec.x, src)));
+        unsigned long long pk = __shfl_sync(0xffffffffu, rec.y, src);
+        const int64_t q = __shfl_sync(0xffffffffu, q_mine, src);
+        uint32_t ps = static_cast<uint32_t>(pk) & 0xFFu;
+        // fp32 sums of rounded-up values with upward rounding: acc[r] >= the in-order fp64 score of doc 8*lane + r
+        float acc[8];
         {
-          const double2* row = reinterpret_cast<const double2*>(pl_smem + ps * PLANE_TILE) + lane;
-  #pragma unroll
-          for (int j = 0; j < 4; ++j) { const double2 v = row[j * 32]; acc[2 * j] = v.x; acc[2 * j + 1] = v.y; }
+          const float4* row = reinterpret_cast<const float4*>(T + ps * PLANE_TILE) + lane;
+          const float4 v0 = row[0], v1 = row[32];
+          acc[0] = v0.x; acc[1] = v0.y; acc[2] = v0.z; acc[3] = v0.w;
+          acc[4] = v1.x; acc[5] = v1.y; acc[6] = v1.z; acc[7] = v1.w;
         }
         for (int i = 1; i < sc.qd_stride; ++i) {
           if ((i & 7) == 0) pk = __ldg(qd64 + q * qw + (i >> 3)); else pk >>= 8;
           ps = static_cast<uint32_t>(pk) & 0xFFu;
           if (ps == 0xFFu) break;
-          const double2* row = reinterpret_cast<const double2*>(pl_smem + ps * PLANE_TILE) + lane;
-  #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const double2 v = row[j * 32];
-            acc[2 * j] = __dadd_rn(acc[2 * j], v.x);
-            acc[2 * j + 1] = __dadd_rn(acc[2 * j + 1], v.y);
-          }
+          const float4* row = reinterpret_cast<const float4*>(T + ps * PLANE_TILE) + lane;
+          const float4 v0 = row[0], v1 = row[32];
+          acc[0] = __fadd_ru(acc[0], v0.x); acc[1] = __fadd_ru(acc[1], v0.y);
+          acc[2] = __fadd_ru(acc[2], v0.z); acc[3] = __fadd_ru(acc[3], v0.w);
+          acc[4] = __fadd_ru(acc[4], v1.x); acc[5] = __fadd_ru(acc[5], v1.y);
+          acc[6] = __fadd_ru(acc[6], v1.z); acc[7] = __fadd_ru(acc[7], v1.w);
         }
-        // docs that reach A's k-th score (a positive fp64, so comparing doubles is comparing keys) and are not
-        // members of the sparse pass
-        if (hist) {
-          uint32_t* H = sc.hist + static_cast<size_t>(rec.x & 0xFFFFu) * H3_BINS;
-  #pragma unroll
-          for (int r = 0; r < 8; ++r)
-            if (acc[r] > 0.0 && !((mb >> r) & 1u)) atomicAdd(&H[h3_bin(acc[r])], 1u);
-          return;
-        }
-        uint32_t pass = 0u;
-  #pragma unroll
-        for (int r = 0; r < 8; ++r) if (acc[r] >= thr_d) pass |= 1u << r;
-        pass &= ~mb;
-        if (__ballot_sync(0xffffffffu, pass != 0u) == 0u) return;
-  #pragma unroll
-        for (int r = 0; r < 8; ++r) {
-          const bool p = (pass >> r) & 1u;
-          const uint32_t m = __ballot_sync(0xffffffffu, p);
-          if (m == 0u) continue;
-          int base = 0;
-          if (lane == 0) base = atomicAdd(&sc.e_cnt[q], __popc(m));
-          base = __shfl_sync(0xffffffffu, base, 0);
-          if (p) {
-            const int pos = base + __popc(m & lt);
-            if (pos < E_CAP) {
-              sc.e_key[q * E_CAP + pos] = f64_key(acc[r]);
-              sc.e_doc[q * E_CAP + pos] = static_cast<uint32_t>(tile * PLANE_TILE + 8 * lane + r);
-            }
-          }
-        }
-    };
-    constexpr int PF = 4;
-    uint32_t cur[PF], nxt[PF];
+        const float thr_f = __double2float_rd(thr_d);
+        bool pass = false;
 #pragma unroll
-    for (int u = 0; u < PF; ++u) {
-      const int64_t qq = q0 + warp + static_cast<int64_t>(u) * PL_WARPS;
-      cur[u] = qq < q1 ? __ldg(bm_tile + qq * 32) : 0u;
-    }
-    for (int64_t q = q0 + warp; q < q1; q += PF * PL_WARPS) {
-#pragma unroll
-      for (int u = 0; u < PF; ++u) {
-        const int64_t qq = q + static_cast<int64_t>(PF + u) * PL_WARPS;
-        nxt[u] = qq < q1 ? __ldg(bm_tile + qq * 32) : 0u;
+        for (int r = 0; r < 8; ++r) pass |= acc[r] >= thr_f;
+        if (__ballot_sync(0xffffffffu, pass) == 0u) continue;
+        // some bound reaches the threshold: the (query, tile) pair is recomputed in fp64 by bm25_recheck_kernel (its
+        // chains of dependent global loads would stall this CTA's tile barrier; queued, thousands run side by side)
+        int at = 0;
+        if (lane == 0) at = atomicAdd(&sc.counters[3], 1);
+        at = __shfl_sync(0xffffffffu, at, 0);
+        if (at < RQ_CAP) { if (lane == 0) sc.rq[at] = make_uint2(static_cast<uint32_t>(q), static_cast<uint32_t>(tile)); }
+        else screen_recheck(RecheckArgs{ix.planes, ix.drow_off, ix.drow_term, sc.qinfo, sc.qd, sc.e_cnt, sc.e_key, sc.e_doc, P, sc.qs,
+                                        sc.qd_stride}, q, tile, thr_d, lane);
       }
-#pragma unroll
-      for (int u = 0; u < PF; ++u) {
-        const int64_t qq = q + static_cast<int64_t>(u) * PL_WARPS;
-        if (qq < q1) process(qq, cur[u]);
-      }
-#pragma unroll
-      for (int u = 0; u < PF; ++u) cur[u] = nxt[u];
     }
+    __syncthreads();
   }
 }
 
-// The histogram path costs one extra sweep over all plane tiles; the per-query fallback costs ~13 us per query and
-// 16K-doc block.  With fewer than H3_MIN listed queries the fallback is cheaper: hand them over.  One block.
+// one warp per queued (query, tile) pair
+__global__ void __launch_bounds__(256)
+bm25_recheck_kernel(const Bm25Dev ix, const BatchScratch sc) {
+  const int lane = threadIdx.x & 31;
+  const int n = min(sc.counters[3], RQ_CAP);
+  const int wpg = (blockDim.x >> 5) * gridDim.x;
+  for (int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); i < n; i += wpg) {
+    const uint2 e = sc.rq[i];
+    screen_recheck(RecheckArgs{ix.planes, ix.drow_off, ix.drow_term, sc.qinfo, sc.qd, sc.e_cnt, sc.e_key, sc.e_doc, ix.n_planes, sc.qs,
+                               sc.qd_stride}, e.x, e.y, key_f64(sc.thr[e.x]), lane);
+  }
+}
+
+// The histogram path costs two extra fp64 sweeps over all plane tiles; the per-query fallback costs ~13 us per query
+// and 16K-doc block.  With fewer than H3_MIN listed queries the fallback is cheaper: hand them over.  One block.
 constexpr int H3_MIN = 64;
 __global__ void __launch_bounds__(256)
 bm25_h3_decide_kernel(const BatchScratch sc) {
@@ -788,18 +757,20 @@ bm25_h3_decide_kernel(const BatchScratch sc) {
 }
 
 // ----------------------------------------------------------------------------
-// 2b. plane pass over the (few) queries of h3_list: emission against the threshold that bm25_h3_threshold_kernel
-// derived from the histogram the main sweep filled.  Returns at once when the list is empty.
+// 2b. histogram path: queries whose list A holds fewer than k docs although they have plane tokens (frequent on
+// small shards and tiny vocabularies).  EMIT = false: histogram of the plane-only scores of ALL docs (a member's
+// plane-only score is counted too: the threshold kernel asks for correspondingly more docs).  EMIT = true: docs at
+// or above the threshold derived from it that are not members go to list E.  Returns at once when the list is empty.
 // ----------------------------------------------------------------------------
+template <bool EMIT>
 __global__ void __launch_bounds__(PL_WARPS * 32, 1)
-bm25_plane_list_kernel(const Bm25Dev ix, const BatchScratch sc) {
+bm25_plane_h3_kernel(const Bm25Dev ix, const BatchScratch sc) {
   extern __shared__ __align__(16) double pll_smem[];           // [n_planes][256]
   const int n3 = min(sc.counters[2], H3_MAX);
   if (n3 == 0) return;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int P = ix.n_planes;
   const uint32_t lt = (1u << lane) - 1u;
-  const uint8_t* bm_bytes = reinterpret_cast<const uint8_t*>(sc.bitmap);
   for (int64_t tile = blockIdx.x; tile < ix.n_tiles; tile += gridDim.x) {
     __syncthreads();
     {
@@ -810,9 +781,12 @@ bm25_plane_list_kernel(const Bm25Dev ix, const BatchScratch sc) {
     __syncthreads();
     for (int idx = warp; idx < n3; idx += PL_WARPS) {
       const int64_t q = sc.h3_list[idx];
-      const unsigned long long t = sc.thr[q];
-      if (t == THR_SKIP) continue;
-      const double thr_d = key_f64(t);
+      double thr_d = 0.0;
+      if (EMIT) {
+        const unsigned long long t = sc.thr[q];
+        if (t == THR_SKIP) continue;
+        thr_d = key_f64(t);
+      }
       double acc[8];
 #pragma unroll
       for (int r = 0; r < 8; ++r) acc[r] = 0.0;
@@ -827,22 +801,27 @@ bm25_plane_list_kernel(const Bm25Dev ix, const BatchScratch sc) {
           acc[2 * j + 1] = __dadd_rn(acc[2 * j + 1], v.y);
         }
       }
-      const uint32_t mb = bm_bytes[(tile * sc.nq + q) * (PLANE_TILE / 8) + lane];
+      if constexpr (!EMIT) {
+        uint32_t* H = sc.hist + static_cast<size_t>(idx) * H3_BINS;
+#pragma unroll
+        for (int r = 0; r < 8; ++r)
+          if (acc[r] > 0.0) atomicAdd(&H[h3_bin(acc[r])], 1u);
+      } else {
 #pragma unroll
       for (int r = 0; r < 8; ++r) {
-        const bool p = acc[r] > 0.0 && !((mb >> r) & 1u) && acc[r] >= thr_d;
+        const int64_t d = tile * PLANE_TILE + 8 * lane + r;
+        bool p = acc[r] > 0.0 && acc[r] >= thr_d;
+        if (p) p = !is_member(ix.drow_off, ix.drow_term, sc.qinfo, sc.qs, q, d);
         const uint32_t m = __ballot_sync(0xffffffffu, p);
         if (m == 0u) continue;
         int base = 0;
         if (lane == 0) base = atomicAdd(&sc.e_cnt[q], __popc(m));
         base = __shfl_sync(0xffffffffu, base, 0);
         if (p) {
-          const int pos = base + __popc(m & lt);
-          if (pos < E_CAP) {
-            sc.e_key[q * E_CAP + pos] = f64_key(acc[r]);
-            sc.e_doc[q * E_CAP + pos] = static_cast<uint32_t>(tile * PLANE_TILE + 8 * lane + r);
-          }
+          const int at = base + __popc(m & lt);
+          if (at < E_CAP) { sc.e_key[q * E_CAP + at] = f64_key(acc[r]); sc.e_doc[q * E_CAP + at] = static_cast<uint32_t>(d); }
         }
+      }
       }
     }
   }
@@ -857,7 +836,9 @@ bm25_h3_threshold_kernel(int k, const BatchScratch sc) {
   const int idx = blockIdx.x * 4 + (threadIdx.x >> 5);
   if (idx >= n3) return;
   const int64_t q = sc.h3_list[idx];
-  const int need = k;        // the members of A may all rank below the k best non-members
+  // the histogram counts every doc by its plane-only score, members included: asking for k more than the number of
+  // members leaves at least k non-members at or above the edge
+  const int need = k + sc.a_cnt[q] + sc.n_nonpos[q];
   const uint32_t* H = sc.hist + static_cast<size_t>(idx) * H3_BINS;
   int running = 0, bin = 0;
   for (int c = H3_BINS / 32 - 1; c >= 0; --c) {
@@ -948,29 +929,23 @@ bm25_flag_merge_kernel(const double* __restrict__ ps, const int64_t* __restrict_
   }
 }
 
-static thread_local int64_t g_stats[4] = {0, 0, 0, 0};
+static thread_local int64_t g_stats[6] = {0, 0, 0, 0, 0, 0};   // queries, fallback queries, emissions, max emissions, rechecks, -
 
 static int batch_set_attrs() {
   static std::once_flag once;
   static cudaError_t err = cudaSuccess;
   std::call_once(once, [] {
-    err = cudaFuncSetAttribute(bm25_sparse_pass_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                               sp_warps<256>() * static_cast<int>(sizeof(SpWarp<256>)));
+    err = cudaFuncSetAttribute(bm25_member_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_MAX);
     if (err == cudaSuccess)
-      err = cudaFuncSetAttribute(bm25_sparse_pass_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 sp_warps<512>() * static_cast<int>(sizeof(SpWarp<512>)));
+      err = cudaFuncSetAttribute(bm25_screen_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_MAX);
     if (err == cudaSuccess)
-      err = cudaFuncSetAttribute(bm25_plane_pass_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PL_SMEM_MAX);
+      err = cudaFuncSetAttribute(bm25_compact_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, C_CAP * 12);
     if (err == cudaSuccess)
-      err = cudaFuncSetAttribute(bm25_plane_list_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_PLANES * PLANE_TILE * 8);
+      err = cudaFuncSetAttribute(bm25_plane_h3_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_PLANES * PLANE_TILE * 8);
+    if (err == cudaSuccess)
+      err = cudaFuncSetAttribute(bm25_plane_h3_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_PLANES * PLANE_TILE * 8);
     if (err == cudaSuccess)
       err = cudaFuncSetAttribute(bm25_flag_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 4096 * 16);
-    if (err == cudaSuccess)
-      err = cudaFuncSetAttribute(bm25_a_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 8192 * 12);
-    if (err == cudaSuccess)
-      err = cudaFuncSetAttribute(bm25_a_merge_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 AMW_WARPS * static_cast<int>(sizeof(AmWarp)));
-
   });
   ARB_CUDA(err);
   return bm25_set_smem_attrs();
@@ -981,93 +956,120 @@ static int batch_chunk(const Bm25Dev& ix, const int32_t* d_terms, int64_t nq, in
   const int sms = num_sms();
   const bool planes = ix.n_planes > 0;
   BatchScratch sc{};
-  sc.bm_tiles = static_cast<int64_t>(ix.nb) * (DOC_BLOCK / PLANE_TILE);  // whole 16K-doc blocks
   sc.nq = nq;
-  AsyncBuf b_akey, b_adoc, b_i32, b_thr, b_u8, b_bitmap, b_ekey, b_edoc, b_pakey, b_padoc, b_pacnt, b_gthr, b_hist;
-  sc.parts = static_cast<int>(std::min<int64_t>(ix.nb, 24));
-  if (const char* v = std::getenv("ARB_BM25_PARTS")) sc.parts = std::max(1, std::min<int>(std::min<int64_t>(ix.nb, 32), atoi(v)));
-  ARB_CUDA(b_pakey.alloc(static_cast<size_t>(nq) * sc.parts * k * 8, st));
-  ARB_CUDA(b_padoc.alloc(static_cast<size_t>(nq) * sc.parts * k * 4, st));
-  ARB_CUDA(b_pacnt.alloc(static_cast<size_t>(nq) * sc.parts * 4, st));
-  ARB_CUDA(b_gthr.alloc(static_cast<size_t>(nq) * 8, st));
-  ARB_CUDA(cudaMemsetAsync(b_gthr.p, 0, static_cast<size_t>(nq) * 8, st));
-  sc.gthr = b_gthr.as<unsigned long long>();
-  sc.pa_key = b_pakey.as<unsigned long long>();
-  sc.pa_doc = b_padoc.as<uint32_t>();
-  sc.pa_cnt = b_pacnt.as<int>();
+  sc.qs = (mq + 3) & ~3;
+  sc.qd_stride = (mq + 7) & ~7;
+  AsyncBuf b_defer, b_rq;
+  ARB_CUDA(b_defer.alloc(static_cast<size_t>(sms) * MJ_DEF * sizeof(MjDefer), st));
+  sc.defer = b_defer.as<MjDefer>();
+  AsyncBuf b_qinfo, b_bt, b_pair, b_ckey, b_cdoc, b_akey, b_adoc, b_i32, b_u64, b_u8, b_ekey, b_edoc, b_hist;
+  const size_t nt = static_cast<size_t>(std::max<int64_t>(ix.n_terms, 1));
+  ARB_CUDA(b_qinfo.alloc(static_cast<size_t>(nq) * sc.qs * 4, st));
+  ARB_CUDA(b_bt.alloc((2 * nt + 1) * 4, st));                                       // bt_cur | bt_off
+  ARB_CUDA(b_pair.alloc(static_cast<size_t>(nq) * sc.qs * (16 + sc.qs * 4) + static_cast<size_t>(nq) * sc.qs * 4, st));   // bt_rec | rec_of
+  ARB_CUDA(b_ckey.alloc(static_cast<size_t>(nq) * C_CAP * 8, st));
+  ARB_CUDA(b_cdoc.alloc(static_cast<size_t>(nq) * C_CAP * 4, st));
   ARB_CUDA(b_akey.alloc(static_cast<size_t>(nq) * k * 8, st));
   ARB_CUDA(b_adoc.alloc(static_cast<size_t>(nq) * k * 4, st));
-  ARB_CUDA(b_i32.alloc((static_cast<size_t>(nq) * 3 + 4 + H3_MAX) * 4, st));   // e_cnt | counters | a_cnt | flag_list | h3_list
-  ARB_CUDA(b_thr.alloc(static_cast<size_t>(nq) * 8, st));
-  sc.qd_stride = (mq + 7) & ~7;
-  ARB_CUDA(b_u8.alloc(static_cast<size_t>(nq) * (sc.qd_stride + 8) + 16, st));
-  if (planes) {
-    ARB_CUDA(b_bitmap.alloc(static_cast<size_t>(nq) * sc.bm_tiles * 32, st));
-    ARB_CUDA(b_ekey.alloc(static_cast<size_t>(nq) * E_CAP * 8, st));
-    ARB_CUDA(b_edoc.alloc(static_cast<size_t>(nq) * E_CAP * 4, st));
-  }
+  ARB_CUDA(b_i32.alloc((static_cast<size_t>(nq) * 5 + 4 + H3_MAX) * 4, st));        // c_cnt | n_nonpos | e_cnt | counters | a_cnt | flag_list | h3_list
+  ARB_CUDA(b_u64.alloc(static_cast<size_t>(nq) * 2 * 8, st));                       // gthr | thr
+  ARB_CUDA(b_u8.alloc(static_cast<size_t>(nq) * (sc.qd_stride + 2) + 16, st));      // qd | state | ovf
+  sc.qinfo = b_qinfo.as<int32_t>();
+  sc.bt_cur = b_bt.as<uint32_t>();
+  sc.bt_off = sc.bt_cur + nt;
+  sc.bt_rec = b_pair.as<int4>();
+  sc.rec_of = reinterpret_cast<uint32_t*>(reinterpret_cast<uint8_t*>(b_pair.p) + static_cast<size_t>(nq) * sc.qs * (16 + sc.qs * 4));
+  sc.c_key = b_ckey.as<unsigned long long>();
+  sc.c_doc = b_cdoc.as<uint32_t>();
   sc.a_key = b_akey.as<unsigned long long>();
   sc.a_doc = b_adoc.as<uint32_t>();
-  sc.e_cnt = b_i32.as<int>();
+  sc.c_cnt = b_i32.as<int>();
+  sc.n_nonpos = sc.c_cnt + nq;
+  sc.e_cnt = sc.n_nonpos + nq;
   sc.counters = sc.e_cnt + nq;
   sc.a_cnt = sc.counters + 4;
   sc.flag_list = sc.a_cnt + nq;
   sc.h3_list = sc.flag_list + nq;
-  sc.thr = b_thr.as<unsigned long long>();
+  sc.gthr = b_u64.as<unsigned long long>();
+  sc.thr = sc.gthr + nq;
   sc.qd = b_u8.as<uint8_t>();                                   // 8-byte aligned rows first
   sc.state = sc.qd + static_cast<size_t>(nq) * sc.qd_stride;
-  sc.bitmap = planes ? b_bitmap.as<uint32_t>() : nullptr;
-  sc.e_key = planes ? b_ekey.as<unsigned long long>() : nullptr;
-  sc.e_doc = planes ? b_edoc.as<uint32_t>() : nullptr;
-  ARB_CUDA(cudaMemsetAsync(sc.e_cnt, 0, (static_cast<size_t>(nq) + 4) * 4, st));
+  sc.ovf = sc.state + nq;
   if (planes) {
+    ARB_CUDA(b_ekey.alloc(static_cast<size_t>(nq) * E_CAP * 8, st));
+    ARB_CUDA(b_edoc.alloc(static_cast<size_t>(nq) * E_CAP * 4, st));
     ARB_CUDA(b_hist.alloc(static_cast<size_t>(H3_MAX) * H3_BINS * 4, st));
+    ARB_CUDA(b_rq.alloc(static_cast<size_t>(RQ_CAP) * 8, st));
+    sc.rq = b_rq.as<uint2>();
+    sc.e_key = b_ekey.as<unsigned long long>();
+    sc.e_doc = b_edoc.as<uint32_t>();
     sc.hist = b_hist.as<uint32_t>();
-    ARB_CUDA(cudaMemsetAsync(sc.hist, 0, static_cast<size_t>(H3_MAX) * H3_BINS * 4, st));
   }
+  ARB_CUDA(cudaMemsetAsync(sc.bt_cur, 0, nt * 4, st));
+  ARB_CUDA(cudaMemsetAsync(sc.c_cnt, 0, (static_cast<size_t>(nq) * 3 + 4) * 4, st));   // c_cnt, n_nonpos, e_cnt, counters
+  ARB_CUDA(cudaMemsetAsync(sc.ovf, 0, static_cast<size_t>(nq), st));
 
   {
     ProfileScope ps(PROF_BM25_SPARSE, st);
-    if (2 * k + 32 <= 256) {
-      constexpr int W = sp_warps<256>();
-      const unsigned grid = static_cast<unsigned>(std::min<int64_t>(sms, (nq * sc.parts + W - 1) / W));
-      bm25_sparse_pass_kernel<256><<<grid, W * 32, W * sizeof(SpWarp<256>), st>>>(ix, d_terms, mq, nq, k, sc);
-    } else {
-      constexpr int W = sp_warps<512>();
-      const unsigned grid = static_cast<unsigned>(std::min<int64_t>(sms, (nq * sc.parts + W - 1) / W));
-      bm25_sparse_pass_kernel<512><<<grid, W * 32, W * sizeof(SpWarp<512>), st>>>(ix, d_terms, mq, nq, k, sc);
-    }
+    // ---- 0. query-term index
+    bm25_qclassify_kernel<<<static_cast<unsigned>((nq + 127) / 128), 128, 0, st>>>(ix, d_terms, mq, nq, sc);
     ARB_LAUNCH_OK();
-    if (sc.parts * k <= AMW_KEYS) {
-      bm25_a_merge_warp_kernel<<<static_cast<unsigned>((nq + AMW_WARPS - 1) / AMW_WARPS), AMW_WARPS * 32,
-                                 AMW_WARPS * sizeof(AmWarp), st>>>(nq, k, sc);
-    } else {
-      int n2 = 2;
-      while (n2 < sc.parts * k) n2 <<= 1;
-      bm25_a_merge_kernel<<<static_cast<unsigned>(nq), 128, static_cast<size_t>(n2) * 12, st>>>(nq, k, n2, sc);
-    }
+    bm25_bt_scan_kernel<<<1, 1024, 0, st>>>(ix.n_terms, sc);
     ARB_LAUNCH_OK();
+    bm25_bt_fill_kernel<<<static_cast<unsigned>((nq * sc.qs + 255) / 256), 256, 0, st>>>(nq * sc.qs, sc);
+    ARB_LAUNCH_OK();
+    // ---- 1. member pass in rounds of growing size (fractions of the tiles, in 64ths), a compaction after each
+    std::vector<int> cuts;
+    if (ix.n_tiles <= 8) cuts = {64};
+    else if (ix.n_tiles < 256) cuts = {4, 16, 64};
+    else cuts = {1, 4, 16, 32, 64};
+    if (const char* v = std::getenv("ARB_BM25_ROUNDS")) { if (atoi(v) == 1) cuts = {64}; }
+    const size_t mj_smem = static_cast<size_t>(ix.n_planes) * MJ_PSTRIDE * 8 + sizeof(MjShared);
+    int64_t prev = 0;
+    for (size_t r = 0; r < cuts.size(); ++r) {
+      const int64_t hi = cuts[r] == 64 ? ix.n_tiles : std::max(prev, (ix.n_tiles * cuts[r] + 63) / 64);
+      const bool last = r + 1 == cuts.size();
+      if (hi > prev) {
+        int sub = 1;
+        while (sub < 8 && (hi - prev) * sub < sms) sub <<= 1;
+        const unsigned grid = static_cast<unsigned>(std::min<int64_t>((hi - prev) * sub, sms));
+        bm25_member_kernel<<<grid, MJ_THREADS, mj_smem, st>>>(ix, sc, prev, hi, sub);
+        ARB_LAUNCH_OK();
+      }
+      if (hi > prev || last) {
+        bm25_compact_kernel<<<static_cast<unsigned>(nq), 256, C_CAP * 12, st>>>(nq, k, last ? 1 : 0, sc);
+        ARB_LAUNCH_OK();
+      }
+      prev = hi;
+    }
   }
   if (planes) {
     ProfileScope ps(PROF_BM25_PLANES, st);
+    ARB_CUDA(cudaMemsetAsync(sc.hist, 0, static_cast<size_t>(H3_MAX) * H3_BINS * 4, st));
     bm25_h3_decide_kernel<<<1, 256, 0, st>>>(sc);
     ARB_LAUNCH_OK();
-    // enough CTAs to fill the GPU: tile sets first, query groups when the corpus has few tiles
-    const int64_t sets = std::min<int64_t>(ix.n_tiles, sms);
-    const size_t plane_smem = static_cast<size_t>(ix.n_planes) * PLANE_TILE * 8;
-    const size_t tmax_smem = static_cast<size_t>((ix.n_planes + 1) & ~1) * 8;
-    const int64_t max_qpg = static_cast<int64_t>((PL_SMEM_MAX - plane_smem - tmax_smem) / 16);   // {thr, slots} records per CTA
-    int64_t groups = std::max<int64_t>(1, std::min<int64_t>(sms / sets, (nq + 4 * PL_WARPS - 1) / (4 * PL_WARPS)));
-    groups = std::max<int64_t>(groups, (nq + max_qpg - 1) / max_qpg);
+    // ---- 2. screening pass: one CTA per SM; query groups sized by what is left of shared memory beside two tiles
+    const size_t tiles_smem = 2 * static_cast<size_t>(ix.n_planes) * PLANE_TILE * 4 + 2 * static_cast<size_t>((ix.n_planes + 1) & ~1) * 8;
+    const int64_t max_qpg = static_cast<int64_t>((SMEM_MAX - tiles_smem) / 20);     // {thr, slots} record + query index per query
+    int64_t groups = std::max<int64_t>(1, (nq + max_qpg - 1) / max_qpg);
+    if (ix.n_tiles * groups < sms)                                                  // few tiles: more groups fill the GPU
+      groups = std::max<int64_t>(groups, std::min<int64_t>((sms + ix.n_tiles - 1) / ix.n_tiles, (nq + 4 * SC_WARPS - 1) / (4 * SC_WARPS)));
     const int64_t qpg = (nq + groups - 1) / groups;
     groups = (nq + qpg - 1) / qpg;
+    const int64_t sets = std::max<int64_t>(1, std::min<int64_t>(ix.n_tiles, sms / groups));
     dim3 grid(static_cast<unsigned>(sets), static_cast<unsigned>(groups));
-    bm25_plane_pass_kernel<<<grid, PL_WARPS * 32, plane_smem + tmax_smem + static_cast<size_t>(qpg) * 16, st>>>(ix, nq, qpg, sc);
+    bm25_screen_kernel<<<grid, SC_WARPS * 32, tiles_smem + static_cast<size_t>(qpg) * 20, st>>>(ix, nq, qpg, sc);
     ARB_LAUNCH_OK();
-    // queries without a bound from list A: their score histogram was filled by the sweep above -> threshold -> emission
+    bm25_recheck_kernel<<<static_cast<unsigned>(8 * sms), 256, 0, st>>>(ix, sc);
+    ARB_LAUNCH_OK();
+    // ---- 2b. histogram path (returns at once unless at least H3_MIN queries lack a bound from list A)
+    const size_t plane_smem = static_cast<size_t>(ix.n_planes) * PLANE_TILE * 8;
+    const unsigned h3_grid = static_cast<unsigned>(std::min<int64_t>(ix.n_tiles, sms));
+    bm25_plane_h3_kernel<false><<<h3_grid, PL_WARPS * 32, plane_smem, st>>>(ix, sc);
+    ARB_LAUNCH_OK();
     bm25_h3_threshold_kernel<<<H3_MAX / 4, 128, 0, st>>>(k, sc);
     ARB_LAUNCH_OK();
-    bm25_plane_list_kernel<<<static_cast<unsigned>(sets), PL_WARPS * 32, plane_smem, st>>>(ix, sc);
+    bm25_plane_h3_kernel<true><<<h3_grid, PL_WARPS * 32, plane_smem, st>>>(ix, sc);
     ARB_LAUNCH_OK();
   }
   {
@@ -1109,6 +1111,7 @@ static int batch_chunk(const Bm25Dev& ix, const int32_t* d_terms, int64_t nq, in
     ARB_CUDA(cudaStreamSynchronize(st));
     g_stats[0] += nq;
     g_stats[1] += h[nq + 1];
+    g_stats[4] += h[nq + 3];
     for (int64_t i = 0; i < nq; ++i) { g_stats[2] += h[i]; g_stats[3] = std::max<int64_t>(g_stats[3], h[i]); }
   }
   return ARB_OK;
@@ -1118,9 +1121,8 @@ int bm25_batch_search(const Bm25Dev& ix, const int32_t* d_terms, int64_t nq, int
                       double* d_scores, int64_t* d_ids, cudaStream_t st) {
   int rc = batch_set_attrs();
   if (rc) return rc;
-  // the member bitmap is nq x n_docs bits: cut the batch so that it stays under ~2 GB
-  const int64_t row_bytes = std::max<int64_t>(1, static_cast<int64_t>(ix.nb) * (DOC_BLOCK / 8));
-  int64_t chunk = std::max<int64_t>(64, (int64_t(2) << 30) / row_bytes);
+  // candidate lists are C_CAP entries per query: cut very large batches so that the scratch stays under ~0.4 GB
+  int64_t chunk = 8192;
   if (const char* v = std::getenv("ARB_BM25_CHUNK")) chunk = std::max<int64_t>(1, atoll(v));
   for (int64_t q0 = 0; q0 < nq; q0 += chunk) {
     const int64_t n = std::min(chunk, nq - q0);
@@ -1132,7 +1134,7 @@ int bm25_batch_search(const Bm25Dev& ix, const int32_t* d_terms, int64_t nq, int
 
 }  // namespace arb
 
-extern "C" int arb_bm25_batch_stats(int64_t out[4], int reset) {
-  for (int i = 0; i < 4; ++i) { if (out) out[i] = arb::g_stats[i]; if (reset) arb::g_stats[i] = 0; }
+extern "C" int arb_bm25_batch_stats(int64_t out[6], int reset) {
+  for (int i = 0; i < 6; ++i) { if (out) out[i] = arb::g_stats[i]; if (reset) arb::g_stats[i] = 0; }
   return ARB_OK;
 }

@@ -1,8 +1,12 @@
 """Seeded synthetic inputs for the BASELINE.json configurations.
 
-Dense rows are generated on the device in fixed chunks of ``CHUNK`` rows from a
-generator keyed by (seed, chunk index), so any sharding of the corpus sees
-identical rows.  BM25 documents are Poisson(mean_len)-long token streams drawn from
+Dense rows are generated in fixed chunks of ``CHUNK`` rows from a generator keyed
+by (seed, chunk index), so any sharding of the corpus sees identical rows.  With
+``host_rng=True`` the generator runs on the CPU whatever the target device, so the
+B200 arm and the CPU reference arm of ``bench.py`` score bit-identical inputs (cfg3);
+the 100 M-row cfg4 shards are generated on the device.  This module imports nothing
+of the package: ``bench.py --impl reference`` loads it by file path without mapping
+the CUDA library.  BM25 documents are Poisson(mean_len)-long token streams drawn from
 a Zipf(s=1) law over ``vocab`` term ids; queries mix 4 Zipf-drawn tokens with 4
 tokens of a random document so that real matches exist.
 """
@@ -15,35 +19,37 @@ CHUNK = 65536
 SEED_CORPUS, SEED_QUERIES, SEED_TEXT = 1234, 1235, 1236
 
 
-def _chunk(seed: int, c: int, d: int, device) -> torch.Tensor:
-    g = torch.Generator(device=device)
+def _chunk(seed: int, c: int, d: int, device, host_rng: bool = False) -> torch.Tensor:
+    gen_dev = "cpu" if host_rng else device
+    g = torch.Generator(device=gen_dev)
     g.manual_seed(seed * 1_000_003 + c)
-    x = torch.randn((CHUNK, d), generator=g, device=device, dtype=torch.float32)
+    x = torch.randn((CHUNK, d), generator=g, device=gen_dev, dtype=torch.float32)
     return torch.nn.functional.normalize(x, dim=1)
 
 
-def dense_rows(row0: int, n: int, d: int, device, dtype=torch.bfloat16, seed: int = SEED_CORPUS):
+def dense_rows(row0: int, n: int, d: int, device, dtype=torch.bfloat16, seed: int = SEED_CORPUS, host_rng: bool = False):
     """Yield (first_row, tensor) pieces covering rows [row0, row0+n): unit-norm rows rounded to ``dtype``."""
     r = row0
     end = row0 + n
     while r < end:
         c = r // CHUNK
-        x = _chunk(seed, c, d, device)
+        x = _chunk(seed, c, d, device, host_rng)
         lo = r - c * CHUNK
         hi = min(CHUNK, end - c * CHUNK)
-        yield r, x[lo:hi].to(dtype)
+        yield r, x[lo:hi].to(dtype).to(device)
         r = c * CHUNK + hi
 
 
 def dense_queries(nq: int, d: int, device, dtype=torch.bfloat16, n_rows: int = CHUNK, seed: int = SEED_QUERIES,
-                  corpus_seed: int = SEED_CORPUS) -> torch.Tensor:
+                  corpus_seed: int = SEED_CORPUS, host_rng: bool = False) -> torch.Tensor:
     """normalise(X[j] + 0.5*N(0,1)) for random rows j of the first corpus chunk."""
-    g = torch.Generator(device=device)
+    gen_dev = "cpu" if host_rng else device
+    g = torch.Generator(device=gen_dev)
     g.manual_seed(seed)
-    base = _chunk(corpus_seed, 0, d, device)[: min(CHUNK, n_rows)]
-    j = torch.randint(0, base.shape[0], (nq,), generator=g, device=device)
-    q = base[j] + 0.5 * torch.randn((nq, d), generator=g, device=device) / (d ** 0.5)
-    return torch.nn.functional.normalize(q, dim=1).to(dtype)
+    base = _chunk(corpus_seed, 0, d, device, host_rng)[: min(CHUNK, n_rows)]
+    j = torch.randint(0, base.shape[0], (nq,), generator=g, device=gen_dev)
+    q = base[j] + 0.5 * torch.randn((nq, d), generator=g, device=gen_dev) / (d ** 0.5)
+    return torch.nn.functional.normalize(q, dim=1).to(dtype).to(device)
 
 
 def zipf_cdf(vocab: int) -> np.ndarray:

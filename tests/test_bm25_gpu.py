@@ -61,6 +61,23 @@ def test_okapi_matches_restated_rank_bm25():
     assert bm25_scores(object(), notes, "w1") == [0.0] * len(notes)
 
 
+def test_okapi_reproduces_rank_bm25_readme_vector():
+    """rank_bm25's README known answer ("windy London" -> [0., 0.93729472, 0.]) through the CUDA path: the only
+    library-held pin for BM25Okapi available offline (utils/bm25_search.py:273,309)."""
+    import ano_rag_b200  # noqa: F401
+    from ano_rag_b200.utils.bm25_search import GpuBM25
+    from oracle import bm25 as obm
+    corpus = ["Hello there good man!", "It is quite windy in London", "How is the weather today?"]
+    tok = [d.split(" ") for d in corpus]
+    gpu = GpuBM25(tok, variant="okapi")
+    s = gpu.get_scores("windy London".split(" "))
+    assert np.round(s, 8).tolist() == [0.0, 0.93729472, 0.0]
+    assert s.tolist() == obm.BM25OkapiOracle(tok).get_scores("windy London".split(" ")).tolist()
+    sc, ids = gpu.search_terms(gpu.encode_queries(["windy London".split(" ")]), 2)
+    assert ids[0].tolist() == [1, -1] and sc[0, 0] == s[1]
+    gpu.close()
+
+
 def test_degenerate_corpora_fall_back_to_simple():
     import ano_rag_b200  # noqa: F401
     from ano_rag_b200.utils.bm25_search import build_bm25_corpus, bm25_scores

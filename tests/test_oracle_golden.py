@@ -74,6 +74,21 @@ def test_okapi_restatement_known_answers():
     assert c.get_scores(["quick", "fox"]).tolist() == [1.627995888953579, 0.0, 0.0, 0.0]
 
 
+README_CORPUS = ["Hello there good man!", "It is quite windy in London", "How is the weather today?"]
+
+
+def test_okapi_oracle_reproduces_rank_bm25_readme_vector():
+    """The one library-held known answer available offline: rank_bm25's README scores its three-sentence corpus
+    (``doc.split(" ")`` tokens) for "windy London" as ``array([0., 0.93729472, 0.])`` -- the printed 8 decimals pin
+    idf (incl. the epsilon floor: "is" has df 2 of 3 -> negative idf), avgdl and the saturation formula at
+    utils/bm25_search.py:273,309."""
+    c = obm.BM25OkapiOracle([d.split(" ") for d in README_CORPUS])
+    s = c.get_scores("windy London".split(" "))
+    assert np.round(s, 8).tolist() == [0.0, 0.93729472, 0.0]
+    assert s[1].hex() == "0x1.dfe51807c1be5p-1"                  # the full fp64 value the CUDA path must reproduce
+    assert c.idf["is"] == c.epsilon * c.average_idf and c.average_idf > 0
+
+
 @pytest.mark.parametrize("variant", ["okapi", "simple"])
 def test_array_oracle_bit_identical_to_class_oracle(variant):
     rng = random.Random(5)
