@@ -144,7 +144,8 @@ def profile_collect():
 
 def bm25_batch_stats(reset: bool = True):
     """Diagnostics of the batched BM25 pipeline (needs ARB_BM25_STATS=1 in the environment)."""
-    out = (c_int64 * 6)()
+    out = (c_int64 * 8)()
     check(lib.arb_bm25_batch_stats(out, 1 if reset else 0))
     return {"queries": int(out[0]), "fallback_queries": int(out[1]), "emissions": int(out[2]),
-            "max_emissions": int(out[3]), "fp64_rechecks": int(out[4])}
+            "max_emissions": int(out[3]), "fp64_rechecks": int(out[4]), "set_aside_pairs": int(out[5]),
+            "set_aside_matched": int(out[6])}

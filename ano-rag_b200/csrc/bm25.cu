@@ -140,6 +140,27 @@ __global__ void bm25_drow_off_kernel(const uint32_t* __restrict__ sorted_key, in
   }
   drow_off[d] = static_cast<uint32_t>(lo);
 }
+// tile-major copy: key = tile of the posting's doc (sentinel n_tiles for plane / zero-idf terms); the stable sort keeps
+// the (term, doc) order of the term-major input inside a tile
+__global__ void bm25_tile_key_kernel(const uint32_t* __restrict__ doc_key, int64_t n_post, uint32_t doc_sentinel,
+                                     uint32_t tile_sentinel, uint32_t* __restrict__ key) {
+  const int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  if (i >= n_post) return;
+  const uint32_t d = doc_key[i];
+  key[i] = d == doc_sentinel ? tile_sentinel : d >> PLANE_TILE_LOG2;
+}
+__global__ void bm25_tt_fill_kernel(const uint32_t* __restrict__ sorted_val, int64_t n_sp, const int64_t* __restrict__ term_ptr,
+                                    int64_t n_terms, const int32_t* __restrict__ doc, const int32_t* __restrict__ gcode,
+                                    const double* __restrict__ idf, const double* __restrict__ gtab, uint32_t* __restrict__ tt_term,
+                                    uint8_t* __restrict__ tt_doc, double* __restrict__ tt_val) {
+  const int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  if (i >= n_sp) return;
+  const int64_t p = sorted_val[i];
+  const int64_t t = term_of_posting(term_ptr, n_terms, p);
+  tt_term[i] = static_cast<uint32_t>(t);
+  tt_doc[i] = static_cast<uint8_t>(doc[p] & (PLANE_TILE - 1));
+  tt_val[i] = __dmul_rn(idf[t], gtab[gcode[p]]);
+}
 // step 3: term id and finished contribution idf * g of every row entry
 __global__ void bm25_drow_fill_kernel(const uint32_t* __restrict__ sorted_val, int64_t n_sp, const int64_t* __restrict__ term_ptr,
                                       int64_t n_terms, const int32_t* __restrict__ gcode, const double* __restrict__ idf,
@@ -762,10 +783,47 @@ extern "C" int arb_bm25_create(arb_bm25** out, int64_t n_docs, int64_t n_terms, 
               v_out.as<uint32_t>(), n_sp, d_ptr.as<int64_t>(), n_terms, d_code.as<int32_t>(), bm->idf, bm->gtab, bm->drow_term, bm->drow_val);
           count_launch();
         }
+        // the tile-major, term-major-inside-a-tile copy (k_in still holds the unsorted doc keys in term-major order)
+        {
+          const int64_t n_tiles = bm->dev.n_tiles;
+          if (cudaMalloc(&bm->tt_off, static_cast<size_t>(n_tiles + 1) * 4) != cudaSuccess ||
+              cudaMalloc(&bm->tt_term, std::max<size_t>(n_sp, 1) * 4) != cudaSuccess ||
+              cudaMalloc(&bm->tt_doc, std::max<size_t>(n_sp, 1) + 16) != cudaSuccess ||
+              cudaMalloc(&bm->tt_val, std::max<size_t>(n_sp, 1) * 8) != cudaSuccess) {
+            cudaGetLastError(); set_error("arb_bm25_create: out of device memory (tile rows)"); return fail(ARB_ENOMEM);
+          }
+          AsyncBuf t_key;
+          e = t_key.alloc(np4, st);
+          if (e != cudaSuccess) { cudaGetLastError(); set_error("arb_bm25_create: out of device memory (tile-row build)"); return fail(ARB_ENOMEM); }
+          bm25_tile_key_kernel<<<static_cast<unsigned>((n_post + 255) / 256), 256, 0, st>>>(
+              k_in.as<uint32_t>(), n_post, static_cast<uint32_t>(n_docs), static_cast<uint32_t>(n_tiles), t_key.as<uint32_t>());
+          count_launch();
+          int tbits = 1;
+          while ((int64_t(1) << tbits) <= n_tiles) ++tbits;     // keys are in [0, n_tiles]
+          size_t tb2 = 0;
+          e = cub::DeviceRadixSort::SortPairs(nullptr, tb2, t_key.as<uint32_t>(), k_out.as<uint32_t>(), v_in.as<uint32_t>(),
+                                              v_out.as<uint32_t>(), static_cast<int>(n_post), 0, tbits, st);
+          AsyncBuf tmp2;
+          if (e == cudaSuccess) e = tmp2.alloc(tb2, st);
+          if (e == cudaSuccess)
+            e = cub::DeviceRadixSort::SortPairs(tmp2.p, tb2, t_key.as<uint32_t>(), k_out.as<uint32_t>(), v_in.as<uint32_t>(),
+                                                v_out.as<uint32_t>(), static_cast<int>(n_post), 0, tbits, st);
+          if (e != cudaSuccess) return fail(cuda_fail(e, "bm25 tile-row sort", __FILE__, __LINE__));
+          bm25_drow_off_kernel<<<static_cast<unsigned>((n_tiles + 1 + 255) / 256), 256, 0, st>>>(k_out.as<uint32_t>(), n_post, n_tiles, bm->tt_off);
+          count_launch();
+          if (n_sp > 0) {
+            bm25_tt_fill_kernel<<<static_cast<unsigned>((n_sp + 255) / 256), 256, 0, st>>>(
+                v_out.as<uint32_t>(), n_sp, d_ptr.as<int64_t>(), n_terms, d_doc.as<int32_t>(), d_code.as<int32_t>(), bm->idf, bm->gtab,
+                bm->tt_term, bm->tt_doc, bm->tt_val);
+            count_launch();
+          }
+        }
         e = cudaStreamSynchronize(st);
         if (e != cudaSuccess) return fail(cuda_fail(e, "bm25 doc rows", __FILE__, __LINE__));
       } else {
         e = cudaMemsetAsync(bm->drow_off, 0, static_cast<size_t>(n_docs + 1) * 4, st);
+        if (e == cudaSuccess && cudaMalloc(&bm->tt_off, static_cast<size_t>(bm->dev.n_tiles + 1) * 4) != cudaSuccess) e = cudaErrorMemoryAllocation;
+        if (e == cudaSuccess) e = cudaMemsetAsync(bm->tt_off, 0, static_cast<size_t>(bm->dev.n_tiles + 1) * 4, st);
         if (e != cudaSuccess) return fail(cuda_fail(e, "bm25 doc rows", __FILE__, __LINE__));
       }
       bm->dev.n_sp = n_sp;
@@ -785,6 +843,7 @@ extern "C" int arb_bm25_create(arb_bm25** out, int64_t n_docs, int64_t n_terms, 
   bm->dev.plane_gmax = bm->plane_tmax ? bm->plane_tmax + static_cast<size_t>(bm->dev.n_tiles) * bm->dev.n_planes : nullptr;
   bm->dev.planes32 = bm->planes32;
   bm->dev.drow_off = bm->drow_off; bm->dev.drow_term = bm->drow_term; bm->dev.drow_val = bm->drow_val;
+  bm->dev.tt_off = bm->tt_off; bm->dev.tt_term = bm->tt_term; bm->dev.tt_doc = bm->tt_doc; bm->dev.tt_val = bm->tt_val;
   *out = bm;
   return ARB_OK;
 }
@@ -804,6 +863,10 @@ extern "C" int arb_bm25_destroy(arb_bm25* bm) {
   if (bm->drow_off) cudaFree(bm->drow_off);
   if (bm->drow_term) cudaFree(bm->drow_term);
   if (bm->drow_val) cudaFree(bm->drow_val);
+  if (bm->tt_off) cudaFree(bm->tt_off);
+  if (bm->tt_term) cudaFree(bm->tt_term);
+  if (bm->tt_doc) cudaFree(bm->tt_doc);
+  if (bm->tt_val) cudaFree(bm->tt_val);
   delete bm;
   return ARB_OK;
 }

@@ -58,6 +58,12 @@ struct Bm25Dev {
   const uint32_t* drow_off;     // [n_docs + 1]
   const uint32_t* drow_term;    // [n_sp]
   const double* drow_val;       // [n_sp]
+  // the same sparse postings once more, tile-major and TERM-major inside a 256-doc tile (docs ascending inside a
+  // term): the member pass applies one decoded query-term record to all docs of its term in the tile
+  const uint32_t* tt_off;       // [n_tiles + 1]
+  const uint32_t* tt_term;      // [n_sp]
+  const uint8_t* tt_doc;        // [n_sp] doc inside the tile
+  const double* tt_val;         // [n_sp]
 };
 
 // Position of doc d (0..255) inside a 256-entry fp32 plane-tile row: lane l owns docs 8l .. 8l+7 and reads them as
@@ -96,5 +102,9 @@ struct arb_bm25 {
   uint32_t* drow_off = nullptr;
   uint32_t* drow_term = nullptr;
   double* drow_val = nullptr;
+  uint32_t* tt_off = nullptr;
+  uint32_t* tt_term = nullptr;
+  uint8_t* tt_doc = nullptr;
+  double* tt_val = nullptr;
   std::vector<int64_t> df;      // host copy of per-term df (roofline accounting)
 };

@@ -47,7 +47,7 @@ namespace arb {
 
 constexpr int SC_WARPS = 32;                         // screening pass: warps per CTA (two fp32 plane tiles in flight)
 constexpr int PL_WARPS = 16;                         // fp64 plane kernels of the histogram path
-constexpr int SMEM_MAX = 227 * 1024 - 128;           // dynamic shared memory per CTA (128 B left for static barriers)
+constexpr int SMEM_MAX = 227 * 1024 - 256;           // dynamic shared memory per CTA (256 B left for static barriers / scan scratch)
 constexpr int C_CAP = 4096;                          // candidate entries a query may collect between two compactions
 constexpr int E_CAP = 1024;                          // screening-pass emissions kept per query
 constexpr int RQ_CAP = 1 << 20;                      // queued fp64 rechecks per batch chunk (more: done in place)
@@ -75,7 +75,8 @@ struct BatchScratch {
   uint32_t* bt_cur;            // [n_terms] occurrence counts, then fill cursors
   int4* bt_rec;                // [sparse tokens of the batch] records of 1 + qs/4 int4, grouped by term (bm25_bt_fill_kernel)
   uint32_t* rec_of;            // [nq * qs] record of a sparse query token, else 0xFFFFFFFF
-  MjDefer* defer;       // [member-pass CTAs, MJ_DEF] set-aside pairs of the unit being joined
+  MjDefer* defer;
+  int* def_cnt;                // [member-pass CTAs] entries queued by the launch       // [member-pass CTAs, MJ_DEF] set-aside pairs of the unit being joined
   // ---- member pass
   unsigned long long* c_key;   // [nq, C_CAP] candidates; [0, k) = running top-k after a compaction
   uint32_t* c_doc;             // [nq, C_CAP]
@@ -95,7 +96,9 @@ struct BatchScratch {
   uint32_t* e_doc;             // [nq, E_CAP]
   int* e_cnt;                  // [nq]
   int* flag_list;              // [nq]
-  int* counters;               // [1] number of flagged queries, [2] histogram queries, [3] queued rechecks
+  int* counters;               // [0] set-aside pairs, [1] flagged queries, [2] histogram queries, [3] queued rechecks, [4] set-aside pairs
+                               // that did match another sparse token (diagnostics)
+  int stats_on;
   uint2* rq;                   // [RQ_CAP] (query, tile) pairs the screening pass wants recomputed in fp64
   int* h3_list;                // [H3_MAX]
   uint32_t* hist;              // [H3_MAX, H3_BINS]
@@ -141,10 +144,16 @@ __device__ __forceinline__ void cta_sort_desc(unsigned long long* key, IdT* id, 
 }
 
 
-// two hash functions into a 384-bit filter; bit 383 is never set (record entries without a sparse term point at it)
-constexpr uint32_t BLOOM_MUL1 = 0x9E3779B1u, BLOOM_MUL2 = 0x85EBCA6Bu;
-constexpr uint32_t BLOOM_NONE = 383u, SLOT_NONE = 127u;
-__host__ __device__ __forceinline__ uint32_t bloom_bit(uint32_t t, uint32_t mul) { return (((t * mul) >> 23) * 383u) >> 9; }   // 0 .. 382
+// Per-doc filter of the doc's sparse terms: 16 words; a term sets three of bits 0..30 of ONE word, so a look-up is one
+// load and one masked compare (~1 % false positives per look-up for a doc with 22 sparse terms).  Bit 31 is never set:
+// a record entry without a sparse term tests for it.
+constexpr uint32_t SLOT_NONE = 127u;
+constexpr int MJ_BLOOM_W = 16;
+__host__ __device__ __forceinline__ uint32_t bloom_word(uint32_t t) { return (t * 0x9E3779B1u) >> 28; }
+__host__ __device__ __forceinline__ uint32_t bloom_mask(uint32_t t) {
+  const uint32_t h = t * 0x85EBCA6Bu;
+  return (1u << ((h >> 27) * 31u >> 5)) | (1u << (((h >> 22) & 31u) * 31u >> 5)) | (1u << (((h >> 17) & 31u) * 31u >> 5));
+}
 
 // ----------------------------------------------------------------------------
 // 0. query-term index of the batch
@@ -197,10 +206,11 @@ bm25_bt_scan_kernel(int64_t n_terms, const BatchScratch sc) {
 
 // One record per sparse query token, grouped by term: everything the member pass needs to score the token's query
 // against a doc arrives with ONE load -- {query << 5 | position, -, bound of the current round (8 B)} followed by
-// one entry per query token: plane slot (bits 0-6, 127 = none) | the two filter bit positions of a sparse term
-// (bits 7-15 and 16-24, 383 = none; the record's OWN token carries none: its value arrives with the posting).  The
-// member pass evaluates every entry the same way, without branching on the token kind; the exact path reads the term
-// ids from qinfo.  rec_of remembers where a query's records went (the compaction updates their bound).
+// one entry per query token: plane slot (bits 0-6, 127 = none) | filter word of a sparse term (bits 7-10, the record's
+// OWN token and non-sparse tokens carry word 0 with the never-set mask bit) | up to three bit positions inside the
+// word (11-15, 16-20, 21-25; 31 = none).  The member pass evaluates every entry the same way, without branching on the token kind; the
+// exact path reads the term ids from qinfo.  rec_of remembers where a query's records went (the compaction updates
+// their bound).
 __global__ void __launch_bounds__(256)
 bm25_bt_fill_kernel(int64_t n, const BatchScratch sc) {
   const int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
@@ -221,13 +231,17 @@ bm25_bt_fill_kernel(int64_t n, const BatchScratch sc) {
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
       const int c = src[4 * j + e];
-      uint32_t slot = SLOT_NONE, b1 = BLOOM_NONE, b2 = BLOOM_NONE;
+      uint32_t slot = SLOT_NONE, w = 0u, x = 31u, y = 31u, z = 31u;
       if (c <= -2) slot = static_cast<uint32_t>(-2 - c);
       else if (c >= 0 && 4 * j + e != static_cast<int>(i - q * sc.qs)) {
-        b1 = bloom_bit(static_cast<uint32_t>(c), BLOOM_MUL1);
-        b2 = bloom_bit(static_cast<uint32_t>(c), BLOOM_MUL2);
+        const uint32_t m = bloom_mask(static_cast<uint32_t>(c));             // one to three distinct bits
+        w = bloom_word(static_cast<uint32_t>(c));
+        x = __ffs(m) - 1;
+        z = 31 - __clz(m);
+        const uint32_t mid = m & ~(1u << x) & ~(1u << z);
+        y = mid ? __ffs(mid) - 1 : x;
       }
-      f[e] = static_cast<int>(slot | (b1 << 7) | (b2 << 16));
+      f[e] = static_cast<int>(slot | (w << 7) | (x << 11) | (y << 16) | (z << 21));
     }
     rec[1 + j] = make_int4(f[0], f[1], f[2], f[3]);
   }
@@ -236,22 +250,14 @@ bm25_bt_fill_kernel(int64_t n, const BatchScratch sc) {
 // ----------------------------------------------------------------------------
 // 1. member pass
 // ----------------------------------------------------------------------------
-constexpr int MJ_THREADS = 768;
-constexpr int MJ_CH = 2048;                          // postings joined per chunk
-constexpr int MJ_BLOOM_W = 12;                       // 384-bit filter per doc, two hash functions
-constexpr int MJ_DEF = 32768;                        // set-aside pairs per CTA and unit, in global scratch (more: finished in place)
+constexpr int MJ_THREADS = 512;
+constexpr int MJ_CH_MAX = 2048;                      // postings joined per chunk (fewer when 96 planes fill shared memory)
+constexpr int MJ_DEF = 65536;                        // set-aside pairs per CTA and launch, in global scratch (more: finished in place)
 constexpr int MJ_PSTRIDE = PLANE_TILE + 2;           // padded plane rows: threads of a warp mostly read the SAME doc of
                                                      // different planes; 258 * 8 B keeps bulk copies 16-byte aligned
-struct MjShared {
-  uint32_t pscan[MJ_CH + 4];             // exclusive scan of the chunk's pair counts; [n_ch] = total
-  uint32_t cbase[MJ_CH];                 // first record of each posting's term
-  uint32_t bloom[PLANE_TILE * MJ_BLOOM_W];
-  uint32_t doff[PLANE_TILE + 4];         // row offsets of the unit's docs
-  uint32_t wsum[32];
-  uint8_t pdoc[MJ_CH];                   // doc (inside the unit) of each posting
-  int n_def;
-};
-static_assert(MAX_PLANES * MJ_PSTRIDE * 8 + sizeof(MjShared) <= SMEM_MAX, "member pass: plane tile + join state must fit one CTA");
+// dynamic shared memory of the member pass: [P + 1][MJ_PSTRIDE] fp64 plane rows (row P = zeros, read for tokens that
+// are not plane terms) | bloom [256][12] | pscan [ch + 4] | cbase [ch] | pinfo [ch]
+__host__ __device__ inline size_t mj_fixed_bytes(int P) { return static_cast<size_t>(P + 1) * MJ_PSTRIDE * 8 + PLANE_TILE * MJ_BLOOM_W * 4 + 16; }
 // index of term c in the ascending list dt[0, n), or -1
 __device__ __forceinline__ int row_find(const uint32_t* __restrict__ dt, int n, uint32_t c) {
   int lo = 0, hi = n;
@@ -278,7 +284,8 @@ __device__ __forceinline__ int seg_of(const uint32_t* off, int n, uint32_t x) {
 }
 
 // append (key, doc) to query q's candidates if it beats the round's bound; count members that can never be candidates
-__device__ __forceinline__ void member_emit(const BatchScratch& sc, int64_t q, double acc, unsigned long long bound, int64_t d) {
+template <class Scratch>
+__device__ __forceinline__ void member_emit(const Scratch& sc, int64_t q, double acc, unsigned long long bound, int64_t d) {
   const unsigned long long key = f64_key(acc);
   if (key > bound) {
     const int at = atomicAdd(sc.c_cnt + q, 1);
@@ -288,35 +295,96 @@ __device__ __forceinline__ void member_emit(const BatchScratch& sc, int64_t q, d
   }
 }
 
-// grid: persistent CTAs over the units of tiles [tile_lo, tile_hi); a unit is 1/sub of a tile's docs.  Per unit:
-// stage the tile of all planes (bulk copy), build the per-doc filters, then join the unit's doc rows with the batch's
-// query-term index 2048 postings at a time: record counts -> CTA-wide exclusive scan -> every thread scores a contiguous
-// run of (posting, record) pairs, keeping the posting's state in registers.  The complete score of a pair's (query, doc)
-// is summed in query-token order: plane tokens from the staged tile, the pair's own token from the posting, +0.0 for
-// every other sparse token of the query -- unless the doc's filter says one of them may be present: those pairs are
-// set aside with the positions in question and finished after the last chunk (doc row searched; a pair whose query
-// matches the doc at an EARLIER position belongs to that position's pair and is dropped).
-struct MjDefer { uint32_t posting, rec, hits; };
+// One set-aside (record, doc) pair: the same in-order sum as the fast path, but the positions whose filter look-up was
+// positive are looked up in the doc's row (binary search).  A pair whose query matches the doc at an EARLIER position
+// belongs to that position's pair and is dropped.  `plane(slot)` returns the doc's value in plane `slot`.
+struct ExactArgs {
+  const uint32_t* drow_off; const uint32_t* drow_term; const double* drow_val; const int32_t* qinfo;
+  unsigned long long* c_key; uint32_t* c_doc; int* c_cnt; int* n_nonpos; int qs, n_planes; int* tp_count;
+};
+template <class PlaneFn>
+__device__ __forceinline__ void exact_pair(const ExactArgs& ea, PlaneFn plane, int64_t d, double myval, const int4* __restrict__ rec,
+                                           uint32_t hits) {
+  const int4 hd = __ldg(rec);
+  const int64_t q = static_cast<uint32_t>(hd.x) >> 5;
+  const int pos = hd.x & 31;
+  const uint32_t r0 = __ldg(ea.drow_off + d);
+  const int row_n = static_cast<int>(__ldg(ea.drow_off + d + 1) - r0);
+  double acc = 0.0;
+  bool dup = false, matched = false;
+  for (int pp = 0; pp < ea.qs; ++pp) {
+    const uint32_t f = static_cast<uint32_t>(__ldg(reinterpret_cast<const int*>(rec + 1) + pp));
+    double v = (f & 127u) == SLOT_NONE ? 0.0 : plane(f & 127u);
+    if (pp == pos) v = myval;
+    if ((hits >> pp) & 1u) {
+      const int idx = row_find(ea.drow_term + r0, row_n, static_cast<uint32_t>(__ldg(ea.qinfo + q * ea.qs + pp)));
+      if (idx >= 0) { matched = true; if (pp < pos) dup = true; else v = __ldg(ea.drow_val + r0 + idx); }
+    }
+    acc = __dadd_rn(acc, v);
+  }
+  if (ea.tp_count && matched) atomicAdd(ea.tp_count, 1);       // diagnostics
+  if (!dup) member_emit(ea, q, acc, (static_cast<unsigned long long>(static_cast<uint32_t>(hd.w)) << 32) | static_cast<uint32_t>(hd.z), d);
+}
+// in place (a full queue): planes from the staged tile
+__device__ __noinline__ void member_exact(const ExactArgs ea, const double* pl_doc, int64_t d, double myval,
+                                          const int4* __restrict__ rec, uint32_t hits) {
+  exact_pair(ea, [&](uint32_t slot) { return pl_doc[slot * MJ_PSTRIDE]; }, d, myval, rec, hits);
+}
+
+// The set-aside pairs of a member-pass launch, one per thread, thousands in flight per SM: chains of dependent loads
+// that would idle a persistent CTA.  grid (x, member-pass CTAs); planes are read from global memory.
+struct MjDefer { uint32_t posting, rec, hits, tile; };
+__global__ void __launch_bounds__(256)
+bm25_member_exact_kernel(const Bm25Dev ix, const BatchScratch sc, int rs4) {
+  const MjDefer* defer = sc.defer + static_cast<size_t>(blockIdx.y) * MJ_DEF;
+  const int n = min(sc.def_cnt[blockIdx.y], MJ_DEF);
+  const ExactArgs ea{ix.drow_off, ix.drow_term, ix.drow_val, sc.qinfo, sc.c_key, sc.c_doc, sc.c_cnt, sc.n_nonpos, sc.qs, ix.n_planes,
+                     sc.stats_on ? sc.counters + 4 : nullptr};
+  for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
+    const MjDefer de = defer[k];
+    const int dl = __ldg(ix.tt_doc + de.posting);
+    const double* pt = ix.planes + static_cast<int64_t>(de.tile) * ix.n_planes * PLANE_TILE + plane_pos(static_cast<uint32_t>(dl));
+    exact_pair(ea, [&](uint32_t slot) { return __ldg(pt + slot * PLANE_TILE); }, static_cast<int64_t>(de.tile) * PLANE_TILE + dl,
+               __ldg(ix.tt_val + de.posting), sc.bt_rec + static_cast<size_t>(de.rec) * rs4, de.hits);
+  }
+}
+
+// grid: persistent CTAs over the units of tiles [tile_lo, tile_hi); a unit is 1/sub of a tile's sparse postings.
+// Per unit: stage the tile of all planes (bulk copy) and build the per-doc filters; then, `ch` postings at a time
+// (term-major: the postings of a term inside the tile form a run), count the (record, doc) pairs per run
+// (records of the term in the batch x docs of the run), scan, and give every thread an equal, contiguous range of
+// pairs in run-major / record-major order: the thread decodes a record into registers once and applies it to every
+// doc of the run.  The complete score of (query of the record, doc) is summed in query-token order: plane tokens from
+// the staged tile, the record's own token from the posting, +0.0 for every other sparse token of the query -- unless
+// the doc's filter says one of them may be present: those pairs are set aside with the positions in question and
+// queued for bm25_member_exact_kernel.  QS = tokens per query rounded up to 4 (<= 32).
+template <int QS>
 __global__ void __launch_bounds__(MJ_THREADS, 1)
-bm25_member_kernel(const Bm25Dev ix, const BatchScratch sc, int64_t tile_lo, int64_t tile_hi, int sub) {
+bm25_member_kernel(const Bm25Dev ix, const BatchScratch sc, int64_t tile_lo, int64_t tile_hi, int sub, int ch, int dbg) {
   extern __shared__ __align__(16) uint8_t mj_smem[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int P = ix.n_planes;
-  const double* pl = reinterpret_cast<const double*>(mj_smem);                     // [P][MJ_PSTRIDE]
-  MjShared& S = *reinterpret_cast<MjShared*>(mj_smem + static_cast<size_t>(P) * MJ_PSTRIDE * 8);
+  double* pl = reinterpret_cast<double*>(mj_smem);                                 // [P + 1][MJ_PSTRIDE]
+  uint32_t* bloom = reinterpret_cast<uint32_t*>(mj_smem + static_cast<size_t>(P + 1) * MJ_PSTRIDE * 8);   // [256][12]
+  uint32_t* pscan = bloom + PLANE_TILE * MJ_BLOOM_W;                               // [ch + 4] exclusive scan of the runs' pair counts
+  uint32_t* cbase = pscan + ch + 4;                                                // [ch] first record of a run's term (at its head)
+  uint32_t* pinfo = cbase + ch;                                                    // [ch] doc in tile | run length << 8 | head << 31
   MjDefer* defer = sc.defer + static_cast<size_t>(blockIdx.x) * MJ_DEF;
   __shared__ __align__(8) uint64_t fill_bar;
-  if (tid == 0) { ptx::mbar_init(&fill_bar, 1); ptx::fence_barrier_init(); }
+  __shared__ uint32_t wsum[32];
+  __shared__ int n_def_s;
+  if (tid == 0) { ptx::mbar_init(&fill_bar, 1); ptx::fence_barrier_init(); n_def_s = 0; }
+  for (int i = tid; i < MJ_PSTRIDE; i += MJ_THREADS) pl[static_cast<size_t>(P) * MJ_PSTRIDE + i] = 0.0;
   uint32_t fill_phase = 0;
-  const int dps = PLANE_TILE / sub;
   const int64_t units = (tile_hi - tile_lo) * sub;
-  const int rs4 = 1 + (sc.qs >> 2);
+  constexpr int RS4 = 1 + QS / 4;
+  const uint32_t zero_off = static_cast<uint32_t>(P) * MJ_PSTRIDE * 8u;
+  const ExactArgs ea{ix.drow_off, ix.drow_term, ix.drow_val, sc.qinfo, sc.c_key, sc.c_doc, sc.c_cnt, sc.n_nonpos, sc.qs, P, nullptr};
   for (int64_t u = blockIdx.x; u < units; u += gridDim.x) {
     const int64_t tile = tile_lo + u / sub;
     const int part = static_cast<int>(u % sub);
     __syncthreads();                                           // the previous unit is done; fill_bar is initialised
     if (tid == 0) {
-      S.n_def = 0;
       if (P > 0) {
         const uint32_t bytes = static_cast<uint32_t>(P) * PLANE_TILE * 8u;
         const char* src = reinterpret_cast<const char*>(ix.planes + tile * P * PLANE_TILE);
@@ -327,171 +395,161 @@ bm25_member_kernel(const Bm25Dev ix, const BatchScratch sc, int64_t tile_lo, int
                             PLANE_TILE * 8u, &fill_bar);
       }
     }
-    const int64_t d0 = tile * PLANE_TILE + static_cast<int64_t>(part) * dps;
-    const int nd = static_cast<int>(max(static_cast<int64_t>(0), min(static_cast<int64_t>(dps), ix.n_docs - d0)));
-    // row offsets and empty filters while the tile is on its way
-    for (int i = tid; i <= nd && nd > 0; i += MJ_THREADS) S.doff[i] = __ldg(ix.drow_off + d0 + i);
-    for (int i = tid; i < nd * MJ_BLOOM_W; i += MJ_THREADS) S.bloom[i] = 0u;
+    // the per-doc filters of the whole tile while the planes are on their way
+    for (int i = tid; i < PLANE_TILE * MJ_BLOOM_W; i += MJ_THREADS) bloom[i] = 0u;
     __syncthreads();
-    const uint32_t o_lo = nd > 0 ? S.doff[0] : 0u, o_hi = nd > 0 ? S.doff[nd] : 0u;
-    for (uint32_t i = o_lo + tid; i < o_hi; i += MJ_THREADS) {
-      const uint32_t t = __ldg(ix.drow_term + i);
-      const int dl = seg_of(S.doff, nd, i);
-      const uint32_t b1 = bloom_bit(t, BLOOM_MUL1), b2 = bloom_bit(t, BLOOM_MUL2);
-      atomicOr(&S.bloom[dl * MJ_BLOOM_W + (b1 >> 5)], 1u << (b1 & 31));
-      atomicOr(&S.bloom[dl * MJ_BLOOM_W + (b2 >> 5)], 1u << (b2 & 31));
+    const uint32_t t_lo = __ldg(ix.tt_off + tile), t_hi = __ldg(ix.tt_off + tile + 1);
+    for (uint32_t i = t_lo + tid; i < t_hi; i += MJ_THREADS) {
+      const uint32_t t = __ldg(ix.tt_term + i);
+      atomicOr(&bloom[__ldg(ix.tt_doc + i) * MJ_BLOOM_W + bloom_word(t)], bloom_mask(t));
     }
     if (P > 0) { ptx::mbar_wait(&fill_bar, fill_phase); fill_phase ^= 1u; }
     __syncthreads();
-    for (uint32_t c0 = o_lo; c0 < o_hi; c0 += MJ_CH) {
-      const int n_ch = static_cast<int>(min(static_cast<uint32_t>(MJ_CH), o_hi - c0));
-      // ---- counts of matching records per posting (thread t owns postings 4t .. 4t+3) and their exclusive scan
+    // this unit's slice of the tile's postings
+    const uint32_t o_lo = t_lo + static_cast<uint32_t>((static_cast<uint64_t>(t_hi - t_lo) * part) / sub);
+    const uint32_t o_hi = t_lo + static_cast<uint32_t>((static_cast<uint64_t>(t_hi - t_lo) * (part + 1)) / sub);
+    const int64_t doc_base = tile * PLANE_TILE;
+    for (uint32_t c0 = o_lo; c0 < o_hi; c0 += ch) {
+      const int n_ch = static_cast<int>(min(static_cast<uint32_t>(ch), o_hi - c0));
+      // ---- runs (thread t owns postings 4t .. 4t+3): head flags, record ranges
+      uint32_t rcnt[4];
+      {
+        uint32_t prev = 0xFFFFFFFFu;
+        if (tid * 4 < n_ch && tid > 0) prev = __ldg(ix.tt_term + c0 + tid * 4 - 1);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int i = tid * 4 + e;
+          rcnt[e] = 0u;
+          if (i < n_ch) {
+            const uint32_t t = __ldg(ix.tt_term + c0 + i);
+            uint32_t info = __ldg(ix.tt_doc + c0 + i);
+            if (t != prev) {                                   // first posting of a run (a chunk boundary starts one too)
+              const uint32_t b0 = __ldg(sc.bt_off + t);
+              rcnt[e] = __ldg(sc.bt_off + t + 1) - b0;
+              cbase[i] = b0;
+              info |= 0x80000000u;
+            }
+            pinfo[i] = info;
+            prev = t;
+          }
+        }
+      }
+      __syncthreads();
+      // ---- run lengths, pairs per run = records x docs, exclusive scan
       uint32_t cnt[4];
       uint32_t tsum = 0u;
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
         const int i = tid * 4 + e;
         cnt[e] = 0u;
-        if (i < n_ch) {
-          const uint32_t t = __ldg(ix.drow_term + c0 + i);
-          const uint32_t b0 = __ldg(sc.bt_off + t);
-          cnt[e] = __ldg(sc.bt_off + t + 1) - b0;
-          S.cbase[i] = b0;
-          S.pdoc[i] = static_cast<uint8_t>(seg_of(S.doff, nd, c0 + i));
+        if (i < n_ch && (pinfo[i] >> 31)) {
+          int len = 1;
+          while (i + len < n_ch && !(pinfo[i + len] >> 31)) ++len;
+          pinfo[i] |= static_cast<uint32_t>(len) << 8;
+          cnt[e] = rcnt[e] * static_cast<uint32_t>(len);
         }
         tsum += cnt[e];
       }
       uint32_t incl = tsum;
 #pragma unroll
       for (int o = 1; o < 32; o <<= 1) { const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
-      if (lane == 31) S.wsum[warp] = incl;
+      if (lane == 31) wsum[warp] = incl;
       __syncthreads();
       if (warp == 0) {
-        const uint32_t w = lane < MJ_THREADS / 32 ? S.wsum[lane] : 0u;
+        const uint32_t w = lane < MJ_THREADS / 32 ? wsum[lane] : 0u;
         uint32_t wi = w;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) { const uint32_t v = __shfl_up_sync(0xffffffffu, wi, o); if (lane >= o) wi += v; }
-        S.wsum[lane] = wi - w;
-        if (lane == 31) S.pscan[n_ch] = wi;
+        wsum[lane] = wi - w;
+        if (lane == 31) pscan[n_ch] = wi;
       }
       __syncthreads();
       {
-        uint32_t run = S.wsum[warp] + incl - tsum;
+        uint32_t run = wsum[warp] + incl - tsum;
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
           const int i = tid * 4 + e;
-          if (i < n_ch) S.pscan[i] = run;
+          if (i < n_ch) pscan[i] = run;
           run += cnt[e];
         }
       }
       __syncthreads();
       // ---- pairs: thread t scores pairs [t * R, (t + 1) * R) of the chunk
-      const uint32_t T = S.pscan[n_ch];
+      const uint32_t T = pscan[n_ch];
       const uint32_t R = (T + MJ_THREADS - 1) / MJ_THREADS;
       uint32_t j = tid * R;
       const uint32_t j_end = min(T, j + R);
-      if (j < j_end) {
-        int p = seg_of(S.pscan, n_ch, j);                      // pscan[p] <= j < pscan[p + 1]
-        uint32_t p_end = 0u;                                   // forces the posting state to be loaded
-        const double* pl_doc = pl;
-        const uint32_t* brow = S.bloom;
-        double myval = 0.0;
-        uint32_t rbase = 0u;
-        int64_t d = 0;
-        --p;
+      if (j < j_end && !(dbg & 4)) {
+        int i0 = seg_of(pscan, n_ch, j);                       // head of the run holding pair j
+        int len = static_cast<int>((pinfo[i0] >> 8) & 0x7FFFFFu);
+        uint32_t n_rec = (pscan[i0 + 1] - pscan[i0]) / static_cast<uint32_t>(len);
+        uint32_t k = (j - pscan[i0]) / static_cast<uint32_t>(len);                 // record of the run
+        int di = static_cast<int>(j - pscan[i0] - k * static_cast<uint32_t>(len));  // doc of the run
+        bool fresh = true;
+        // the decoded record: per token the byte offset of its plane row (zero row when it is no plane term), the byte
+        // offset of its filter word and the mask it must find there
+        uint32_t po[QS], bw[QS], bm[QS];
+        uint32_t own_bit = 0u, r = 0u;
+        int64_t q = 0;
+        unsigned long long bound = 0ull;
         for (; j < j_end; ++j) {
-          if (j >= p_end) {                                    // next posting with records (skips postings without)
-            do { ++p; p_end = S.pscan[p + 1]; } while (j >= p_end);
-            const int dl = S.pdoc[p];
-            d = d0 + dl;
-            pl_doc = pl + plane_pos(static_cast<uint32_t>(d) & (PLANE_TILE - 1));
-            brow = S.bloom + dl * MJ_BLOOM_W;
-            myval = __ldg(ix.drow_val + c0 + p);
-            rbase = S.cbase[p] - S.pscan[p];
-            if (p + 1 < n_ch) ptx::prefetch_l1(sc.bt_rec + static_cast<size_t>(S.cbase[p + 1]) * rs4);   // likely the next posting
+          if (fresh) {
+            fresh = false;
+            r = cbase[i0] + k;
+            const int4* rec = sc.bt_rec + static_cast<size_t>(r) * RS4;
+            const int4 hd = __ldg(rec);
+#pragma unroll
+            for (int p4 = 0; p4 < QS / 4; ++p4) {
+              const int4 c4 = __ldg(rec + 1 + p4);
+              const uint32_t ee[4] = {static_cast<uint32_t>(c4.x), static_cast<uint32_t>(c4.y), static_cast<uint32_t>(c4.z), static_cast<uint32_t>(c4.w)};
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const uint32_t f = ee[e], slot = f & 127u;
+                po[4 * p4 + e] = slot == SLOT_NONE ? zero_off : slot * (MJ_PSTRIDE * 8u);
+                bw[4 * p4 + e] = ((f >> 7) & 15u) * 4u;
+                bm[4 * p4 + e] = (1u << ((f >> 11) & 31u)) | (1u << ((f >> 16) & 31u)) | (1u << ((f >> 21) & 31u));
+              }
+            }
+            own_bit = 1u << (hd.x & 31);
+            q = static_cast<uint32_t>(hd.x) >> 5;
+            bound = (static_cast<unsigned long long>(static_cast<uint32_t>(hd.w)) << 32) | static_cast<uint32_t>(hd.z);
           }
-          const uint32_t r = rbase + j;
-          const int4* rec = sc.bt_rec + static_cast<size_t>(r) * rs4;
-          ptx::prefetch_l1(reinterpret_cast<const char*>(rec) + 128);   // the records of a term are contiguous
-          const int4 hd = __ldg(rec);
-          const int pos = hd.x & 31;
+          const int i = i0 + di;
+          const int dl = pinfo[i] & 0xFF;
+          const double myval = __ldg(ix.tt_val + c0 + i);
+          const char* pl_doc = reinterpret_cast<const char*>(pl + plane_pos(static_cast<uint32_t>(dl)));
+          const char* brow = reinterpret_cast<const char*>(bloom + dl * MJ_BLOOM_W);
           double acc = 0.0;
           uint32_t hits = 0u;
-          for (int p4 = 0; p4 < rs4 - 1; ++p4) {
-            const int4 c4 = __ldg(rec + 1 + p4);
-            const uint32_t ee[4] = {static_cast<uint32_t>(c4.x), static_cast<uint32_t>(c4.y), static_cast<uint32_t>(c4.z), static_cast<uint32_t>(c4.w)};
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const uint32_t f = ee[e];
-              const uint32_t slot = f & 127u, b1 = (f >> 7) & 511u, b2 = (f >> 16) & 511u;
-              double v = 0.0;                                  // adding +0.0 changes nothing (the sum is never -0.0)
-              if (slot != SLOT_NONE) v = pl_doc[slot * MJ_PSTRIDE];
-              if (p4 * 4 + e == pos) v = myval;
-              acc = __dadd_rn(acc, v);
-              hits |= ((brow[b1 >> 5] >> (b1 & 31)) & (brow[b2 >> 5] >> (b2 & 31)) & 1u) << (p4 * 4 + e);
+          for (int p = 0; p < QS; ++p) {
+            double v = *reinterpret_cast<const double*>(pl_doc + po[p]);   // +0.0 for tokens that are no plane terms
+            if (own_bit & (1u << p)) v = myval;
+            acc = __dadd_rn(acc, v);                                         // (the sum is never -0.0: adding +0.0 changes nothing)
+            if ((*reinterpret_cast<const uint32_t*>(brow + bw[p]) & bm[p]) == bm[p]) hits |= 1u << p;
+          }
+          if (hits == 0u) { if (!(dbg & 2)) member_emit(sc, q, acc, bound, doc_base + dl); else if (acc == 123.0) sc.c_cnt[0] = 1; }
+          else if (!(dbg & 1)) {
+            const int at = atomicAdd(&n_def_s, 1);
+            if (at < MJ_DEF) *reinterpret_cast<uint4*>(defer + at) = make_uint4(c0 + i, r, hits, static_cast<uint32_t>(tile));
+            else member_exact(ea, reinterpret_cast<const double*>(pl_doc), doc_base + dl, myval, sc.bt_rec + static_cast<size_t>(r) * RS4, hits);
+          }
+          if (++di == len) {                                   // next record of the run, or the next run that has records
+            di = 0;
+            fresh = true;
+            if (++k == n_rec && j + 1 < j_end) {
+              k = 0;
+              do { i0 += len; len = static_cast<int>((pinfo[i0] >> 8) & 0x7FFFFFu); } while (pscan[i0 + 1] == pscan[i0]);
+              n_rec = (pscan[i0 + 1] - pscan[i0]) / static_cast<uint32_t>(len);
             }
           }
-          if (hits != 0u) {
-            const int at = atomicAdd(&S.n_def, 1);
-            if (at < MJ_DEF) { defer[at].posting = c0 + p; defer[at].rec = r; defer[at].hits = hits; continue; }
-            // (a full list cannot happen with MJ_DEF pairs per unit; if it does the pair is finished in place below)
-            bool dup = false;
-            const int64_t q = static_cast<uint32_t>(hd.x) >> 5;
-            const uint32_t r0 = S.doff[S.pdoc[p]];
-            const int row_n = static_cast<int>(S.doff[S.pdoc[p] + 1] - r0);
-            acc = 0.0;
-            for (int pp = 0; pp < sc.qs; ++pp) {
-              const uint32_t f = static_cast<uint32_t>(reinterpret_cast<const int*>(rec + 1)[pp]);
-              const uint32_t slot = f & 127u;
-              double v = 0.0;
-              if (slot != SLOT_NONE) v = pl_doc[slot * MJ_PSTRIDE];
-              if (pp == pos) v = myval;
-              if ((hits >> pp) & 1u) {
-                const int idx = row_find(ix.drow_term + r0, row_n, static_cast<uint32_t>(__ldg(sc.qinfo + q * sc.qs + pp)));
-                if (idx >= 0) { if (pp < pos) dup = true; else v = __ldg(ix.drow_val + r0 + idx); }
-              }
-              acc = __dadd_rn(acc, v);
-            }
-            if (!dup) member_emit(sc, q, acc, (static_cast<unsigned long long>(static_cast<uint32_t>(hd.w)) << 32) | static_cast<uint32_t>(hd.z), d);
-            continue;
-          }
-          member_emit(sc, static_cast<uint32_t>(hd.x) >> 5, acc,
-                      (static_cast<unsigned long long>(static_cast<uint32_t>(hd.w)) << 32) | static_cast<uint32_t>(hd.z), d);
         }
       }
-      __syncthreads();                                         // pscan / cbase / pdoc are rewritten by the next chunk
-    }
-    // ---- the set-aside pairs of the unit: same sum, the positions in question looked up in the doc's row
-    const int n_def = min(S.n_def, MJ_DEF);
-    for (int i = tid; i < n_def; i += MJ_THREADS) {
-      const MjDefer de = defer[i];
-      const int dl = seg_of(S.doff, nd, de.posting);
-      const int64_t d = d0 + dl;
-      const double* pl_doc = pl + plane_pos(static_cast<uint32_t>(d) & (PLANE_TILE - 1));
-      const double myval = __ldg(ix.drow_val + de.posting);
-      const uint32_t r0 = S.doff[dl];
-      const int row_n = static_cast<int>(S.doff[dl + 1] - r0);
-      const int4* rec = sc.bt_rec + static_cast<size_t>(de.rec) * rs4;
-      const int4 hd = __ldg(rec);
-      const int64_t q = static_cast<uint32_t>(hd.x) >> 5;
-      const int pos = hd.x & 31;
-      double acc = 0.0;
-      bool dup = false;
-      for (int pp = 0; pp < sc.qs; ++pp) {
-        const uint32_t f = static_cast<uint32_t>(__ldg(reinterpret_cast<const int*>(rec + 1) + pp));
-        const uint32_t slot = f & 127u;
-        double v = 0.0;
-        if (slot != SLOT_NONE) v = pl_doc[slot * MJ_PSTRIDE];
-        if (pp == pos) v = myval;
-        if ((de.hits >> pp) & 1u) {
-          const int idx = row_find(ix.drow_term + r0, row_n, static_cast<uint32_t>(__ldg(sc.qinfo + q * sc.qs + pp)));
-          if (idx >= 0) { if (pp < pos) dup = true; else v = __ldg(ix.drow_val + r0 + idx); }
-        }
-        acc = __dadd_rn(acc, v);
-      }
-      if (!dup) member_emit(sc, q, acc, (static_cast<unsigned long long>(static_cast<uint32_t>(hd.w)) << 32) | static_cast<uint32_t>(hd.z), d);
+      __syncthreads();                                         // pscan / cbase / pinfo are rewritten by the next chunk
     }
   }
+  __syncthreads();
+  if (tid == 0) { sc.def_cnt[blockIdx.x] = n_def_s; atomicAdd(&sc.counters[0], n_def_s); }   // this CTA's queue: bm25_member_exact_kernel finishes it
 }
 
 // Between rounds: cut a query's candidate list back to its k best and publish the k-th key as the next bound.
@@ -929,13 +987,16 @@ bm25_flag_merge_kernel(const double* __restrict__ ps, const int64_t* __restrict_
   }
 }
 
-static thread_local int64_t g_stats[6] = {0, 0, 0, 0, 0, 0};   // queries, fallback queries, emissions, max emissions, rechecks, -
+static thread_local int64_t g_stats[8] = {0, 0, 0, 0, 0, 0, 0, 0};   // queries, fallback queries, emissions, max emissions, rechecks, set-aside pairs, of which matched, -
 
 static int batch_set_attrs() {
   static std::once_flag once;
   static cudaError_t err = cudaSuccess;
   std::call_once(once, [] {
-    err = cudaFuncSetAttribute(bm25_member_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_MAX);
+    err = cudaFuncSetAttribute(bm25_member_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_MAX);
+#define ARB_MJ(QS_) if (err == cudaSuccess) err = cudaFuncSetAttribute(bm25_member_kernel<QS_>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_MAX);
+    ARB_MJ(8) ARB_MJ(12) ARB_MJ(16) ARB_MJ(20) ARB_MJ(24) ARB_MJ(28) ARB_MJ(32)
+#undef ARB_MJ
     if (err == cudaSuccess)
       err = cudaFuncSetAttribute(bm25_screen_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_MAX);
     if (err == cudaSuccess)
@@ -960,8 +1021,9 @@ static int batch_chunk(const Bm25Dev& ix, const int32_t* d_terms, int64_t nq, in
   sc.qs = (mq + 3) & ~3;
   sc.qd_stride = (mq + 7) & ~7;
   AsyncBuf b_defer, b_rq;
-  ARB_CUDA(b_defer.alloc(static_cast<size_t>(sms) * MJ_DEF * sizeof(MjDefer), st));
+  ARB_CUDA(b_defer.alloc(static_cast<size_t>(sms) * MJ_DEF * sizeof(MjDefer) + static_cast<size_t>(sms) * 4, st));
   sc.defer = b_defer.as<MjDefer>();
+  sc.def_cnt = reinterpret_cast<int*>(sc.defer + static_cast<size_t>(sms) * MJ_DEF);
   AsyncBuf b_qinfo, b_bt, b_pair, b_ckey, b_cdoc, b_akey, b_adoc, b_i32, b_u64, b_u8, b_ekey, b_edoc, b_hist;
   const size_t nt = static_cast<size_t>(std::max<int64_t>(ix.n_terms, 1));
   ARB_CUDA(b_qinfo.alloc(static_cast<size_t>(nq) * sc.qs * 4, st));
@@ -971,7 +1033,7 @@ static int batch_chunk(const Bm25Dev& ix, const int32_t* d_terms, int64_t nq, in
   ARB_CUDA(b_cdoc.alloc(static_cast<size_t>(nq) * C_CAP * 4, st));
   ARB_CUDA(b_akey.alloc(static_cast<size_t>(nq) * k * 8, st));
   ARB_CUDA(b_adoc.alloc(static_cast<size_t>(nq) * k * 4, st));
-  ARB_CUDA(b_i32.alloc((static_cast<size_t>(nq) * 5 + 4 + H3_MAX) * 4, st));        // c_cnt | n_nonpos | e_cnt | counters | a_cnt | flag_list | h3_list
+  ARB_CUDA(b_i32.alloc((static_cast<size_t>(nq) * 5 + 8 + H3_MAX) * 4, st));        // c_cnt | n_nonpos | e_cnt | counters | a_cnt | flag_list | h3_list
   ARB_CUDA(b_u64.alloc(static_cast<size_t>(nq) * 2 * 8, st));                       // gthr | thr
   ARB_CUDA(b_u8.alloc(static_cast<size_t>(nq) * (sc.qd_stride + 2) + 16, st));      // qd | state | ovf
   sc.qinfo = b_qinfo.as<int32_t>();
@@ -987,7 +1049,8 @@ static int batch_chunk(const Bm25Dev& ix, const int32_t* d_terms, int64_t nq, in
   sc.n_nonpos = sc.c_cnt + nq;
   sc.e_cnt = sc.n_nonpos + nq;
   sc.counters = sc.e_cnt + nq;
-  sc.a_cnt = sc.counters + 4;
+  sc.a_cnt = sc.counters + 8;
+  sc.stats_on = std::getenv("ARB_BM25_STATS") ? 1 : 0;
   sc.flag_list = sc.a_cnt + nq;
   sc.h3_list = sc.flag_list + nq;
   sc.gthr = b_u64.as<unsigned long long>();
@@ -1006,7 +1069,7 @@ static int batch_chunk(const Bm25Dev& ix, const int32_t* d_terms, int64_t nq, in
     sc.hist = b_hist.as<uint32_t>();
   }
   ARB_CUDA(cudaMemsetAsync(sc.bt_cur, 0, nt * 4, st));
-  ARB_CUDA(cudaMemsetAsync(sc.c_cnt, 0, (static_cast<size_t>(nq) * 3 + 4) * 4, st));   // c_cnt, n_nonpos, e_cnt, counters
+  ARB_CUDA(cudaMemsetAsync(sc.c_cnt, 0, (static_cast<size_t>(nq) * 3 + 8) * 4, st));   // c_cnt, n_nonpos, e_cnt, counters
   ARB_CUDA(cudaMemsetAsync(sc.ovf, 0, static_cast<size_t>(nq), st));
 
   {
@@ -1024,8 +1087,10 @@ static int batch_chunk(const Bm25Dev& ix, const int32_t* d_terms, int64_t nq, in
     else if (ix.n_tiles < 256) cuts = {4, 16, 64};
     else cuts = {1, 4, 16, 32, 64};
     if (const char* v = std::getenv("ARB_BM25_ROUNDS")) { if (atoi(v) == 1) cuts = {64}; }
-    const size_t mj_smem = static_cast<size_t>(ix.n_planes) * MJ_PSTRIDE * 8 + sizeof(MjShared);
+    const int mj_ch = static_cast<int>(std::min<size_t>(MJ_CH_MAX, ((SMEM_MAX - mj_fixed_bytes(ix.n_planes)) / 12 - 4) & ~size_t(3)));
+    const size_t mj_smem = mj_fixed_bytes(ix.n_planes) + static_cast<size_t>(mj_ch + 4) * 12;
     int64_t prev = 0;
+    const int dbg = std::getenv("ARB_BM25_DEBUG") ? atoi(std::getenv("ARB_BM25_DEBUG")) : 0;   // timing experiments only (wrong results)
     for (size_t r = 0; r < cuts.size(); ++r) {
       const int64_t hi = cuts[r] == 64 ? ix.n_tiles : std::max(prev, (ix.n_tiles * cuts[r] + 63) / 64);
       const bool last = r + 1 == cuts.size();
@@ -1033,7 +1098,14 @@ static int batch_chunk(const Bm25Dev& ix, const int32_t* d_terms, int64_t nq, in
         int sub = 1;
         while (sub < 8 && (hi - prev) * sub < sms) sub <<= 1;
         const unsigned grid = static_cast<unsigned>(std::min<int64_t>((hi - prev) * sub, sms));
-        bm25_member_kernel<<<grid, MJ_THREADS, mj_smem, st>>>(ix, sc, prev, hi, sub);
+        switch (sc.qs) {
+#define ARB_MJ(QS_) case QS_: bm25_member_kernel<QS_><<<grid, MJ_THREADS, mj_smem, st>>>(ix, sc, prev, hi, sub, mj_ch, dbg); break;
+          ARB_MJ(4) ARB_MJ(8) ARB_MJ(12) ARB_MJ(16) ARB_MJ(20) ARB_MJ(24) ARB_MJ(28) ARB_MJ(32)
+#undef ARB_MJ
+          default: set_error("bm25 batch: more than 32 tokens per query"); return ARB_ELIMIT;
+        }
+        ARB_LAUNCH_OK();
+        bm25_member_exact_kernel<<<dim3(32, grid), 256, 0, st>>>(ix, sc, 1 + sc.qs / 4);
         ARB_LAUNCH_OK();
       }
       if (hi > prev || last) {
@@ -1106,12 +1178,14 @@ static int batch_chunk(const Bm25Dev& ix, const int32_t* d_terms, int64_t nq, in
     }
   }
   if (std::getenv("ARB_BM25_STATS")) {                           // diagnostics only: synchronises
-    std::vector<int> h(static_cast<size_t>(nq) + 4);
+    std::vector<int> h(static_cast<size_t>(nq) + 8);
     ARB_CUDA(cudaMemcpyAsync(h.data(), sc.e_cnt, h.size() * 4, cudaMemcpyDeviceToHost, st));
     ARB_CUDA(cudaStreamSynchronize(st));
     g_stats[0] += nq;
     g_stats[1] += h[nq + 1];
     g_stats[4] += h[nq + 3];
+    g_stats[5] += h[nq + 0];
+    g_stats[6] += h[nq + 4];
     for (int64_t i = 0; i < nq; ++i) { g_stats[2] += h[i]; g_stats[3] = std::max<int64_t>(g_stats[3], h[i]); }
   }
   return ARB_OK;
@@ -1134,7 +1208,7 @@ int bm25_batch_search(const Bm25Dev& ix, const int32_t* d_terms, int64_t nq, int
 
 }  // namespace arb
 
-extern "C" int arb_bm25_batch_stats(int64_t out[6], int reset) {
-  for (int i = 0; i < 6; ++i) { if (out) out[i] = arb::g_stats[i]; if (reset) arb::g_stats[i] = 0; }
+extern "C" int arb_bm25_batch_stats(int64_t out[8], int reset) {
+  for (int i = 0; i < 8; ++i) { if (out) out[i] = arb::g_stats[i]; if (reset) arb::g_stats[i] = 0; }
   return ARB_OK;
 }

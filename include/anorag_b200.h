@@ -195,8 +195,9 @@ ARB_API int arb_bm25_scores(const arb_bm25* bm, const int32_t* q_terms, int64_t 
 /* Diagnostics of the batched pipeline, collected only while the environment variable ARB_BM25_STATS is
  * set (each search then synchronises): [0] queries scored, [1] queries re-scored by the per-query
  * fallback, [2] screening-pass emissions in total, [3] most emissions for one query, [4] (query, tile) pairs the
- * screening pass recomputed in fp64, [5] reserved.  Per calling thread. */
-ARB_API int arb_bm25_batch_stats(int64_t out[6], int reset);
+ * screening pass recomputed in fp64, [5] (record, doc) pairs the member pass set aside for the exact kernel, [6] those
+ * of them that did match another sparse token, [7] reserved.  Per calling thread. */
+ARB_API int arb_bm25_batch_stats(int64_t out[8], int reset);
 
 /* FieldWeightedBM25.get_scores combination (utils/bm25_search.py:117-145):
  * out[i] = ((0.0 + w[0]*s[0][i]) + w[1]*s[1][i]) + ... in fp64, fields in the given order; then, if
