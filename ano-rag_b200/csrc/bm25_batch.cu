@@ -71,8 +71,8 @@ struct BatchScratch {
   // ---- query-term index of the batch
   int32_t* qinfo;              // [nq, qs] per query token: >= 0 sparse term id, -1 contributes nothing, <= -2 plane slot (-2 - slot)
   int qs;                      // tokens per query rounded up to a multiple of 4 (16-byte rows)
-  uint32_t* bt_off;            // [n_terms + 1] pairs of term t: bt_pair[bt_off[t] .. bt_off[t + 1])
-  uint32_t* bt_cur;            // [n_terms] occurrence counts, then fill cursors
+  uint2* bt_ent;               // [n_terms] {first record, number of records} of a term in bt_rec (count 0: not in the batch)
+  uint32_t* bt_cur;            // [n_terms] 0 = unclaimed, then 1 + records placed so far
   int4* bt_rec;                // [sparse tokens of the batch] records of 1 + qs/4 int4, grouped by term (bm25_bt_fill_kernel)
   uint32_t* rec_of;            // [nq * qs] record of a sparse query token, else 0xFFFFFFFF
   MjDefer* defer;
@@ -97,7 +97,7 @@ struct BatchScratch {
   int* e_cnt;                  // [nq]
   int* flag_list;              // [nq]
   int* counters;               // [0] set-aside pairs, [1] flagged queries, [2] histogram queries, [3] queued rechecks, [4] set-aside pairs
-                               // that did match another sparse token (diagnostics)
+                               // that did match another sparse token (diagnostics), [5] records handed out
   int stats_on;
   uint2* rq;                   // [RQ_CAP] (query, tile) pairs the screening pass wants recomputed in fp64
   int* h3_list;                // [H3_MAX]
@@ -170,7 +170,7 @@ bm25_qclassify_kernel(const Bm25Dev ix, const int32_t* __restrict__ q_terms, int
     if (t >= 0 && t < ix.n_terms && __ldg(ix.idf + t) != 0.0) {        // (idf.get(q) or 0) == 0 adds +0.0: a no-op
       const int ps = ix.n_planes > 0 ? __ldg(ix.plane_slot + t) : -1;
       if (ps >= 0) { code = -2 - ps; sc.qd[q * sc.qd_stride + np++] = static_cast<uint8_t>(ps); }
-      else { code = t; atomicAdd(sc.bt_cur + t, 1u); }
+      else { code = t; atomicAdd(&sc.bt_ent[t].y, 1u); }
     }
     sc.qinfo[q * sc.qs + p] = code;
   }
@@ -178,30 +178,16 @@ bm25_qclassify_kernel(const Bm25Dev ix, const int32_t* __restrict__ q_terms, int
   sc.gthr[q] = f64_key(0.0);                                            // only positive scores are candidates
 }
 
-// exclusive scan of the per-term counts (one CTA: the table is small and L2 resident); the counts become cursors
-__global__ void __launch_bounds__(1024)
-bm25_bt_scan_kernel(int64_t n_terms, const BatchScratch sc) {
-  __shared__ uint32_t warp_tot[32];
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int64_t chunk = (n_terms + 1023) / 1024;
-  const int64_t lo = min(n_terms, static_cast<int64_t>(tid) * chunk), hi = min(n_terms, lo + chunk);
-  uint32_t sum = 0;
-  for (int64_t i = lo; i < hi; ++i) sum += sc.bt_cur[i];
-  uint32_t incl = sum;
-#pragma unroll
-  for (int o = 1; o < 32; o <<= 1) { const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
-  if (lane == 31) warp_tot[warp] = incl;
-  __syncthreads();
-  if (warp == 0) {
-    uint32_t w = warp_tot[lane], wi = w;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) { const uint32_t v = __shfl_up_sync(0xffffffffu, wi, o); if (lane >= o) wi += v; }
-    warp_tot[lane] = wi - w;
-  }
-  __syncthreads();
-  uint32_t run = warp_tot[warp] + incl - sum;
-  for (int64_t i = lo; i < hi; ++i) { const uint32_t c = sc.bt_cur[i]; sc.bt_off[i] = run; sc.bt_cur[i] = 0u; run += c; }
-  if (tid == 1023) sc.bt_off[n_terms] = run;
+// The records of a term are contiguous; their place is handed out by whichever token of the term gets there first
+// (no pass over the vocabulary: only its per-batch zeroing is O(n_terms)).
+__global__ void __launch_bounds__(256)
+bm25_bt_alloc_kernel(int64_t n, const BatchScratch sc) {
+  const int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  if (i >= n) return;
+  const int code = sc.qinfo[i];
+  if (code < 0) return;
+  if (atomicExch(sc.bt_cur + code, 1u) == 0u)
+    sc.bt_ent[code].x = static_cast<uint32_t>(atomicAdd(&sc.counters[5], static_cast<int>(sc.bt_ent[code].y)));
 }
 
 // One record per sparse query token, grouped by term: everything the member pass needs to score the token's query
@@ -218,7 +204,7 @@ bm25_bt_fill_kernel(int64_t n, const BatchScratch sc) {
   const int code = sc.qinfo[i];
   if (code < 0) { sc.rec_of[i] = 0xFFFFFFFFu; return; }
   const int64_t q = i / sc.qs;
-  const uint32_t at = __ldg(sc.bt_off + code) + atomicAdd(sc.bt_cur + code, 1u);
+  const uint32_t at = sc.bt_ent[code].x + atomicAdd(sc.bt_cur + code, 1u) - 1u;
   sc.rec_of[i] = at;
   const int rs4 = 1 + (sc.qs >> 2);
   int4* rec = sc.bt_rec + static_cast<size_t>(at) * rs4;
@@ -250,7 +236,7 @@ bm25_bt_fill_kernel(int64_t n, const BatchScratch sc) {
 // ----------------------------------------------------------------------------
 // 1. member pass
 // ----------------------------------------------------------------------------
-constexpr int MJ_THREADS = 512;
+constexpr int MJ_THREADS = 640;
 constexpr int MJ_CH_MAX = 2048;                      // postings joined per chunk (fewer when 96 planes fill shared memory)
 constexpr int MJ_DEF = 65536;                        // set-aside pairs per CTA and launch, in global scratch (more: finished in place)
 constexpr int MJ_PSTRIDE = PLANE_TILE + 2;           // padded plane rows: threads of a warp mostly read the SAME doc of
@@ -424,9 +410,9 @@ bm25_member_kernel(const Bm25Dev ix, const BatchScratch sc, int64_t tile_lo, int
             const uint32_t t = __ldg(ix.tt_term + c0 + i);
             uint32_t info = __ldg(ix.tt_doc + c0 + i);
             if (t != prev) {                                   // first posting of a run (a chunk boundary starts one too)
-              const uint32_t b0 = __ldg(sc.bt_off + t);
-              rcnt[e] = __ldg(sc.bt_off + t + 1) - b0;
-              cbase[i] = b0;
+              const uint2 be = __ldg(sc.bt_ent + t);
+              rcnt[e] = be.y;
+              cbase[i] = be.x;
               info |= 0x80000000u;
             }
             pinfo[i] = info;
@@ -489,7 +475,7 @@ bm25_member_kernel(const Bm25Dev ix, const BatchScratch sc, int64_t tile_lo, int
         // the decoded record: per token the byte offset of its plane row (zero row when it is no plane term), the byte
         // offset of its filter word and the mask it must find there
         uint32_t po[QS], bw[QS], bm[QS];
-        uint32_t own_bit = 0u, r = 0u;
+        uint32_t own_bit = 0u, plane_bits = 0u, sparse_bits = 0u, r = 0u;
         int64_t q = 0;
         unsigned long long bound = 0ull;
         for (; j < j_end; ++j) {
@@ -498,6 +484,8 @@ bm25_member_kernel(const Bm25Dev ix, const BatchScratch sc, int64_t tile_lo, int
             r = cbase[i0] + k;
             const int4* rec = sc.bt_rec + static_cast<size_t>(r) * RS4;
             const int4 hd = __ldg(rec);
+            ptx::prefetch_l1(rec + RS4);                       // the next record of the run (records of a term are contiguous)
+            plane_bits = 0u; sparse_bits = 0u;
 #pragma unroll
             for (int p4 = 0; p4 < QS / 4; ++p4) {
               const int4 c4 = __ldg(rec + 1 + p4);
@@ -508,6 +496,8 @@ bm25_member_kernel(const Bm25Dev ix, const BatchScratch sc, int64_t tile_lo, int
                 po[4 * p4 + e] = slot == SLOT_NONE ? zero_off : slot * (MJ_PSTRIDE * 8u);
                 bw[4 * p4 + e] = ((f >> 7) & 15u) * 4u;
                 bm[4 * p4 + e] = (1u << ((f >> 11) & 31u)) | (1u << ((f >> 16) & 31u)) | (1u << ((f >> 21) & 31u));
+                if (slot != SLOT_NONE) plane_bits |= 1u << (4 * p4 + e);
+                if (((f >> 11) & 31u) != 31u) sparse_bits |= 1u << (4 * p4 + e);
               }
             }
             own_bit = 1u << (hd.x & 31);
@@ -523,10 +513,12 @@ bm25_member_kernel(const Bm25Dev ix, const BatchScratch sc, int64_t tile_lo, int
           uint32_t hits = 0u;
 #pragma unroll
           for (int p = 0; p < QS; ++p) {
-            double v = *reinterpret_cast<const double*>(pl_doc + po[p]);   // +0.0 for tokens that are no plane terms
+            // only real plane / sparse tokens touch shared memory: random addresses across a warp, fewer lanes = fewer bank conflicts
+            double v = 0.0;
+            if (plane_bits & (1u << p)) v = *reinterpret_cast<const double*>(pl_doc + po[p]);
             if (own_bit & (1u << p)) v = myval;
             acc = __dadd_rn(acc, v);                                         // (the sum is never -0.0: adding +0.0 changes nothing)
-            if ((*reinterpret_cast<const uint32_t*>(brow + bw[p]) & bm[p]) == bm[p]) hits |= 1u << p;
+            if ((sparse_bits & (1u << p)) && (*reinterpret_cast<const uint32_t*>(brow + bw[p]) & bm[p]) == bm[p]) hits |= 1u << p;
           }
           if (hits == 0u) { if (!(dbg & 2)) member_emit(sc, q, acc, bound, doc_base + dl); else if (acc == 123.0) sc.c_cnt[0] = 1; }
           else if (!(dbg & 1)) {
@@ -553,12 +545,20 @@ bm25_member_kernel(const Bm25Dev ix, const BatchScratch sc, int64_t tile_lo, int
 }
 
 // Between rounds: cut a query's candidate list back to its k best and publish the k-th key as the next bound.
-// After the last round: list A, the screening threshold and the query's state.  One CTA per query.
+// After the last round: list A (sorted), the screening threshold and the query's state.  One CTA per query.
+// The k best are SELECTED, not sorted out of the whole list: a 4096-bin histogram of the scores (128 bins per octave)
+// finds the bin holding the k-th score; everything above it is in, and only that bin's entries are sorted.
+__device__ __forceinline__ int key_bin(unsigned long long key) {          // same bins as h3_bin()
+  const long long t = static_cast<long long>(key >> 45) - static_cast<long long>(H3_BASE);
+  return static_cast<int>(t < 0 ? 0 : (t > H3_BINS - 1 ? H3_BINS - 1 : t));
+}
+constexpr int CP_SLOTS = C_CAP + 256;
+constexpr int CP_SMEM = CP_SLOTS * 12 + H3_BINS * 4;
 __global__ void __launch_bounds__(256)
 bm25_compact_kernel(int64_t nq, int k, int last, const BatchScratch sc) {
-  extern __shared__ __align__(16) uint8_t cp_smem[];             // C_CAP x 12 B
+  extern __shared__ __align__(16) uint8_t cp_smem[];
   const int64_t q = blockIdx.x;
-  const int tid = threadIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int raw = sc.c_cnt[q];
   const bool ovf = sc.ovf[q] != 0 || raw > C_CAP;
   auto publish = [&](unsigned long long bound) {              // the next round reads the bound from the query's records
@@ -579,21 +579,77 @@ bm25_compact_kernel(int64_t nq, int k, int last, const BatchScratch sc) {
   }
   const int n = ovf ? 0 : raw;
   unsigned long long* key = reinterpret_cast<unsigned long long*>(cp_smem);
-  uint32_t* doc = reinterpret_cast<uint32_t*>(cp_smem + static_cast<size_t>(C_CAP) * 8);
-  int n2 = 2;
-  while (n2 < n) n2 <<= 1;
-  for (int i = tid; i < n2; i += blockDim.x) {
-    key[i] = i < n ? sc.c_key[q * C_CAP + i] : 0ull;
-    doc[i] = i < n ? sc.c_doc[q * C_CAP + i] : 0xFFFFFFFFu;
+  uint32_t* doc = reinterpret_cast<uint32_t*>(cp_smem + static_cast<size_t>(CP_SLOTS) * 8);
+  uint32_t* hist = doc + CP_SLOTS;
+  __shared__ int s_bin, s_hi, s_nhi, s_nb;
+  __shared__ uint32_t s_w[8];
+  int cnt = min(n, k);
+  if (n > k) {
+    for (int i = tid; i < H3_BINS; i += 256) hist[i] = 0u;
+    if (tid == 0) { s_nhi = 0; s_nb = 0; }
+    __syncthreads();
+    for (int i = tid; i < n; i += 256) atomicAdd(&hist[key_bin(sc.c_key[q * C_CAP + i])], 1u);
+    __syncthreads();
+    // thread t owns the 16 bins [4096 - 16 (t + 1), 4096 - 16 t): counts from the top
+    uint32_t mine = 0u;
+    const int b_top = H3_BINS - 16 * tid;
+#pragma unroll
+    for (int j = 1; j <= 16; ++j) mine += hist[b_top - j];
+    uint32_t incl = mine;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
+    if (lane == 31) s_w[warp] = incl;
+    __syncthreads();
+    uint32_t above = incl - mine;
+    for (int w = 0; w < warp; ++w) above += s_w[w];
+    if (above < static_cast<uint32_t>(k) && above + mine >= static_cast<uint32_t>(k)) {   // the k-th score lies in one of my bins
+      int b = b_top;
+      uint32_t c = above;
+      do { --b; c += hist[b]; } while (c < static_cast<uint32_t>(k));
+      s_bin = b; s_hi = static_cast<int>(c - hist[b]);
+    }
+    __syncthreads();
+    const int B = s_bin, c_hi = s_hi;                            // c_hi < k entries lie in bins above B
+    for (int i = tid; i < n; i += 256) {
+      const unsigned long long kk = sc.c_key[q * C_CAP + i];
+      const int b = key_bin(kk);
+      if (b > B) { const int at = atomicAdd(&s_nhi, 1); key[at] = kk; doc[at] = sc.c_doc[q * C_CAP + i]; }
+      else if (b == B) { const int at = c_hi + atomicAdd(&s_nb, 1); key[at] = kk; doc[at] = sc.c_doc[q * C_CAP + i]; }
+    }
+    __syncthreads();
+    const int nb = s_nb;
+    if (nb > k - c_hi) {                                       // more than needed in bin B: the best of them by (key desc, doc asc)
+      int n2 = 2;
+      while (n2 < nb) n2 <<= 1;
+      for (int i = nb + tid; i < n2; i += 256) { key[c_hi + i] = 0ull; doc[c_hi + i] = 0xFFFFFFFFu; }
+      cta_sort_desc(key + c_hi, doc + c_hi, n2);
+    }
+  } else {
+    for (int i = tid; i < n; i += 256) { key[i] = sc.c_key[q * C_CAP + i]; doc[i] = sc.c_doc[q * C_CAP + i]; }
+    __syncthreads();
   }
-  cta_sort_desc(key, doc, n2);
-  const int cnt = min(n, k);
+  // key/doc[0, cnt) now hold the cnt best entries (unordered above bin B)
   if (!last) {
-    for (int i = tid; i < cnt; i += blockDim.x) { sc.c_key[q * C_CAP + i] = key[i]; sc.c_doc[q * C_CAP + i] = doc[i]; }
-    if (tid == 0) { sc.c_cnt[q] = cnt; if (cnt >= k) sc.gthr[q] = key[k - 1]; }
-    if (cnt >= k) publish(key[k - 1]);
+    // the k-th key = the smallest selected one
+    unsigned long long kmin = ~0ull;
+    for (int i = tid; i < cnt; i += 256) kmin = min(kmin, key[i]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) kmin = min(kmin, __shfl_xor_sync(0xffffffffu, kmin, o));
+    __shared__ unsigned long long s_min[8];
+    if (lane == 0) s_min[warp] = kmin;
+    __syncthreads();
+    kmin = s_min[0];
+    for (int w = 1; w < 8; ++w) kmin = min(kmin, s_min[w]);
+    for (int i = tid; i < cnt; i += 256) { sc.c_key[q * C_CAP + i] = key[i]; sc.c_doc[q * C_CAP + i] = doc[i]; }
+    if (tid == 0) { sc.c_cnt[q] = cnt; if (cnt >= k) sc.gthr[q] = kmin; }
+    if (cnt >= k) publish(kmin);
     return;
   }
+  int n2 = 2;
+  while (n2 < cnt) n2 <<= 1;
+  __syncthreads();
+  for (int i = cnt + tid; i < n2; i += 256) { key[i] = 0ull; doc[i] = 0xFFFFFFFFu; }
+  cta_sort_desc(key, doc, n2);
   for (int i = tid; i < k; i += blockDim.x) {
     sc.a_key[q * k + i] = i < cnt ? key[i] : 0ull;
     sc.a_doc[q * k + i] = i < cnt ? doc[i] : 0xFFFFFFFFu;
@@ -1000,7 +1056,7 @@ static int batch_set_attrs() {
     if (err == cudaSuccess)
       err = cudaFuncSetAttribute(bm25_screen_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_MAX);
     if (err == cudaSuccess)
-      err = cudaFuncSetAttribute(bm25_compact_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, C_CAP * 12);
+      err = cudaFuncSetAttribute(bm25_compact_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CP_SMEM);
     if (err == cudaSuccess)
       err = cudaFuncSetAttribute(bm25_plane_h3_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_PLANES * PLANE_TILE * 8);
     if (err == cudaSuccess)
@@ -1027,7 +1083,7 @@ static int batch_chunk(const Bm25Dev& ix, const int32_t* d_terms, int64_t nq, in
   AsyncBuf b_qinfo, b_bt, b_pair, b_ckey, b_cdoc, b_akey, b_adoc, b_i32, b_u64, b_u8, b_ekey, b_edoc, b_hist;
   const size_t nt = static_cast<size_t>(std::max<int64_t>(ix.n_terms, 1));
   ARB_CUDA(b_qinfo.alloc(static_cast<size_t>(nq) * sc.qs * 4, st));
-  ARB_CUDA(b_bt.alloc((2 * nt + 1) * 4, st));                                       // bt_cur | bt_off
+  ARB_CUDA(b_bt.alloc(3 * nt * 4, st));                                             // bt_ent | bt_cur
   ARB_CUDA(b_pair.alloc(static_cast<size_t>(nq) * sc.qs * (16 + sc.qs * 4) + static_cast<size_t>(nq) * sc.qs * 4, st));   // bt_rec | rec_of
   ARB_CUDA(b_ckey.alloc(static_cast<size_t>(nq) * C_CAP * 8, st));
   ARB_CUDA(b_cdoc.alloc(static_cast<size_t>(nq) * C_CAP * 4, st));
@@ -1037,8 +1093,8 @@ static int batch_chunk(const Bm25Dev& ix, const int32_t* d_terms, int64_t nq, in
   ARB_CUDA(b_u64.alloc(static_cast<size_t>(nq) * 2 * 8, st));                       // gthr | thr
   ARB_CUDA(b_u8.alloc(static_cast<size_t>(nq) * (sc.qd_stride + 2) + 16, st));      // qd | state | ovf
   sc.qinfo = b_qinfo.as<int32_t>();
-  sc.bt_cur = b_bt.as<uint32_t>();
-  sc.bt_off = sc.bt_cur + nt;
+  sc.bt_ent = b_bt.as<uint2>();
+  sc.bt_cur = b_bt.as<uint32_t>() + 2 * nt;
   sc.bt_rec = b_pair.as<int4>();
   sc.rec_of = reinterpret_cast<uint32_t*>(reinterpret_cast<uint8_t*>(b_pair.p) + static_cast<size_t>(nq) * sc.qs * (16 + sc.qs * 4));
   sc.c_key = b_ckey.as<unsigned long long>();
@@ -1068,7 +1124,7 @@ static int batch_chunk(const Bm25Dev& ix, const int32_t* d_terms, int64_t nq, in
     sc.e_doc = b_edoc.as<uint32_t>();
     sc.hist = b_hist.as<uint32_t>();
   }
-  ARB_CUDA(cudaMemsetAsync(sc.bt_cur, 0, nt * 4, st));
+  ARB_CUDA(cudaMemsetAsync(sc.bt_ent, 0, 3 * nt * 4, st));
   ARB_CUDA(cudaMemsetAsync(sc.c_cnt, 0, (static_cast<size_t>(nq) * 3 + 8) * 4, st));   // c_cnt, n_nonpos, e_cnt, counters
   ARB_CUDA(cudaMemsetAsync(sc.ovf, 0, static_cast<size_t>(nq), st));
 
@@ -1077,7 +1133,7 @@ static int batch_chunk(const Bm25Dev& ix, const int32_t* d_terms, int64_t nq, in
     // ---- 0. query-term index
     bm25_qclassify_kernel<<<static_cast<unsigned>((nq + 127) / 128), 128, 0, st>>>(ix, d_terms, mq, nq, sc);
     ARB_LAUNCH_OK();
-    bm25_bt_scan_kernel<<<1, 1024, 0, st>>>(ix.n_terms, sc);
+    bm25_bt_alloc_kernel<<<static_cast<unsigned>((nq * sc.qs + 255) / 256), 256, 0, st>>>(nq * sc.qs, sc);
     ARB_LAUNCH_OK();
     bm25_bt_fill_kernel<<<static_cast<unsigned>((nq * sc.qs + 255) / 256), 256, 0, st>>>(nq * sc.qs, sc);
     ARB_LAUNCH_OK();
@@ -1109,7 +1165,7 @@ static int batch_chunk(const Bm25Dev& ix, const int32_t* d_terms, int64_t nq, in
         ARB_LAUNCH_OK();
       }
       if (hi > prev || last) {
-        bm25_compact_kernel<<<static_cast<unsigned>(nq), 256, C_CAP * 12, st>>>(nq, k, last ? 1 : 0, sc);
+        bm25_compact_kernel<<<static_cast<unsigned>(nq), 256, CP_SMEM, st>>>(nq, k, last ? 1 : 0, sc);
         ARB_LAUNCH_OK();
       }
       prev = hi;
