@@ -152,7 +152,7 @@ __global__ void bm25_tile_key_kernel(const uint32_t* __restrict__ doc_key, int64
 __global__ void bm25_tt_fill_kernel(const uint32_t* __restrict__ sorted_val, int64_t n_sp, const int64_t* __restrict__ term_ptr,
                                     int64_t n_terms, const int32_t* __restrict__ doc, const int32_t* __restrict__ gcode,
                                     const double* __restrict__ idf, const double* __restrict__ gtab, uint32_t* __restrict__ tt_term,
-                                    uint8_t* __restrict__ tt_doc, double* __restrict__ tt_val) {
+                                    uint8_t* __restrict__ tt_doc, double* __restrict__ tt_val, uint32_t* __restrict__ tt_bloom) {
   const int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
   if (i >= n_sp) return;
   const int64_t p = sorted_val[i];
@@ -160,6 +160,7 @@ __global__ void bm25_tt_fill_kernel(const uint32_t* __restrict__ sorted_val, int
   tt_term[i] = static_cast<uint32_t>(t);
   tt_doc[i] = static_cast<uint8_t>(doc[p] & (PLANE_TILE - 1));
   tt_val[i] = __dmul_rn(idf[t], gtab[gcode[p]]);
+  atomicOr(tt_bloom + static_cast<int64_t>(doc[p]) * BLOOM_W + bloom_word(static_cast<uint32_t>(t)), bloom_mask(static_cast<uint32_t>(t)));
 }
 // step 3: term id and finished contribution idf * g of every row entry
 __global__ void bm25_drow_fill_kernel(const uint32_t* __restrict__ sorted_val, int64_t n_sp, const int64_t* __restrict__ term_ptr,
@@ -198,9 +199,11 @@ __device__ __forceinline__ Bm25Smem carve(uint8_t* base) {
 // Accumulate the scores of one doc block for one query into s.acc (fp64, query
 // token order).  All threads of the CTA call this; ends with a barrier.
 __device__ __forceinline__ void bm25_accumulate_block(const Bm25Dev& ix, const Bm25Smem& s, const int32_t* q_terms,
-                                                      int max_qt, int b, bool g_in_smem) {
+                                                      int max_qt, int b, bool g_in_smem, const double* init = nullptr,
+                                                      int n_init = 0) {
   const int tid = threadIdx.x;
-  for (int i = tid; i < DOC_BLOCK / 2; i += BM25_THREADS) reinterpret_cast<double2*>(s.acc)[i] = make_double2(0.0, 0.0);
+  // `init`: the sums so far of a query longer than one call's token limit (the chunks continue the same in-order sum)
+  for (int i = tid; i < DOC_BLOCK; i += BM25_THREADS) s.acc[i] = (init && i < n_init) ? init[i] : 0.0;
   if (tid < max_qt) {
     const int t = q_terms[tid];
     uint32_t lo = 0, hi = 0;
@@ -541,7 +544,7 @@ bm25_topk_kernel(const Bm25Dev ix, const int32_t* __restrict__ q_terms_all, int 
 // Full score vectors: grid (nq, nb); out[q, doc] for doc < n_out.
 __global__ void __launch_bounds__(BM25_THREADS, 1)
 bm25_scores_kernel(const Bm25Dev ix, const int32_t* __restrict__ q_terms_all, int max_qt, int64_t n_out,
-                   double* __restrict__ out) {
+                   double* __restrict__ out, int accumulate) {
   extern __shared__ __align__(16) uint8_t bsm[];
   const Bm25Smem s = carve(bsm);
   const int tid = threadIdx.x;
@@ -550,9 +553,10 @@ bm25_scores_kernel(const Bm25Dev ix, const int32_t* __restrict__ q_terms_all, in
   const bool g_in_smem = ix.n_g <= GTAB_SMEM;
   if (g_in_smem) for (int i = tid; i < ix.n_g; i += BM25_THREADS) s.gtab[i] = ix.gtab[i];
   __syncthreads();
-  bm25_accumulate_block(ix, s, q_terms_all + q * max_qt, max_qt, b, g_in_smem);
   const int64_t doc0 = static_cast<int64_t>(b) << DOC_BLOCK_LOG2;
   const long long lim = min(min(static_cast<long long>(ix.n_docs), static_cast<long long>(n_out)) - static_cast<long long>(doc0), static_cast<long long>(DOC_BLOCK));
+  bm25_accumulate_block(ix, s, q_terms_all + q * max_qt, max_qt, b, g_in_smem, accumulate ? out + q * n_out + doc0 : nullptr,
+                        static_cast<int>(max(0ll, lim)));
   for (int64_t d = tid; d < lim; d += BM25_THREADS) out[q * n_out + doc0 + d] = s.acc[d];
 }
 
@@ -792,6 +796,12 @@ extern "C" int arb_bm25_create(arb_bm25** out, int64_t n_docs, int64_t n_terms, 
               cudaMalloc(&bm->tt_val, std::max<size_t>(n_sp, 1) * 8) != cudaSuccess) {
             cudaGetLastError(); set_error("arb_bm25_create: out of device memory (tile rows)"); return fail(ARB_ENOMEM);
           }
+          const size_t bloom_bytes = static_cast<size_t>(n_tiles) * PLANE_TILE * BLOOM_W * 4;
+          if (cudaMalloc(&bm->tt_bloom, bloom_bytes) != cudaSuccess) {
+            cudaGetLastError(); set_error("arb_bm25_create: out of device memory (doc filters)"); return fail(ARB_ENOMEM);
+          }
+          e = cudaMemsetAsync(bm->tt_bloom, 0, bloom_bytes, st);
+          if (e != cudaSuccess) return fail(cuda_fail(e, "bm25 doc filters", __FILE__, __LINE__));
           AsyncBuf t_key;
           e = t_key.alloc(np4, st);
           if (e != cudaSuccess) { cudaGetLastError(); set_error("arb_bm25_create: out of device memory (tile-row build)"); return fail(ARB_ENOMEM); }
@@ -814,7 +824,7 @@ extern "C" int arb_bm25_create(arb_bm25** out, int64_t n_docs, int64_t n_terms, 
           if (n_sp > 0) {
             bm25_tt_fill_kernel<<<static_cast<unsigned>((n_sp + 255) / 256), 256, 0, st>>>(
                 v_out.as<uint32_t>(), n_sp, d_ptr.as<int64_t>(), n_terms, d_doc.as<int32_t>(), d_code.as<int32_t>(), bm->idf, bm->gtab,
-                bm->tt_term, bm->tt_doc, bm->tt_val);
+                bm->tt_term, bm->tt_doc, bm->tt_val, bm->tt_bloom);
             count_launch();
           }
         }
@@ -824,6 +834,8 @@ extern "C" int arb_bm25_create(arb_bm25** out, int64_t n_docs, int64_t n_terms, 
         e = cudaMemsetAsync(bm->drow_off, 0, static_cast<size_t>(n_docs + 1) * 4, st);
         if (e == cudaSuccess && cudaMalloc(&bm->tt_off, static_cast<size_t>(bm->dev.n_tiles + 1) * 4) != cudaSuccess) e = cudaErrorMemoryAllocation;
         if (e == cudaSuccess) e = cudaMemsetAsync(bm->tt_off, 0, static_cast<size_t>(bm->dev.n_tiles + 1) * 4, st);
+        if (e == cudaSuccess && cudaMalloc(&bm->tt_bloom, static_cast<size_t>(bm->dev.n_tiles) * PLANE_TILE * BLOOM_W * 4) != cudaSuccess) e = cudaErrorMemoryAllocation;
+        if (e == cudaSuccess) e = cudaMemsetAsync(bm->tt_bloom, 0, static_cast<size_t>(bm->dev.n_tiles) * PLANE_TILE * BLOOM_W * 4, st);
         if (e != cudaSuccess) return fail(cuda_fail(e, "bm25 doc rows", __FILE__, __LINE__));
       }
       bm->dev.n_sp = n_sp;
@@ -844,6 +856,7 @@ extern "C" int arb_bm25_create(arb_bm25** out, int64_t n_docs, int64_t n_terms, 
   bm->dev.planes32 = bm->planes32;
   bm->dev.drow_off = bm->drow_off; bm->dev.drow_term = bm->drow_term; bm->dev.drow_val = bm->drow_val;
   bm->dev.tt_off = bm->tt_off; bm->dev.tt_term = bm->tt_term; bm->dev.tt_doc = bm->tt_doc; bm->dev.tt_val = bm->tt_val;
+  bm->dev.tt_bloom = bm->tt_bloom;
   *out = bm;
   return ARB_OK;
 }
@@ -867,6 +880,7 @@ extern "C" int arb_bm25_destroy(arb_bm25* bm) {
   if (bm->tt_term) cudaFree(bm->tt_term);
   if (bm->tt_doc) cudaFree(bm->tt_doc);
   if (bm->tt_val) cudaFree(bm->tt_val);
+  if (bm->tt_bloom) cudaFree(bm->tt_bloom);
   delete bm;
   return ARB_OK;
 }
@@ -922,7 +936,7 @@ extern "C" int arb_bm25_search(const arb_bm25* bm, const int32_t* q_terms, int64
 
   // Batches go through the plane/sparse pipeline (bm25_batch.cu); small batches and long queries use the
   // per-query kernel.  ARB_BM25_MODE=query|batch forces one of them (tests exercise both).
-  int64_t batch_min = 64;
+  int64_t batch_min = 256;                                       // below this the tile-major pipeline's per-tile fixed costs lose to one CTA per query
   bool force_query = false;
   if (const char* v = std::getenv("ARB_BM25_MODE")) {
     if (!strcmp(v, "query")) force_query = true;
@@ -985,14 +999,17 @@ extern "C" int arb_bm25_scores(const arb_bm25* bm, const int32_t* q_terms, int64
   double* d_out = out;
   if (!out_is_device) { ARB_CUDA(obuf.alloc(static_cast<size_t>(nq) * n_out * 8, st)); d_out = obuf.as<double>(); }
   const int64_t total = nq * n_out;
-  if (n_out > bm->dev.n_docs) {                                // pad slots beyond the corpus with 0.0 (:320-323)
+  const int accumulate = (normalise >> 1) & 1;                 // bit 1: continue the sums already in `out` (queries of > 64 tokens)
+  normalise &= 1;
+  ARB_CHECK(!accumulate || out_is_device, ARB_EINVAL, "arb_bm25_scores: accumulation needs a device-resident output");
+  if (n_out > bm->dev.n_docs && !accumulate) {                 // pad slots beyond the corpus with 0.0 (:320-323)
     fill_f64_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, st>>>(d_out, 0.0, total);
     ARB_LAUNCH_OK();
   }
   const int nb_used = static_cast<int>(std::min<int64_t>(bm->dev.nb, (std::min(n_out, bm->dev.n_docs) + DOC_BLOCK - 1) / DOC_BLOCK));
   if (nb_used > 0) {
     dim3 grid(static_cast<unsigned>(nq), static_cast<unsigned>(nb_used));
-    bm25_scores_kernel<<<grid, BM25_THREADS, BM25_SMEM, st>>>(bm->dev, d_terms, max_qt, n_out, d_out);
+    bm25_scores_kernel<<<grid, BM25_THREADS, BM25_SMEM, st>>>(bm->dev, d_terms, max_qt, n_out, d_out, accumulate);
     ARB_LAUNCH_OK();
   }
   if (normalise) {

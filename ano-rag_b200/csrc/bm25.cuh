@@ -64,7 +64,18 @@ struct Bm25Dev {
   const uint32_t* tt_term;      // [n_sp]
   const uint8_t* tt_doc;        // [n_sp] doc inside the tile
   const double* tt_val;         // [n_sp]
+  const uint32_t* tt_bloom;     // [n_tiles * 256 * BLOOM_W] per-doc filter of the doc's sparse terms (bloom_word / bloom_mask)
 };
+
+// Per-doc filter of the doc's sparse terms: 16 words; a term sets three of bits 0..30 of ONE word, so a look-up is one
+// load and one masked compare (~1 % false positives per look-up for a doc with 22 sparse terms).  Bit 31 is never set:
+// a record entry without a sparse term tests for it.
+constexpr int BLOOM_W = 16;
+__host__ __device__ __forceinline__ uint32_t bloom_word(uint32_t t) { return (t * 0x9E3779B1u) >> 28; }
+__host__ __device__ __forceinline__ uint32_t bloom_mask(uint32_t t) {
+  const uint32_t h = t * 0x85EBCA6Bu;
+  return (1u << ((h >> 27) * 31u >> 5)) | (1u << (((h >> 22) & 31u) * 31u >> 5)) | (1u << (((h >> 17) & 31u) * 31u >> 5));
+}
 
 // Position of doc d (0..255) inside a 256-entry fp32 plane-tile row: lane l owns docs 8l .. 8l+7 and reads them as
 // two 16-byte chunks; chunk j of all lanes is contiguous (conflict-free LDS.128):  d = 8l + 4j + e -> (j*32 + l)*4 + e.
@@ -106,5 +117,6 @@ struct arb_bm25 {
   uint32_t* tt_term = nullptr;
   uint8_t* tt_doc = nullptr;
   double* tt_val = nullptr;
+  uint32_t* tt_bloom = nullptr;
   std::vector<int64_t> df;      // host copy of per-term df (roofline accounting)
 };

@@ -144,16 +144,8 @@ __device__ __forceinline__ void cta_sort_desc(unsigned long long* key, IdT* id, 
 }
 
 
-// Per-doc filter of the doc's sparse terms: 16 words; a term sets three of bits 0..30 of ONE word, so a look-up is one
-// load and one masked compare (~1 % false positives per look-up for a doc with 22 sparse terms).  Bit 31 is never set:
-// a record entry without a sparse term tests for it.
 constexpr uint32_t SLOT_NONE = 127u;
-constexpr int MJ_BLOOM_W = 16;
-__host__ __device__ __forceinline__ uint32_t bloom_word(uint32_t t) { return (t * 0x9E3779B1u) >> 28; }
-__host__ __device__ __forceinline__ uint32_t bloom_mask(uint32_t t) {
-  const uint32_t h = t * 0x85EBCA6Bu;
-  return (1u << ((h >> 27) * 31u >> 5)) | (1u << (((h >> 22) & 31u) * 31u >> 5)) | (1u << (((h >> 17) & 31u) * 31u >> 5));
-}
+constexpr int MJ_BLOOM_W = BLOOM_W;                  // bm25.cuh: the per-doc filters are part of the index
 
 // ----------------------------------------------------------------------------
 // 0. query-term index of the batch
@@ -361,6 +353,7 @@ bm25_member_kernel(const Bm25Dev ix, const BatchScratch sc, int64_t tile_lo, int
   __shared__ int n_def_s;
   if (tid == 0) { ptx::mbar_init(&fill_bar, 1); ptx::fence_barrier_init(); n_def_s = 0; }
   for (int i = tid; i < MJ_PSTRIDE; i += MJ_THREADS) pl[static_cast<size_t>(P) * MJ_PSTRIDE + i] = 0.0;
+  constexpr uint32_t BLOOM_BYTES = PLANE_TILE * MJ_BLOOM_W * 4u;
   uint32_t fill_phase = 0;
   const int64_t units = (tile_hi - tile_lo) * sub;
   constexpr int RS4 = 1 + QS / 4;
@@ -370,26 +363,23 @@ bm25_member_kernel(const Bm25Dev ix, const BatchScratch sc, int64_t tile_lo, int
     const int64_t tile = tile_lo + u / sub;
     const int part = static_cast<int>(u % sub);
     __syncthreads();                                           // the previous unit is done; fill_bar is initialised
-    if (tid == 0) {
-      if (P > 0) {
-        const uint32_t bytes = static_cast<uint32_t>(P) * PLANE_TILE * 8u;
-        const char* src = reinterpret_cast<const char*>(ix.planes + tile * P * PLANE_TILE);
-        ptx::fence_proxy_async_smem();
-        ptx::mbar_expect_tx(&fill_bar, bytes);
-        for (int r = 0; r < P; ++r)                             // one 2 KB row at a time into the padded rows
-          ptx::bulk_load_1d(mj_smem + static_cast<size_t>(r) * MJ_PSTRIDE * 8, src + static_cast<size_t>(r) * PLANE_TILE * 8,
-                            PLANE_TILE * 8u, &fill_bar);
+    if (warp == 0) {
+      // the tile of all planes (one 2 KB row at a time into the padded rows) and the tile's per-doc filters: the copies
+      // are issued by the 32 lanes side by side, all completing on one mbarrier
+      ptx::fence_proxy_async_smem();                            // every issuing lane: earlier generic reads before its async writes
+      if (lane == 0) {
+        ptx::mbar_expect_tx(&fill_bar, static_cast<uint32_t>(P) * PLANE_TILE * 8u + BLOOM_BYTES);
+        ptx::bulk_load_1d(bloom, ix.tt_bloom + tile * (PLANE_TILE * MJ_BLOOM_W), BLOOM_BYTES, &fill_bar);
       }
+      __syncwarp();
+      const char* src = reinterpret_cast<const char*>(ix.planes + tile * P * PLANE_TILE);
+      for (int r = lane; r < P; r += 32)
+        ptx::bulk_load_1d(mj_smem + static_cast<size_t>(r) * MJ_PSTRIDE * 8, src + static_cast<size_t>(r) * PLANE_TILE * 8,
+                          PLANE_TILE * 8u, &fill_bar);
     }
-    // the per-doc filters of the whole tile while the planes are on their way
-    for (int i = tid; i < PLANE_TILE * MJ_BLOOM_W; i += MJ_THREADS) bloom[i] = 0u;
-    __syncthreads();
     const uint32_t t_lo = __ldg(ix.tt_off + tile), t_hi = __ldg(ix.tt_off + tile + 1);
-    for (uint32_t i = t_lo + tid; i < t_hi; i += MJ_THREADS) {
-      const uint32_t t = __ldg(ix.tt_term + i);
-      atomicOr(&bloom[__ldg(ix.tt_doc + i) * MJ_BLOOM_W + bloom_word(t)], bloom_mask(t));
-    }
-    if (P > 0) { ptx::mbar_wait(&fill_bar, fill_phase); fill_phase ^= 1u; }
+    ptx::mbar_wait(&fill_bar, fill_phase);
+    fill_phase ^= 1u;
     __syncthreads();
     // this unit's slice of the tile's postings
     const uint32_t o_lo = t_lo + static_cast<uint32_t>((static_cast<uint64_t>(t_hi - t_lo) * part) / sub);
@@ -1140,7 +1130,7 @@ static int batch_chunk(const Bm25Dev& ix, const int32_t* d_terms, int64_t nq, in
     // ---- 1. member pass in rounds of growing size (fractions of the tiles, in 64ths), a compaction after each
     std::vector<int> cuts;
     if (ix.n_tiles <= 8) cuts = {64};
-    else if (ix.n_tiles < 256) cuts = {4, 16, 64};
+    else if (ix.n_tiles < 1024) cuts = {4, 16, 64};              // shards of up to 256 K docs: a round costs more than it prunes
     else cuts = {1, 4, 16, 32, 64};
     if (const char* v = std::getenv("ARB_BM25_ROUNDS")) { if (atoi(v) == 1) cuts = {64}; }
     const int mj_ch = static_cast<int>(std::min<size_t>(MJ_CH_MAX, ((SMEM_MAX - mj_fixed_bytes(ix.n_planes)) / 12 - 4) & ~size_t(3)));

@@ -268,15 +268,20 @@ class BM25Index:
                                           ids.ctypes.data, 0, _stream_ptr()))
         return scores, ids
 
-    def scores_device(self, q_terms, n_out: Optional[int] = None, normalise: bool = False):
-        """Full fp64 score vectors [nq, n_out] left on the device (torch CUDA tensor)."""
+    def scores_device(self, q_terms, n_out: Optional[int] = None, normalise: bool = False, continue_from=None):
+        """Full fp64 score vectors [nq, n_out] left on the device (torch CUDA tensor).  ``continue_from``: the tensor an
+        earlier call returned for the FIRST tokens of the same queries -- the sums continue in it, token by token, so a
+        query longer than the kernel's per-call limit keeps the reference's summation order."""
         b = self._terms(q_terms)
         nq, mq = b.shape
         n_out = self.n_docs if n_out is None else int(n_out)
         device = b.device if b.is_device else torch.device("cuda", torch.cuda.current_device())
         with torch.cuda.device(device):
-            out = torch.empty((nq, n_out), dtype=torch.float64, device=device)
-            nat.check(nat.lib.arb_bm25_scores(self._h, b.ptr, nq, mq, b.is_device, 1 if normalise else 0, n_out,
+            out = continue_from if continue_from is not None else torch.empty((nq, n_out), dtype=torch.float64, device=device)
+            if tuple(out.shape) != (nq, n_out) or out.dtype != torch.float64 or not out.is_contiguous():
+                raise ValueError("continue_from must be the contiguous fp64 [nq, n_out] tensor of the earlier call")
+            flags = (1 if normalise else 0) | (2 if continue_from is not None else 0)
+            nat.check(nat.lib.arb_bm25_scores(self._h, b.ptr, nq, mq, b.is_device, flags, n_out,
                                               out.data_ptr(), 1, _stream_ptr(device)))
         return out
 

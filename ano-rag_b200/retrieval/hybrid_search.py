@@ -19,6 +19,7 @@ from typing import Any, Dict, Hashable, List, Optional, Sequence, Tuple
 import numpy as np
 
 from .. import engine
+from .._log import logger
 
 _SRC = ("dense", "bm25", "graph", "path")
 MAX_PER_SOURCE = 256        # kernel limit (include/anorag_b200.h arb_fuse)
@@ -49,8 +50,14 @@ class HybridSearcher:
         per_src: List[Dict[Hashable, float]] = [{nid: s for nid, s in lst} for lst in lists]
         if not any(per_src):
             return []
-        if max(len(d) for d in per_src) > MAX_PER_SOURCE:
-            raise ValueError(f"fuse(): more than {MAX_PER_SOURCE} ids in one source list")
+        for i, d in enumerate(per_src):
+            if len(d) > MAX_PER_SOURCE:
+                # the fusion kernel holds MAX_PER_SOURCE entries per source; the reference has no limit and never raises.
+                # Keep the source's best MAX_PER_SOURCE by score (stable, dict order otherwise unchanged): their ranks and
+                # the normalising maximum are what they were; only contributions of rank > MAX_PER_SOURCE are lost.
+                logger.warning(f"fuse(): {_SRC[i]} list has {len(d)} ids; keeping its best {MAX_PER_SOURCE}")
+                keep = set(sorted(d, key=lambda n: d[n], reverse=True)[:MAX_PER_SOURCE])
+                per_src[i] = {n: v for n, v in d.items() if n in keep}
         code: Dict[Hashable, int] = {}
         for d in per_src:
             for nid in d:

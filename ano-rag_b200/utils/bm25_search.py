@@ -79,23 +79,42 @@ class GpuBM25:
         return {w: float(idf[t]) for w, t in self.vocab.ids.items()}
 
     # -- encoding of queries into padded term-id matrices
+    def _term_ids(self, toks: Sequence[Any]) -> List[int]:
+        """Known term ids of a tokenised query, in token order.  Tokens outside the vocabulary add +0.0 in the
+        reference (``idf.get(q) or 0``): leaving them out changes nothing and keeps the id matrix narrow."""
+        ids = self.vocab.encode_query(toks) if self.vocab is not None else [int(t) for t in toks]
+        return [t for t in ids if t >= 0]
+
     def encode_queries(self, token_lists: Sequence[Sequence[Any]]) -> np.ndarray:
-        width = max(1, max((len(t) for t in token_lists), default=1))
+        rows = [self._term_ids(toks) if toks else [] for toks in token_lists]
+        width = max(1, max((len(r) for r in rows), default=1))
         if width > MAX_QUERY_TERMS:
-            raise ValueError(f"queries longer than {MAX_QUERY_TERMS} tokens are outside the kernel's limit")
-        out = np.full((len(token_lists), width), -1, dtype=np.int32)
-        for i, toks in enumerate(token_lists):
-            if not toks:
-                continue
-            ids = self.vocab.encode_query(toks) if self.vocab is not None else [int(t) for t in toks]
+            raise ValueError(f"queries with more than {MAX_QUERY_TERMS} known tokens need scores_long()")
+        out = np.full((len(rows), width), -1, dtype=np.int32)
+        for i, ids in enumerate(rows):
             out[i, :len(ids)] = ids
         return out
+
+    def scores_long(self, query_tokens: Sequence[Any], n_out: Optional[int] = None, normalise: bool = False) -> np.ndarray:
+        """Scores of every doc for ONE query of any length (the reference has no limit): the known tokens are scored
+        ``MAX_QUERY_TERMS`` at a time, every chunk continuing the sums of the previous one on the device, so the
+        fp64 summation order is the reference's token order throughout."""
+        ids = self._term_ids(list(query_tokens))
+        chunks = [ids[i:i + MAX_QUERY_TERMS] for i in range(0, max(1, len(ids)), MAX_QUERY_TERMS)]
+        acc = None
+        for j, ch in enumerate(chunks):
+            qt = np.asarray([ch if ch else [-1]], dtype=np.int32)
+            acc = self.index.scores_device(qt, n_out=n_out, normalise=normalise and j == len(chunks) - 1, continue_from=acc)
+        return acc[0].cpu().numpy()
 
     # -- reference-shaped scoring
     def get_scores(self, query: Sequence[Any]) -> np.ndarray:
         """Raw scores of every doc for one tokenised query (BM25Okapi.get_scores contract:
         float64 ndarray of length N)."""
-        return self.index.scores(self.encode_queries([list(query)]))[0]
+        query = list(query)
+        if len(query) > MAX_QUERY_TERMS:
+            return self.scores_long(query)
+        return self.index.scores(self.encode_queries([query]))[0]
 
     # -- batched GPU paths (additions)
     def scores_batch(self, queries: Sequence[str], n_out: Optional[int] = None, normalise: bool = True) -> np.ndarray:
@@ -130,8 +149,14 @@ class FieldWeightedBM25:
         self.field_idf = {f: c.idf for f, c in self.fields.items()}
 
     def _scores_device(self, query_tokens: Sequence[str], normalise: bool, n_out: Optional[int] = None):
-        per_field = [c.index.scores_device(c.encode_queries([list(query_tokens)]), n_out=n_out)
-                     for c in self.fields.values()]
+        per_field = []
+        for c in self.fields.values():
+            ids = c._term_ids(list(query_tokens))
+            acc = None
+            for i in range(0, max(1, len(ids)), MAX_QUERY_TERMS):       # any query length: chunks continue the same sums
+                qt = np.asarray([ids[i:i + MAX_QUERY_TERMS] or [-1]], dtype=np.int32)
+                acc = c.index.scores_device(qt, n_out=n_out, continue_from=acc)
+            per_field.append(acc)
         return engine.combine_fields(per_field, list(self.field_weights.values()), normalise)
 
     def get_scores(self, query: List[str]) -> List[float]:
@@ -211,8 +236,25 @@ def bm25_scores(corpus: Any, docs: List[Dict[str, Any]], query: str) -> List[flo
         if isinstance(corpus, GpuBM25):
             if len(docs) == 0:
                 return []
+            if len(query_tokens) > MAX_QUERY_TERMS:
+                return corpus.scores_long(query_tokens, n_out=len(docs), normalise=True).tolist()
             return corpus.index.scores(corpus.encode_queries([query_tokens]), n_out=len(docs),
                                        normalise=True)[0].tolist()
+        if isinstance(corpus, FieldWeightedBM25):
+            return field_weighted_bm25_scores(corpus, docs, query)
+        if hasattr(corpus, "get_scores"):
+            # any other corpus object with the reference's duck type (:307-314): its own scorer, then the same
+            # pad / truncate / max-normalise steps (:320-333)
+            scores = corpus.get_scores(query_tokens)
+            scores = scores.tolist() if hasattr(scores, "tolist") else list(scores)
+            if len(scores) < len(docs):
+                scores = scores + [0.0] * (len(docs) - len(scores))
+            elif len(scores) > len(docs):
+                scores = scores[:len(docs)]
+            max_score = max(scores) if scores else 0.0
+            if max_score > 0:
+                scores = [s / max_score for s in scores]
+            return scores
         logger.error("Invalid corpus object")
         return [0.0] * len(docs)
     except Exception as e:

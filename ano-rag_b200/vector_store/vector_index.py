@@ -29,6 +29,7 @@ import numpy as np
 from .._log import logger
 from ..config import config
 from .. import engine
+from .._native import MAX_TOPK
 from . import faiss_io
 
 try:
@@ -178,6 +179,11 @@ class VectorIndex:
     # ------------------------------------------------------------------ search
     def search_tensors(self, query_vectors, top_k: int = 10):
         """(scores fp32 [nq,k], ids int64 [nq,k]); numpy in -> numpy out, CUDA in -> CUDA out."""
+        if top_k > MAX_TOPK:
+            # the select kernel keeps at most MAX_TOPK candidates per query (faiss has no such limit): the best MAX_TOPK are
+            # returned rather than nothing (VectorRetriever.retrieve asks for 3 x top_k, retriever.py:381)
+            logger.warning(f"top_k={top_k} exceeds the kernel limit; returning the best {MAX_TOPK} per query")
+            top_k = MAX_TOPK
         if self._ivf_lists() and self.index.nlist > 0:
             return self.index.ivf_search(self._as_rows(query_vectors), top_k, self.nprobe)   # index.nprobe (:91)
         return self.index.search(self._as_rows(query_vectors), top_k)
@@ -198,7 +204,7 @@ class VectorIndex:
             for query_idx in range(len(indices_l)):                                         # :227-253
                 query_results = []
                 row_i, row_s = indices_l[query_idx], scores_l[query_idx]
-                for rank in range(top_k):
+                for rank in range(min(top_k, len(row_i))):
                     idx = row_i[rank]
                     if idx == -1:
                         continue

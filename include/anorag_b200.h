@@ -187,7 +187,9 @@ ARB_API int arb_bm25_search(const arb_bm25* bm, const int32_t* q_terms, int64_t 
                     int out_is_device, void* stream);
 /* Full score vectors (bm25_scores, utils/bm25_search.py:286-340): out [nq, n_out]
  * fp64; docs >= n_out are truncated, slots >= n_docs padded with 0.0 (:320-327);
- * `normalise` != 0 divides by the per-query max when it is > 0 (:329-333). */
+ * bit 0 of `normalise` divides by the per-query max when it is > 0 (:329-333); bit 1 CONTINUES the sums already in
+ * `out` (device-resident) instead of starting from zero: a query longer than ARB_MAX_QUERY_TERMS is scored in
+ * consecutive chunks, which keeps the reference's token-by-token summation order bit for bit. */
 ARB_API int arb_bm25_scores(const arb_bm25* bm, const int32_t* q_terms, int64_t nq, int max_qt,
                     int q_is_device, int normalise, int64_t n_out, double* out,
                     int out_is_device, void* stream);
