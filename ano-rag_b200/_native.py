@@ -37,6 +37,10 @@ def _load():
         mod = importlib.util.module_from_spec(spec)
         spec.loader.exec_module(mod)
         mod.build()
+    try:                                # torch maps libcudart.so.12, which the library links dynamically; the image's
+        import torch  # noqa: F401      # own /usr/local/cuda copy serves when torch is absent
+    except Exception:
+        pass
     return ctypes.CDLL(LIB_PATH)
 
 

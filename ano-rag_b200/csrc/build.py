@@ -62,7 +62,9 @@ def build(force=False, verbose=False):
                 if r.returncode != 0:
                     raise RuntimeError(f"nvcc failed on {src}:\n{r.stdout}\n{r.stderr}")
     if force or _newer(LIB, objs):
-        cmd = [nvcc] + ARCH + ["-shared", "-o", LIB] + objs + ["-cudart", "static"]
+        # the shared CUDA runtime: torch has already mapped libcudart.so.12 when the library is loaded (_native.py imports
+        # torch first), and the shipped object then carries no copy of the runtime's entry-point tables
+        cmd = [nvcc] + ARCH + ["-shared", "-o", LIB] + objs + ["-cudart", "shared"]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")

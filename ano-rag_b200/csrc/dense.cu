@@ -594,8 +594,9 @@ dense_topk_pair_kernel(const __grid_constant__ CUtensorMap tmap_a,
 // (a query has n_splits * EPI_HALVES lists -- 10 at 4096 queries, 74 at 512 -- and the serial version was
 // latency-bound: ~1 ms of a 1.45 ms dense stage at 512 queries).  Warp 0 then folds the other warps' survivors.
 // ----------------------------------------------------------------------------
-constexpr int MERGE_WARPS = 4;
-template <int EPL, bool IVF>
+// MERGE_WARPS = 4 for batches (few lists per query, thousands of CTAs), 16 for small batches: a single query against
+// 1 M rows has 2 x 148 lists, and the merge was a third of its latency with four warps.
+template <int EPL, bool IVF, int MERGE_WARPS = 4>
 __global__ void __launch_bounds__(32 * MERGE_WARPS)
 dense_merge_kernel(const DenseParams p, int64_t id_base, float* __restrict__ out_scores,
                    int64_t* __restrict__ out_ids) {
@@ -817,6 +818,14 @@ static int make_tmap(CUtensorMap* m, const void* base, uint64_t rows, uint64_t c
 
 using namespace arb;
 
+// a mutex that a struct copy does not carry along (k-means borrows an index's rows through a by-value view)
+struct HandleMutex {
+  std::mutex m;
+  HandleMutex() = default;
+  HandleMutex(const HandleMutex&) {}
+  HandleMutex& operator=(const HandleMutex&) { return *this; }
+};
+
 struct arb_index {
   int dim = 0, d_pad = 0, storage = 0, planes = 1, normalize = 1;
   int normalize_rows = 1;        // rows of the next add calls (arb_index_set_row_normalization); queries follow `normalize`
@@ -834,6 +843,9 @@ struct arb_index {
   __nv_bfloat16* g_rows = nullptr;     // rows regrouped list-major
   int64_t* g_ids = nullptr;            // [g_n] add-order position of each regrouped row
   uint32_t* list_off = nullptr;        // [nlist + 1]
+  // Searches are re-entrant on a read-only index, but the first IVF search after an add regroups the rows (frees and
+  // reallocates g_rows / g_ids): that step, and everything that writes the index, is serialised per handle.
+  HandleMutex mu;
 };
 
 static int launch_prep(const void* src_dev, int dtype, int64_t n, int d, int d_pad, int planes, int normalize,
@@ -1140,6 +1152,9 @@ static int run_dense_chunk(const arb_index* ix, int64_t n_rows, const uint32_t* 
       attr_err = cudaFuncSetAttribute(dense_topk_kernel<EPL, false, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, DENSE_SMEM);
     if (attr_err == cudaSuccess)
       attr_err = cudaFuncSetAttribute(dense_topk_pair_kernel<EPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, PAIR_SMEM);
+    if (attr_err == cudaSuccess)
+      attr_err = cudaFuncSetAttribute(dense_merge_kernel<EPL, false, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      static_cast<int>(16 * 32 * EPL * sizeof(uint2)));
   });
   ARB_CUDA(attr_err);
   {
@@ -1165,8 +1180,10 @@ static int run_dense_chunk(const arb_index* ix, int64_t n_rows, const uint32_t* 
   ARB_LAUNCH_OK();
   const int wpb = 4;
   {
-    dense_merge_kernel<EPL, false><<<static_cast<unsigned>(nq), MERGE_WARPS * 32, MERGE_WARPS * C * sizeof(uint2), st>>>(
-        p, id_base, d_scores, d_ids);
+    if (p.n_splits * EPI_HALVES >= 48 && nq <= 2048)
+      dense_merge_kernel<EPL, false, 16><<<static_cast<unsigned>(nq), 16 * 32, 16 * C * sizeof(uint2), st>>>(p, id_base, d_scores, d_ids);
+    else
+      dense_merge_kernel<EPL, false, 4><<<static_cast<unsigned>(nq), 4 * 32, 4 * C * sizeof(uint2), st>>>(p, id_base, d_scores, d_ids);
   }
   ARB_LAUNCH_OK();
   return ARB_OK;
@@ -1453,6 +1470,7 @@ static int ivf_sort_by_list(const int32_t* assign, int64_t n, int nlist, AsyncBu
 }
 
 static int ivf_regroup(arb_index* ix, cudaStream_t st) {
+  std::lock_guard<std::mutex> lock(ix->mu.m);                      // two first searches after an add must not both regroup
   if (!ix->grouped_dirty) return ARB_OK;
   ARB_CHECK(ix->n < (int64_t(1) << 31), ARB_ELIMIT, "IVF: at most 2^31 rows per shard");
   if (ix->g_cap < ix->n) {
@@ -1651,7 +1669,7 @@ static int run_ivf(arb_index* ix, const __nv_bfloat16* qplanes, int q_planes, in
   const int wpb = 4;
   {
     ProfileScope ps(PROF_DENSE_MERGE, st);
-    dense_merge_kernel<EPL, true><<<static_cast<unsigned>(nq), MERGE_WARPS * 32, MERGE_WARPS * C * sizeof(uint2), st>>>(
+    dense_merge_kernel<EPL, true, 4><<<static_cast<unsigned>(nq), 4 * 32, 4 * C * sizeof(uint2), st>>>(
         p, id_base, d_scores, d_ids);
   }
   ARB_LAUNCH_OK();

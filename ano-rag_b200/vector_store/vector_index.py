@@ -61,6 +61,7 @@ class VectorIndex:
         self.index: Optional[engine.DenseIndex] = None
         self.is_trained = False
         self.total_vectors = 0
+        self._id_table = None            # row -> id given to add_vectors (None: ids are the row numbers)
         self.index_dir = config.get("storage.vector_index_path")                            # :30-39
         if not self.index_dir:
             work_dir = config.get("storage.work_dir")
@@ -129,12 +130,19 @@ class VectorIndex:
                 return False
         try:
             if ids is not None and self.index_type not in ("Flat", "HNSW", "LSH"):
-                # the reference passes ids to add_with_ids (:187-193); VectorRetriever always
-                # passes arange(N) (retriever.py:156), the only mapping the flat kernel keeps
-                ids = np.asarray(ids)
-                expect = np.arange(self.total_vectors, self.total_vectors + len(vectors), dtype=np.int64)
-                if ids.shape != expect.shape or not np.array_equal(ids, expect):
-                    raise ValueError("custom ids must be the running row numbers on the B200 path")
+                # add_with_ids (:187-193): the kernels number rows in add order; ids that are not those running numbers
+                # (VectorRetriever passes arange(N), retriever.py:156) are kept in a row -> id table applied to results
+                ids = np.asarray(ids, dtype=np.int64).reshape(-1)
+                if len(ids) != len(vectors):
+                    raise ValueError("ids and vectors differ in length")
+                n0 = self.index.ntotal
+                running = np.arange(n0, n0 + len(ids), dtype=np.int64)
+                if self._id_table is not None or not np.array_equal(ids, running):
+                    base = self._id_table if self._id_table is not None else np.arange(n0, dtype=np.int64)
+                    self._id_table = np.concatenate([base, ids])
+            elif self._id_table is not None:
+                n0 = self.index.ntotal
+                self._id_table = np.concatenate([self._id_table, np.arange(n0, n0 + len(vectors), dtype=np.int64)])
             self.index.add(self._as_rows(vectors))
             self.total_vectors += len(vectors)
             logger.info(f"Added {len(vectors)} vectors to index, total: {self.total_vectors}")
@@ -199,6 +207,8 @@ class VectorIndex:
             scores, indices = self.search_tensors(query_vectors, top_k)                     # :220-223
             if torch is not None and isinstance(scores, torch.Tensor):
                 scores, indices = scores.cpu().numpy(), indices.cpu().numpy()
+            if self._id_table is not None:                                                  # ids given to add_vectors (:187-193)
+                indices = np.where(indices >= 0, self._id_table[np.clip(indices, 0, len(self._id_table) - 1)], -1)
             scores_l, indices_l = scores.tolist(), indices.tolist()
             results = []
             for query_idx in range(len(indices_l)):                                         # :227-253
@@ -278,6 +288,7 @@ class VectorIndex:
             metadata_file = filepath.replace(".faiss", "_metadata.json")
             self.embedding_dim = data.d
             self.total_vectors = 0
+            self._id_table = None            # row -> id given to add_vectors (None: ids are the row numbers)
             if os.path.exists(metadata_file):                                               # :338-347
                 with open(metadata_file, "r", encoding="utf-8") as f:
                     metadata = json.load(f)
@@ -329,12 +340,16 @@ class VectorIndex:
         try:
             ids = np.unique(np.asarray(ids, dtype=np.int64))
             n = self.index.ntotal
-            keep = np.setdiff1d(np.arange(n, dtype=np.int64), ids)
+            if self._id_table is not None:                                                  # remove_ids acts on the ids given at add time
+                keep = np.flatnonzero(~np.isin(self._id_table[:n], ids))
+                self._id_table = self._id_table[keep]
+            else:
+                keep = np.setdiff1d(np.arange(n, dtype=np.int64), ids)
             removed = n - len(keep)
             rows = self.index.reconstruct(0, n)[keep] if n else np.zeros((0, self.embedding_dim), np.float32)
             self.index.reset()
             if len(rows):
-                self.index.add(rows)
+                self.index.add_prepared(rows)                                               # stored rows are already normalised
             self.total_vectors -= len(ids)                                                  # :404 (reference subtracts len(ids))
             logger.info(f"Removed {removed} vectors from index")
             return True
@@ -346,6 +361,7 @@ class VectorIndex:
         if self.index is not None:
             self.index.reset()
         self.total_vectors = 0
+        self._id_table = None            # row -> id given to add_vectors (None: ids are the row numbers)
         self.is_trained = False
         logger.info("Index reset completed")
 

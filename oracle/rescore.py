@@ -202,3 +202,34 @@ def rerank_khop(dense: Sequence[float], bm25: Sequence[float], focused: Sequence
         score[i] = float(final)
     order = sorted(range(n), key=lambda i: score[i], reverse=True)             # :1632 (stable)
     return order, score
+
+
+def cluster_suppression(candidates, vecs, cos_threshold: float = 0.90, keep_per_cluster: int = 2):
+    """``QueryProcessor._apply_cluster_suppression`` (query/query_processor.py:1637-1697) restated.
+
+    Greedy near-duplicate suppression over a small candidate list: walk the candidates in order; an unused candidate i
+    opens a cluster of itself and every later unused j with ``cos(v_i, v_j) >= cos_threshold`` (vectors divided by
+    ``norm + 1e-8``, :1676-1682); the cluster is sorted by ``final_score`` (stable, descending, missing = 0.0) and its
+    first ``keep_per_cluster`` members are kept, ALL members are marked used (:1684-1689); the kept list is finally
+    sorted by ``final_score`` again (stable, :1691).  PINNED: tests/golden/cluster_suppression_golden.json.
+    """
+    import numpy as np
+    kept, used = [], set()
+    unit = [np.asarray(v) / (np.linalg.norm(v) + 1e-8) for v in vecs]
+    for i, ci in enumerate(candidates):
+        if i in used:
+            continue
+        cluster = [(i, ci)]
+        for j in range(i + 1, len(candidates)):
+            if j in used:
+                continue
+            if float(unit[i] @ unit[j]) >= cos_threshold:
+                cluster.append((j, candidates[j]))
+        cluster.sort(key=lambda x: x[1].get("final_score", 0.0), reverse=True)
+        for k, c in cluster[:keep_per_cluster]:
+            kept.append(c)
+            used.add(k)
+        for k, _ in cluster[keep_per_cluster:]:
+            used.add(k)
+    kept.sort(key=lambda x: x.get("final_score", 0.0), reverse=True)
+    return kept

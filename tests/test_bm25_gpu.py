@@ -210,3 +210,29 @@ def test_batched_pipeline_shapes(n, v, nq, mq, k, mean_len, monkeypatch):
         ws, wi = obm.topk_positive(ora.get_scores([t for t in qt[r] if t >= 0]), k)
         assert np.array_equal(i1[r], wi) and np.array_equal(s1[r], ws), f"query {r}"
     gpu.close()
+
+
+def test_queries_longer_than_the_kernel_limit_keep_the_summation_order():
+    """The reference scores queries of any length; the kernels take 64 tokens per call.  Longer queries are scored in
+    chunks that continue the same fp64 sums on the device: bit-identical to the oracle's single pass (bm25_search.py:309)."""
+    import ano_rag_b200  # noqa: F401
+    from ano_rag_b200.utils.bm25_search import build_bm25_corpus, bm25_scores, build_field_weighted_bm25_corpus, field_weighted_bm25_scores
+    from oracle import bm25 as obm
+    rng = random.Random(9)
+    docs = [" ".join(f"w{rng.randrange(120)}" for _ in range(rng.randint(5, 60))) for _ in range(700)]
+    notes = [{"content": d, "title": d[:12], "entities": [d.split()[0]]} for d in docs]
+    gpu = build_bm25_corpus(notes, lambda n: n["content"])
+    ora = obm.build_bm25_corpus(notes, lambda n: n["content"], backend="okapi")
+    for n_tok in (65, 100, 150, 200):
+        q = " ".join(f"w{rng.randrange(140)}" for _ in range(n_tok))          # some tokens are outside the vocabulary
+        toks = obm.tokenize_text(q)
+        assert gpu.get_scores(toks).tolist() == ora.get_scores(toks).tolist(), n_tok
+        got = bm25_scores(gpu, notes, q)
+        assert got == obm.bm25_scores(ora, notes, q) and max(got) == 1.0
+        assert bm25_scores(gpu, notes[:50], q) == obm.bm25_scores(ora, notes[:50], q)
+    fw = build_field_weighted_bm25_corpus(notes)
+    long_q = " ".join(f"w{rng.randrange(120)}" for _ in range(90))
+    s = field_weighted_bm25_scores(fw, notes, long_q)
+    assert len(s) == len(notes) and max(s) == 1.0
+    assert bm25_scores(fw, notes, long_q) == s                                # FieldWeightedBM25 through the generic entry point
+    fw.close(); gpu.close()

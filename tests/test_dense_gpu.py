@@ -226,3 +226,47 @@ def test_prepass_and_cta_pair_variants_are_bit_identical(monkeypatch):
     ok, _, _, worst = od.compare_topk(base[1][:16], base[0][:16], wi, ws, tol=TOL)
     assert ok, worst
     ix.close()
+
+
+def test_top_k_beyond_the_kernel_limit_returns_the_best_256():
+    """faiss accepts any k; the select kernel keeps 256 candidates.  Asking for more returns the best 256 instead of an
+    empty result (VectorRetriever.retrieve asks for 3 x top_k, vector_store/retriever.py:381)."""
+    import ano_rag_b200  # noqa: F401
+    from ano_rag_b200.config import config
+    from ano_rag_b200.vector_store import VectorIndex
+    from oracle import dense as od
+    config.reset()
+    rng = np.random.default_rng(3)
+    x = rng.standard_normal((2000, 48)).astype(np.float32)
+    q = rng.standard_normal((3, 48)).astype(np.float32)
+    vi = VectorIndex(embedding_dim=48)
+    assert vi.create_index("Flat") and vi.add_vectors(x)
+    res = vi.search(q, top_k=300)
+    assert len(res) == 3 and all(len(r) == 256 for r in res)
+    ws, wi = od.flat_ip_topk(od.preprocess_vectors(q), od.preprocess_vectors(x), 256)
+    ok, *_ = od.compare_topk(np.array([[e["index"] for e in r] for r in res]), np.array([[e["score"] for e in r] for r in res]), wi, ws, tol=1e-5)
+    assert ok
+    vi.cleanup()
+
+
+def test_add_vectors_keeps_custom_ids_like_add_with_ids():
+    """vector_store/vector_index.py:187-193: non-Flat index types receive the caller's ids (add_with_ids); results carry
+    them, remove_vectors takes them."""
+    import ano_rag_b200  # noqa: F401
+    from ano_rag_b200.config import config
+    from ano_rag_b200.vector_store import VectorIndex
+    config.reset()
+    rng = np.random.default_rng(8)
+    x = rng.standard_normal((500, 32)).astype(np.float32)
+    vi = VectorIndex(embedding_dim=32)
+    vi.index_type = "IVFFlat"
+    assert vi.create_index("IVFFlat")
+    ids = np.arange(500, dtype=np.int64) * 7 + 1000
+    assert vi.add_vectors(x[:300], ids[:300]) and vi.add_vectors(x[300:], ids[300:])
+    res = vi.search(x[[5, 410]], top_k=3)
+    assert res[0][0]["index"] == 1035 and res[1][0]["index"] == 1000 + 7 * 410
+    assert vi.remove_vectors(np.array([1035])) and vi.index.ntotal == 499
+    res = vi.search(x[[5]], top_k=3)
+    assert all(e["index"] != 1035 for e in res) and all((e["index"] - 1000) % 7 == 0 for e in res)
+    assert abs(res[0]["score"] - float(np.sort((x / np.linalg.norm(x, axis=1, keepdims=True)) @ (x[5] / np.linalg.norm(x[5])))[-2])) < 1e-5
+    vi.cleanup()

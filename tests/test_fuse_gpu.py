@@ -114,3 +114,18 @@ def test_pipeline_host_call_equals_device_call():
             assert np.array_equal(got[2], want[3]) and np.array_equal(got[3], want[2], equal_nan=True)
         assert np.array_equal(first[0], want[0])                  # the first call's views are still intact after one more call
     g.close(); ix.close()
+
+
+def test_fuse_with_more_ids_than_the_kernel_holds_keeps_the_best_per_source():
+    """The reference never raises (retrieval/hybrid_search.py:34-103); lists longer than the kernel's 256 entries per
+    source are cut to their best 256, whose ranks, normalised scores and fused values are what the reference computes
+    for them when the cut entries appear in no other source."""
+    import ano_rag_b200  # noqa: F401
+    from ano_rag_b200.retrieval.hybrid_search import HybridSearcher
+    from oracle import fusion as ofu
+    cfg = {"retrieval": {"candidate_pool": 40, "hybrid": {"fusion_method": "rrf", "rrf_k": 60, "weights": {"dense": 1.0, "bm25": 0.5}}}}
+    dense = [(f"d{i}", 1.0 - i * 1e-3) for i in range(400)]
+    bm25 = [(f"b{i}", 50.0 - i * 0.1) for i in range(300)] + [("d3", 60.0)]
+    got = HybridSearcher(cfg).fuse(dense=dense, bm25=bm25)
+    want = ofu.HybridSearcherOracle(cfg).fuse(dense=dense, bm25=bm25)
+    assert [(e["note_id"], e["final_similarity"]) for e in got] == [(e["note_id"], e["final_similarity"]) for e in want]

@@ -100,8 +100,8 @@ def test_bench_layout_choice():
     spec.loader.exec_module(bench)
     a = types.SimpleNamespace(row_shards="auto", workload="cfg3", notes=1_000_000, dim=768, hbm_budget_gb=140.0)
     assert [bench.choose_row_shards(a, w) for w in (1, 2, 4, 8)] == [1, 1, 1, 1]          # replicated corpus, split batch
-    a.notes, a.dim = 100_000_000, 1024                                                    # 205 GB of rows + postings
-    assert bench.choose_row_shards(a, 8) == 2 and bench.choose_row_shards(a, 1) == 1
+    a.notes, a.dim = 100_000_000, 1024                                                    # 205 GB of rows + ~160 GB of BM25 index
+    assert bench.choose_row_shards(a, 8) == 4 and bench.choose_row_shards(a, 1) == 1
     a.workload = "cfg4"
     assert bench.choose_row_shards(a, 8) == 8
     a.row_shards = "4"
@@ -111,3 +111,27 @@ def test_bench_layout_choice():
         bench.choose_row_shards(a, 8)
     cfg = bench.workload_config(types.SimpleNamespace(workload="cfg3", notes=10, dim=4, queries=2, topk=1, vocab=5), 8, 2)
     assert cfg["sharding"] == "2 row shard(s) x 4 query group(s)"
+
+
+def test_bm25_scores_accepts_any_corpus_with_get_scores():
+    """utils/bm25_search.py:307-314 duck-types on ``get_scores``: a foreign corpus object (rank_bm25, the reference's own
+    SimpleBM25, a test dummy) is scored by itself and gets the same pad / truncate / max-normalise treatment."""
+    import numpy as np
+    import ano_rag_b200  # noqa: F401
+    from ano_rag_b200.utils.bm25_search import bm25_scores
+
+    class Dummy:
+        def get_scores(self, tokens):
+            return np.array([0.0, 2.0, 1.0, 4.0]) * len(tokens)
+
+    docs = [{}] * 4
+    assert bm25_scores(Dummy(), docs, "a b") == [0.0, 0.5, 0.25, 1.0]
+    assert bm25_scores(Dummy(), docs[:2], "a b") == [0.0, 1.0]                 # truncated first, normalised after (:320-333)
+    assert bm25_scores(Dummy(), docs + [{}], "a") == [0.0, 0.5, 0.25, 1.0, 0.0]
+    assert bm25_scores(Dummy(), docs, "") == [0.0] * 4
+    assert bm25_scores(object(), docs, "a") == [0.0] * 4
+
+    class ListCorpus:
+        def get_scores(self, tokens):
+            return [0.0, 0.0]
+    assert bm25_scores(ListCorpus(), [{}] * 2, "x") == [0.0, 0.0]

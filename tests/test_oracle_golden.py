@@ -321,3 +321,30 @@ def test_tfidf_fallback_oracle_matches_reference_golden(golden_dir):
         for r in c["results"]:
             got = fb.search(r["query"], c["top_k"])
             assert [i for i, _ in got] == r["ids"] and [s for _, s in got] == [float.fromhex(v) for v in r["sims"]]
+
+
+def _cluster_cases(golden_dir):
+    import base64
+    with open(os.path.join(golden_dir, "cluster_suppression_golden.json")) as f:
+        gold = json.load(f)
+    for c in gold["cases"]:
+        vecs = np.frombuffer(base64.b64decode(c["vecs_f32_b64"]), dtype=np.float32).reshape(-1, c["dim"])
+        cands = []
+        for i, fs in enumerate(c["final_score"]):
+            e = {"note_id": f"n{i}", "_embed_vec": vecs[i].copy()}
+            if fs is not None:
+                e["final_score"] = fs
+            cands.append(e)
+        yield c, cands, vecs
+    return gold
+
+
+def test_cluster_suppression_oracle_matches_reference_golden(golden_dir):
+    """query/query_processor.py:1637-1697 restated in oracle/rescore.py against lists kept by the reference method itself."""
+    from oracle import rescore as ors
+    n = 0
+    for c, cands, vecs in _cluster_cases(golden_dir):
+        kept = ors.cluster_suppression(cands, list(vecs), c["threshold"], c["keep_per_cluster"])
+        assert [k["note_id"] for k in kept] == c["kept"]
+        n += 1
+    assert n == 16
