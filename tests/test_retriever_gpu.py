@@ -67,3 +67,53 @@ def test_build_search_retrieve_and_hybrid(tmp_path):
            [n["note_id"] for n in vr.search_single(queries[2], top_k=3)]
     vr.cleanup(); vr2.cleanup()
     config.reset()
+
+
+def test_rebuild_cli_full_incremental_and_triggers(tmp_path):
+    """vector_store/rebuild_vector_index.py:127-190 on the device path: triggers (:88-119), full rebuild with faiss-format
+    artefacts on disk, incremental rebuild in batches, the smoke queries of :262-272, exit codes of main()."""
+    import json
+    import os
+    import time
+    import types
+    import ano_rag_b200  # noqa: F401
+    from ano_rag_b200.config import config
+    from ano_rag_b200.vector_store import VectorRetriever, rebuild_vector_index as rvi
+    from ano_rag_b200.vector_store.embedding_stub import HashingEmbeddingManager
+    config.reset()
+    config.update({"storage": {"vector_store_path": str(tmp_path / "store"), "vector_index_path": str(tmp_path / "ix")},
+                   "vector_store": {"similarity_threshold": 0.0},
+                   "embedding_strategy": {"index_rebuilding": {"batch_size": 64, "rebuild_triggers": {"note_count_threshold": 250}}}})
+    notes = make_notes(300)
+    # triggers
+    assert rvi.should_rebuild_index(notes) and not rvi.should_rebuild_index(notes[:100])
+    old = types.SimpleNamespace(created_at=time.time() - 200 * 3600, metadata={"config_hash": rvi._calculate_config_hash()})
+    fresh = types.SimpleNamespace(created_at=time.time(), metadata={"config_hash": rvi._calculate_config_hash()})
+    stale_cfg = types.SimpleNamespace(created_at=time.time(), metadata={"config_hash": "other"})
+    strat = lambda v: types.SimpleNamespace(current_version_id="v1", versions={"v1": v})
+    assert rvi.should_rebuild_index(notes[:100], strat(old)) and rvi.should_rebuild_index(notes[:100], strat(stale_cfg))
+    assert not rvi.should_rebuild_index(notes[:100], strat(fresh))
+    # nothing to do -> True without touching the retriever
+    assert rvi.rebuild_vector_index(notes[:100], retriever=None, embedding_strategy=strat(fresh)) is True
+    # full rebuild
+    vr = VectorRetriever(embedding_manager=HashingEmbeddingManager(96))
+    assert rvi.rebuild_vector_index(notes, save_index=True, force_rebuild=True, retriever=vr)
+    assert vr.vector_index.total_vectors == 300 and len(rvi._test_retrieval(vr)) == 3
+    saved = os.listdir(str(tmp_path / "store")) + os.listdir(str(tmp_path / "ix"))
+    assert any(f.endswith(".faiss") for f in saved)
+    # incremental: 300 notes in batches of 64 on top of an empty retriever == the full build's results
+    vr2 = VectorRetriever(embedding_manager=HashingEmbeddingManager(96))
+    assert rvi.rebuild_vector_index(notes, incremental=True, retriever=vr2) and vr2.vector_index.total_vectors == 300
+    a = vr.search(["honey bees dance"], top_k=5)[0]
+    b = vr2.search(["honey bees dance"], top_k=5)[0]
+    assert [n["note_id"] for n in a] == [n["note_id"] for n in b]
+    # a failing retriever -> False, never raises
+    bad = types.SimpleNamespace(build_index=lambda **k: (_ for _ in ()).throw(RuntimeError("boom")))
+    assert rvi.rebuild_vector_index(notes, force_rebuild=True, retriever=bad) is False
+    # main(): loaders and exit codes
+    p = tmp_path / "notes.jsonl"
+    p.write_text("\n".join(json.dumps(n) for n in notes[:20]))
+    assert len(rvi.load_atomic_notes(str(p))) == 20
+    assert rvi.main(["--data_path", str(p), "--dry_run"]) == 0
+    assert rvi.main(["--data_path", str(tmp_path / "missing.json")]) == 1
+    vr.cleanup(); vr2.cleanup()
