@@ -1127,18 +1127,25 @@ static int batch_chunk(const Bm25Dev& ix, const int32_t* d_terms, int64_t nq, in
     ARB_LAUNCH_OK();
     bm25_bt_fill_kernel<<<static_cast<unsigned>((nq * sc.qs + 255) / 256), 256, 0, st>>>(nq * sc.qs, sc);
     ARB_LAUNCH_OK();
-    // ---- 1. member pass in rounds of growing size (fractions of the tiles, in 64ths), a compaction after each
-    std::vector<int> cuts;
-    if (ix.n_tiles <= 8) cuts = {64};
-    else if (ix.n_tiles < 1024) cuts = {4, 16, 64};              // shards of up to 256 K docs: a round costs more than it prunes
-    else cuts = {1, 4, 16, 32, 64};
-    if (const char* v = std::getenv("ARB_BM25_ROUNDS")) { if (atoi(v) == 1) cuts = {64}; }
+    // ---- 1. member pass in rounds of growing size, a compaction after each.  The first round runs without a bound, so
+    // every member with a positive score is a candidate: it covers ~64 tiles (16 K docs) whatever the corpus size, which
+    // keeps even heavy queries below C_CAP; each later round covers 4x (the last two 2x) the docs before it, so with the
+    // bound of the rounds before it a query collects ~3k (~k) new candidates per round, independent of the corpus size.
+    std::vector<int64_t> cuts;                                   // ascending round ends, in tiles
+    if (ix.n_tiles <= 8) cuts = {ix.n_tiles};
+    else if (ix.n_tiles < 1024) cuts = {(ix.n_tiles * 4 + 63) / 64, (ix.n_tiles * 16 + 63) / 64, ix.n_tiles};   // shards of up to 256 K docs: a round costs more than it prunes
+    else {
+      cuts = {ix.n_tiles, (ix.n_tiles + 1) / 2};
+      for (int64_t c = (ix.n_tiles + 3) / 4; ; c = (c + 3) / 4) { cuts.push_back(c); if (c <= 64) break; }
+      std::reverse(cuts.begin(), cuts.end());
+    }
+    if (const char* v = std::getenv("ARB_BM25_ROUNDS")) { if (atoi(v) == 1) cuts = {ix.n_tiles}; }
     const int mj_ch = static_cast<int>(std::min<size_t>(MJ_CH_MAX, ((SMEM_MAX - mj_fixed_bytes(ix.n_planes)) / 12 - 4) & ~size_t(3)));
     const size_t mj_smem = mj_fixed_bytes(ix.n_planes) + static_cast<size_t>(mj_ch + 4) * 12;
     int64_t prev = 0;
     const int dbg = std::getenv("ARB_BM25_DEBUG") ? atoi(std::getenv("ARB_BM25_DEBUG")) : 0;   // timing experiments only (wrong results)
     for (size_t r = 0; r < cuts.size(); ++r) {
-      const int64_t hi = cuts[r] == 64 ? ix.n_tiles : std::max(prev, (ix.n_tiles * cuts[r] + 63) / 64);
+      const int64_t hi = std::max(prev, cuts[r]);
       const bool last = r + 1 == cuts.size();
       if (hi > prev) {
         int sub = 1;

@@ -209,19 +209,12 @@ class VectorIndex:
                 scores, indices = scores.cpu().numpy(), indices.cpu().numpy()
             if self._id_table is not None:                                                  # ids given to add_vectors (:187-193)
                 indices = np.where(indices >= 0, self._id_table[np.clip(indices, 0, len(self._id_table) - 1)], -1)
-            scores_l, indices_l = scores.tolist(), indices.tolist()
-            results = []
-            for query_idx in range(len(indices_l)):                                         # :227-253
-                query_results = []
-                row_i, row_s = indices_l[query_idx], scores_l[query_idx]
-                for rank in range(min(top_k, len(row_i))):
-                    idx = row_i[rank]
-                    if idx == -1:
-                        continue
-                    score = row_s[rank]
-                    query_results.append({"index": int(idx), "score": float(score), "rank": rank,
-                                          "similarity": float(score)})
-                results.append(query_results)
+            # :227-253 -- one dict per hit, rank = position in the kernel's list, -1 slots skipped.  tolist() hands back
+            # Python ints / floats, so the comprehension is the whole shaping cost (nq * k dict constructions)
+            k_eff = min(top_k, indices.shape[1])
+            results = [[{"index": idx, "score": sc, "rank": rank, "similarity": sc}
+                        for rank, (idx, sc) in enumerate(zip(row_i, row_s)) if idx != -1]
+                       for row_i, row_s in zip(indices[:, :k_eff].tolist(), scores[:, :k_eff].tolist())]
             if len(results) == 1:                                                           # :256-257
                 return results[0]
             return results
