@@ -145,6 +145,8 @@ __device__ __forceinline__ void cta_sort_desc(unsigned long long* key, IdT* id, 
 
 
 constexpr uint32_t SLOT_NONE = 127u;
+constexpr int MJ_ROW_BYTES = (PLANE_TILE + 4) * 4;     // padded fp32 plane rows of the member pass: 1040 B keeps bulk copies 16-byte aligned
+__host__ __device__ __forceinline__ int rec_int4s(int qs) { return 2 + (qs >> 1); }   // int4 words of a query-term record
 constexpr int MJ_BLOOM_W = BLOOM_W;                  // bm25.cuh: the per-doc filters are part of the index
 
 // ----------------------------------------------------------------------------
@@ -183,59 +185,60 @@ bm25_bt_alloc_kernel(int64_t n, const BatchScratch sc) {
 }
 
 // One record per sparse query token, grouped by term: everything the member pass needs to score the token's query
-// against a doc arrives with ONE load -- {query << 5 | position, -, bound of the current round (8 B)} followed by
-// one entry per query token: plane slot (bits 0-6, 127 = none) | filter word of a sparse term (bits 7-10, the record's
-// OWN token and non-sparse tokens carry word 0 with the never-set mask bit) | up to three bit positions inside the
-// word (11-15, 16-20, 21-25; 31 = none).  The member pass evaluates every entry the same way, without branching on the token kind; the
-// exact path reads the term ids from qinfo.  rec_of remembers where a query's records went (the compaction updates
-// their bound).
+// against a doc arrives DECODED -- int4 #0 {query << 5 | position, bitmap of the plane tokens, bound of the current round
+// (8 B)}, int4 #1 {bitmap of the query's OTHER sparse tokens}, then 8 bytes per query token: {byte offset of its plane
+// row in the staged tile (bits 0-16; the zero row when it is no plane term) | byte offset of its filter word (17-22) |
+// plane slot (23-29, 127 = none), filter mask (one to three bits; bit 31, never set in a filter, for tokens that are not
+// another sparse term)}.  The member pass starts a new record every few pairs, with a third of its lanes: decoding there
+// cost as many issue slots as scoring.  rec_of remembers where a query's records went (the compaction updates their bound).
 __global__ void __launch_bounds__(256)
-bm25_bt_fill_kernel(int64_t n, const BatchScratch sc) {
+bm25_bt_fill_kernel(int64_t n, const BatchScratch sc, int n_planes) {
   const int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
   if (i >= n) return;
   const int code = sc.qinfo[i];
   if (code < 0) { sc.rec_of[i] = 0xFFFFFFFFu; return; }
   const int64_t q = i / sc.qs;
+  const int own = static_cast<int>(i - q * sc.qs);
   const uint32_t at = sc.bt_ent[code].x + atomicAdd(sc.bt_cur + code, 1u) - 1u;
   sc.rec_of[i] = at;
-  const int rs4 = 1 + (sc.qs >> 2);
-  int4* rec = sc.bt_rec + static_cast<size_t>(at) * rs4;
-  const unsigned long long b0 = f64_key(0.0);
-  rec[0] = make_int4(static_cast<int>(static_cast<uint32_t>(q << 5) | static_cast<uint32_t>(i - q * sc.qs)), 0,
-                     static_cast<int>(static_cast<uint32_t>(b0)), static_cast<int>(static_cast<uint32_t>(b0 >> 32)));
+  int4* rec = sc.bt_rec + static_cast<size_t>(at) * rec_int4s(sc.qs);
   const int* src = sc.qinfo + q * sc.qs;
-  for (int j = 0; j < (sc.qs >> 2); ++j) {
-    int f[4];
+  uint32_t plane_bits = 0u, sparse_bits = 0u;
+  for (int j = 0; j < (sc.qs >> 1); ++j) {
+    uint32_t f[4];
 #pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      const int c = src[4 * j + e];
-      uint32_t slot = SLOT_NONE, w = 0u, x = 31u, y = 31u, z = 31u;
-      if (c <= -2) slot = static_cast<uint32_t>(-2 - c);
-      else if (c >= 0 && 4 * j + e != static_cast<int>(i - q * sc.qs)) {
-        const uint32_t m = bloom_mask(static_cast<uint32_t>(c));             // one to three distinct bits
-        w = bloom_word(static_cast<uint32_t>(c));
-        x = __ffs(m) - 1;
-        z = 31 - __clz(m);
-        const uint32_t mid = m & ~(1u << x) & ~(1u << z);
-        y = mid ? __ffs(mid) - 1 : x;
+    for (int e = 0; e < 2; ++e) {
+      const int p = 2 * j + e;
+      const int c = src[p];
+      uint32_t slot = SLOT_NONE, po = static_cast<uint32_t>(n_planes) * MJ_ROW_BYTES, bw = 0u, bm = 1u << 31;
+      if (c <= -2) { slot = static_cast<uint32_t>(-2 - c); po = slot * MJ_ROW_BYTES; plane_bits |= 1u << p; }
+      else if (c >= 0 && p != own) {
+        bm = bloom_mask(static_cast<uint32_t>(c));                             // one to three distinct bits
+        bw = bloom_word(static_cast<uint32_t>(c)) * 4u;
+        sparse_bits |= 1u << p;
       }
-      f[e] = static_cast<int>(slot | (w << 7) | (x << 11) | (y << 16) | (z << 21));
+      f[2 * e] = po | (bw << 17) | (slot << 23);
+      f[2 * e + 1] = bm;
     }
-    rec[1 + j] = make_int4(f[0], f[1], f[2], f[3]);
+    rec[2 + j] = make_int4(static_cast<int>(f[0]), static_cast<int>(f[1]), static_cast<int>(f[2]), static_cast<int>(f[3]));
   }
+  const unsigned long long b0 = f64_key(0.0);
+  rec[0] = make_int4(static_cast<int>(static_cast<uint32_t>(q << 5) | static_cast<uint32_t>(own)), static_cast<int>(plane_bits),
+                     static_cast<int>(static_cast<uint32_t>(b0)), static_cast<int>(static_cast<uint32_t>(b0 >> 32)));
+  rec[1] = make_int4(static_cast<int>(sparse_bits), 0, 0, 0);
 }
 
 // ----------------------------------------------------------------------------
 // 1. member pass
 // ----------------------------------------------------------------------------
 constexpr int MJ_THREADS = 640;
-constexpr int MJ_CH_MAX = 2048;                      // postings joined per chunk (fewer when 96 planes fill shared memory)
+constexpr int MJ_CH_MAX = 2560;                      // postings joined per chunk (4 per thread)
+constexpr int MJ_LAUNCH_TILES = 2048;                 // tiles per member-pass launch
 constexpr int MJ_DEF = 65536;                        // set-aside pairs per CTA and launch, in global scratch (more: finished in place)
-constexpr int MJ_PSTRIDE = PLANE_TILE + 2;           // padded plane rows: threads of a warp mostly read the SAME doc of
-                                                     // different planes; 258 * 8 B keeps bulk copies 16-byte aligned
-// dynamic shared memory of the member pass: [P + 1][MJ_PSTRIDE] fp64 plane rows (row P = zeros, read for tokens that
-// are not plane terms) | bloom [256][12] | pscan [ch + 4] | cbase [ch] | pinfo [ch]
-__host__ __device__ inline size_t mj_fixed_bytes(int P) { return static_cast<size_t>(P + 1) * MJ_PSTRIDE * 8 + PLANE_TILE * MJ_BLOOM_W * 4 + 16; }
+constexpr int MJ_PSTRIDE = MJ_ROW_BYTES / 4;
+// dynamic shared memory of the member pass: [P + 1][MJ_PSTRIDE] fp32 plane rows, rounded up (row P = zeros) |
+// bloom [256][16] | pscan [ch + 4] | cbase [ch] | pinfo [ch]
+__host__ __device__ inline size_t mj_fixed_bytes(int P) { return static_cast<size_t>(P + 1) * MJ_PSTRIDE * 4 + PLANE_TILE * MJ_BLOOM_W * 4 + 16; }
 // index of term c in the ascending list dt[0, n), or -1
 __device__ __forceinline__ int row_find(const uint32_t* __restrict__ dt, int n, uint32_t c) {
   int lo = 0, hi = n;
@@ -291,8 +294,8 @@ __device__ __forceinline__ void exact_pair(const ExactArgs& ea, PlaneFn plane, i
   double acc = 0.0;
   bool dup = false, matched = false;
   for (int pp = 0; pp < ea.qs; ++pp) {
-    const uint32_t f = static_cast<uint32_t>(__ldg(reinterpret_cast<const int*>(rec + 1) + pp));
-    double v = (f & 127u) == SLOT_NONE ? 0.0 : plane(f & 127u);
+    const uint32_t slot = (static_cast<uint32_t>(__ldg(reinterpret_cast<const int*>(rec + 2) + 2 * pp)) >> 23) & 127u;
+    double v = slot == SLOT_NONE ? 0.0 : plane(slot);
     if (pp == pos) v = myval;
     if ((hits >> pp) & 1u) {
       const int idx = row_find(ea.drow_term + r0, row_n, static_cast<uint32_t>(__ldg(ea.qinfo + q * ea.qs + pp)));
@@ -303,17 +306,18 @@ __device__ __forceinline__ void exact_pair(const ExactArgs& ea, PlaneFn plane, i
   if (ea.tp_count && matched) atomicAdd(ea.tp_count, 1);       // diagnostics
   if (!dup) member_emit(ea, q, acc, (static_cast<unsigned long long>(static_cast<uint32_t>(hd.w)) << 32) | static_cast<uint32_t>(hd.z), d);
 }
-// in place (a full queue): planes from the staged tile
-__device__ __noinline__ void member_exact(const ExactArgs ea, const double* pl_doc, int64_t d, double myval,
+// in place (a full queue): fp64 planes from global memory, pt = the doc's entry in plane 0 of its tile
+__device__ __noinline__ void member_exact(const ExactArgs ea, const double* __restrict__ pt, int64_t d, double myval,
                                           const int4* __restrict__ rec, uint32_t hits) {
-  exact_pair(ea, [&](uint32_t slot) { return pl_doc[slot * MJ_PSTRIDE]; }, d, myval, rec, hits);
+  exact_pair(ea, [&](uint32_t slot) { return __ldg(pt + slot * PLANE_TILE); }, d, myval, rec, hits);
 }
 
 // The set-aside pairs of a member-pass launch, one per thread, thousands in flight per SM: chains of dependent loads
 // that would idle a persistent CTA.  grid (x, member-pass CTAs); planes are read from global memory.
 struct MjDefer { uint32_t posting, rec, hits, tile; };
 __global__ void __launch_bounds__(256)
-bm25_member_exact_kernel(const Bm25Dev ix, const BatchScratch sc, int rs4) {
+bm25_member_exact_kernel(const Bm25Dev ix, const BatchScratch sc) {
+  const int rs4 = rec_int4s(sc.qs);
   const MjDefer* defer = sc.defer + static_cast<size_t>(blockIdx.y) * MJ_DEF;
   const int n = min(sc.def_cnt[blockIdx.y], MJ_DEF);
   const ExactArgs ea{ix.drow_off, ix.drow_term, ix.drow_val, sc.qinfo, sc.c_key, sc.c_doc, sc.c_cnt, sc.n_nonpos, sc.qs, ix.n_planes,
@@ -332,18 +336,21 @@ bm25_member_exact_kernel(const Bm25Dev ix, const BatchScratch sc, int rs4) {
 // (term-major: the postings of a term inside the tile form a run), count the (record, doc) pairs per run
 // (records of the term in the batch x docs of the run), scan, and give every thread an equal, contiguous range of
 // pairs in run-major / record-major order: the thread decodes a record into registers once and applies it to every
-// doc of the run.  The complete score of (query of the record, doc) is summed in query-token order: plane tokens from
-// the staged tile, the record's own token from the posting, +0.0 for every other sparse token of the query -- unless
-// the doc's filter says one of them may be present: those pairs are set aside with the positions in question and
-// queued for bm25_member_exact_kernel.  QS = tokens per query rounded up to 4 (<= 32).
+// doc of the run.  The pair is SCREENED in fp32: the staged tile holds the planes rounded up to fp32, the record's own
+// token comes from the posting (rounded up), every other sparse token adds +0.0, and the sum runs in query-token order
+// with upward rounding -- a rigorous upper bound of the in-order fp64 score (fp64 rounding is monotone), at half the
+// shared-memory bytes of an fp64 tile.  Only pairs whose bound exceeds the query's running bound -- a few hundred per
+// query and round -- and pairs where the doc's filter says another sparse token of the query may be present (with the
+// positions in question) are queued for bm25_member_exact_kernel, which computes the exact fp64 score.
+// QS = tokens per query rounded up to 4 (<= 32).
 template <int QS>
 __global__ void __launch_bounds__(MJ_THREADS, 1)
 bm25_member_kernel(const Bm25Dev ix, const BatchScratch sc, int64_t tile_lo, int64_t tile_hi, int sub, int ch, int dbg) {
   extern __shared__ __align__(16) uint8_t mj_smem[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int P = ix.n_planes;
-  double* pl = reinterpret_cast<double*>(mj_smem);                                 // [P + 1][MJ_PSTRIDE]
-  uint32_t* bloom = reinterpret_cast<uint32_t*>(mj_smem + static_cast<size_t>(P + 1) * MJ_PSTRIDE * 8);   // [256][12]
+  float* pl = reinterpret_cast<float*>(mj_smem);                                   // [P + 1][MJ_PSTRIDE]
+  uint32_t* bloom = reinterpret_cast<uint32_t*>(mj_smem + static_cast<size_t>(P + 1) * MJ_PSTRIDE * 4);   // [256][16]
   uint32_t* pscan = bloom + PLANE_TILE * MJ_BLOOM_W;                               // [ch + 4] exclusive scan of the runs' pair counts
   uint32_t* cbase = pscan + ch + 4;                                                // [ch] first record of a run's term (at its head)
   uint32_t* pinfo = cbase + ch;                                                    // [ch] doc in tile | run length << 8 | head << 31
@@ -352,12 +359,11 @@ bm25_member_kernel(const Bm25Dev ix, const BatchScratch sc, int64_t tile_lo, int
   __shared__ uint32_t wsum[32];
   __shared__ int n_def_s;
   if (tid == 0) { ptx::mbar_init(&fill_bar, 1); ptx::fence_barrier_init(); n_def_s = 0; }
-  for (int i = tid; i < MJ_PSTRIDE; i += MJ_THREADS) pl[static_cast<size_t>(P) * MJ_PSTRIDE + i] = 0.0;
+  for (int i = tid; i < MJ_PSTRIDE; i += MJ_THREADS) pl[static_cast<size_t>(P) * MJ_PSTRIDE + i] = 0.0f;
   constexpr uint32_t BLOOM_BYTES = PLANE_TILE * MJ_BLOOM_W * 4u;
   uint32_t fill_phase = 0;
   const int64_t units = (tile_hi - tile_lo) * sub;
-  constexpr int RS4 = 1 + QS / 4;
-  const uint32_t zero_off = static_cast<uint32_t>(P) * MJ_PSTRIDE * 8u;
+  constexpr int RS4 = 2 + QS / 2;
   const ExactArgs ea{ix.drow_off, ix.drow_term, ix.drow_val, sc.qinfo, sc.c_key, sc.c_doc, sc.c_cnt, sc.n_nonpos, sc.qs, P, nullptr};
   for (int64_t u = blockIdx.x; u < units; u += gridDim.x) {
     const int64_t tile = tile_lo + u / sub;
@@ -368,14 +374,14 @@ bm25_member_kernel(const Bm25Dev ix, const BatchScratch sc, int64_t tile_lo, int
       // are issued by the 32 lanes side by side, all completing on one mbarrier
       ptx::fence_proxy_async_smem();                            // every issuing lane: earlier generic reads before its async writes
       if (lane == 0) {
-        ptx::mbar_expect_tx(&fill_bar, static_cast<uint32_t>(P) * PLANE_TILE * 8u + BLOOM_BYTES);
+        ptx::mbar_expect_tx(&fill_bar, static_cast<uint32_t>(P) * PLANE_TILE * 4u + BLOOM_BYTES);
         ptx::bulk_load_1d(bloom, ix.tt_bloom + tile * (PLANE_TILE * MJ_BLOOM_W), BLOOM_BYTES, &fill_bar);
       }
       __syncwarp();
-      const char* src = reinterpret_cast<const char*>(ix.planes + tile * P * PLANE_TILE);
+      const char* src = reinterpret_cast<const char*>(ix.planes32 + tile * P * PLANE_TILE);
       for (int r = lane; r < P; r += 32)
-        ptx::bulk_load_1d(mj_smem + static_cast<size_t>(r) * MJ_PSTRIDE * 8, src + static_cast<size_t>(r) * PLANE_TILE * 8,
-                          PLANE_TILE * 8u, &fill_bar);
+        ptx::bulk_load_1d(mj_smem + static_cast<size_t>(r) * MJ_PSTRIDE * 4, src + static_cast<size_t>(r) * PLANE_TILE * 4,
+                          PLANE_TILE * 4u, &fill_bar);
     }
     const uint32_t t_lo = __ldg(ix.tt_off + tile), t_hi = __ldg(ix.tt_off + tile + 1);
     ptx::mbar_wait(&fill_bar, fill_phase);
@@ -467,7 +473,7 @@ bm25_member_kernel(const Bm25Dev ix, const BatchScratch sc, int64_t tile_lo, int
         uint32_t po[QS], bw[QS], bm[QS];
         uint32_t own_bit = 0u, plane_bits = 0u, sparse_bits = 0u, r = 0u;
         int64_t q = 0;
-        unsigned long long bound = 0ull;
+        double bound_d = 0.0;
         for (; j < j_end; ++j) {
           if (fresh) {
             fresh = false;
@@ -475,46 +481,48 @@ bm25_member_kernel(const Bm25Dev ix, const BatchScratch sc, int64_t tile_lo, int
             const int4* rec = sc.bt_rec + static_cast<size_t>(r) * RS4;
             const int4 hd = __ldg(rec);
             ptx::prefetch_l1(rec + RS4);                       // the next record of the run (records of a term are contiguous)
-            plane_bits = 0u; sparse_bits = 0u;
+            plane_bits = static_cast<uint32_t>(hd.y);
+            sparse_bits = static_cast<uint32_t>(__ldg(reinterpret_cast<const int*>(rec + 1)));
 #pragma unroll
-            for (int p4 = 0; p4 < QS / 4; ++p4) {
-              const int4 c4 = __ldg(rec + 1 + p4);
-              const uint32_t ee[4] = {static_cast<uint32_t>(c4.x), static_cast<uint32_t>(c4.y), static_cast<uint32_t>(c4.z), static_cast<uint32_t>(c4.w)};
-#pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                const uint32_t f = ee[e], slot = f & 127u;
-                po[4 * p4 + e] = slot == SLOT_NONE ? zero_off : slot * (MJ_PSTRIDE * 8u);
-                bw[4 * p4 + e] = ((f >> 7) & 15u) * 4u;
-                bm[4 * p4 + e] = (1u << ((f >> 11) & 31u)) | (1u << ((f >> 16) & 31u)) | (1u << ((f >> 21) & 31u));
-                if (slot != SLOT_NONE) plane_bits |= 1u << (4 * p4 + e);
-                if (((f >> 11) & 31u) != 31u) sparse_bits |= 1u << (4 * p4 + e);
-              }
+            for (int p2 = 0; p2 < QS / 2; ++p2) {
+              const int4 c4 = __ldg(rec + 2 + p2);
+              po[2 * p2] = static_cast<uint32_t>(c4.x) & 0x1FFFFu;
+              bw[2 * p2] = (static_cast<uint32_t>(c4.x) >> 17) & 63u;
+              bm[2 * p2] = static_cast<uint32_t>(c4.y);
+              po[2 * p2 + 1] = static_cast<uint32_t>(c4.z) & 0x1FFFFu;
+              bw[2 * p2 + 1] = (static_cast<uint32_t>(c4.z) >> 17) & 63u;
+              bm[2 * p2 + 1] = static_cast<uint32_t>(c4.w);
             }
             own_bit = 1u << (hd.x & 31);
             q = static_cast<uint32_t>(hd.x) >> 5;
-            bound = (static_cast<unsigned long long>(static_cast<uint32_t>(hd.w)) << 32) | static_cast<uint32_t>(hd.z);
+            bound_d = key_f64((static_cast<unsigned long long>(static_cast<uint32_t>(hd.w)) << 32) | static_cast<uint32_t>(hd.z));
           }
           const int i = i0 + di;
           const int dl = pinfo[i] & 0xFF;
           const double myval = __ldg(ix.tt_val + c0 + i);
-          const char* pl_doc = reinterpret_cast<const char*>(pl + plane_pos(static_cast<uint32_t>(dl)));
+          const char* pl_doc = reinterpret_cast<const char*>(pl + pos32(static_cast<uint32_t>(dl)));
           const char* brow = reinterpret_cast<const char*>(bloom + dl * MJ_BLOOM_W);
-          double acc = 0.0;
+          const float myub = __double2float_ru(myval);
+          float ub = 0.0f;
           uint32_t hits = 0u;
 #pragma unroll
           for (int p = 0; p < QS; ++p) {
             // only real plane / sparse tokens touch shared memory: random addresses across a warp, fewer lanes = fewer bank conflicts
-            double v = 0.0;
-            if (plane_bits & (1u << p)) v = *reinterpret_cast<const double*>(pl_doc + po[p]);
-            if (own_bit & (1u << p)) v = myval;
-            acc = __dadd_rn(acc, v);                                         // (the sum is never -0.0: adding +0.0 changes nothing)
+            if (plane_bits & (1u << p)) ub = __fadd_ru(ub, *reinterpret_cast<const float*>(pl_doc + po[p]));
+            if (own_bit & (1u << p)) ub = __fadd_ru(ub, myub);
             if ((sparse_bits & (1u << p)) && (*reinterpret_cast<const uint32_t*>(brow + bw[p]) & bm[p]) == bm[p]) hits |= 1u << p;
           }
-          if (hits == 0u) { if (!(dbg & 2)) member_emit(sc, q, acc, bound, doc_base + dl); else if (acc == 123.0) sc.c_cnt[0] = 1; }
-          else if (!(dbg & 1)) {
+          // ub >= the exact score when no other sparse token matches.  A doc that may match another one (hits) or whose
+          // bound beats the query's running bound gets its exact fp64 score from the queue's kernel; a bound that is not
+          // positive settles the pair as a member that can never be a candidate.
+          const bool maybe = hits != 0u || static_cast<double>(ub) > bound_d;
+          if (maybe && !(dbg & 1)) {
             const int at = atomicAdd(&n_def_s, 1);
             if (at < MJ_DEF) *reinterpret_cast<uint4*>(defer + at) = make_uint4(c0 + i, r, hits, static_cast<uint32_t>(tile));
-            else member_exact(ea, reinterpret_cast<const double*>(pl_doc), doc_base + dl, myval, sc.bt_rec + static_cast<size_t>(r) * RS4, hits);
+            else member_exact(ea, ix.planes + tile * P * PLANE_TILE + plane_pos(static_cast<uint32_t>(dl)), doc_base + dl, myval,
+                              sc.bt_rec + static_cast<size_t>(r) * RS4, hits);
+          } else if (!maybe && !(ub > 0.0f)) {
+            atomicAdd(sc.n_nonpos + q, 1);
           }
           if (++di == len) {                                   // next record of the run, or the next run that has records
             di = 0;
@@ -552,7 +560,7 @@ bm25_compact_kernel(int64_t nq, int k, int last, const BatchScratch sc) {
   const int raw = sc.c_cnt[q];
   const bool ovf = sc.ovf[q] != 0 || raw > C_CAP;
   auto publish = [&](unsigned long long bound) {              // the next round reads the bound from the query's records
-    const int rs4 = 1 + (sc.qs >> 2);
+    const int rs4 = rec_int4s(sc.qs);
     if (tid < sc.qs) {
       const uint32_t r = sc.rec_of[q * sc.qs + tid];
       if (r != 0xFFFFFFFFu)
@@ -1074,7 +1082,7 @@ static int batch_chunk(const Bm25Dev& ix, const int32_t* d_terms, int64_t nq, in
   const size_t nt = static_cast<size_t>(std::max<int64_t>(ix.n_terms, 1));
   ARB_CUDA(b_qinfo.alloc(static_cast<size_t>(nq) * sc.qs * 4, st));
   ARB_CUDA(b_bt.alloc(3 * nt * 4, st));                                             // bt_ent | bt_cur
-  ARB_CUDA(b_pair.alloc(static_cast<size_t>(nq) * sc.qs * (16 + sc.qs * 4) + static_cast<size_t>(nq) * sc.qs * 4, st));   // bt_rec | rec_of
+  ARB_CUDA(b_pair.alloc(static_cast<size_t>(nq) * sc.qs * (32 + sc.qs * 8) + static_cast<size_t>(nq) * sc.qs * 4, st));   // bt_rec | rec_of
   ARB_CUDA(b_ckey.alloc(static_cast<size_t>(nq) * C_CAP * 8, st));
   ARB_CUDA(b_cdoc.alloc(static_cast<size_t>(nq) * C_CAP * 4, st));
   ARB_CUDA(b_akey.alloc(static_cast<size_t>(nq) * k * 8, st));
@@ -1086,7 +1094,7 @@ static int batch_chunk(const Bm25Dev& ix, const int32_t* d_terms, int64_t nq, in
   sc.bt_ent = b_bt.as<uint2>();
   sc.bt_cur = b_bt.as<uint32_t>() + 2 * nt;
   sc.bt_rec = b_pair.as<int4>();
-  sc.rec_of = reinterpret_cast<uint32_t*>(reinterpret_cast<uint8_t*>(b_pair.p) + static_cast<size_t>(nq) * sc.qs * (16 + sc.qs * 4));
+  sc.rec_of = reinterpret_cast<uint32_t*>(reinterpret_cast<uint8_t*>(b_pair.p) + static_cast<size_t>(nq) * sc.qs * (32 + sc.qs * 8));
   sc.c_key = b_ckey.as<unsigned long long>();
   sc.c_doc = b_cdoc.as<uint32_t>();
   sc.a_key = b_akey.as<unsigned long long>();
@@ -1125,7 +1133,7 @@ static int batch_chunk(const Bm25Dev& ix, const int32_t* d_terms, int64_t nq, in
     ARB_LAUNCH_OK();
     bm25_bt_alloc_kernel<<<static_cast<unsigned>((nq * sc.qs + 255) / 256), 256, 0, st>>>(nq * sc.qs, sc);
     ARB_LAUNCH_OK();
-    bm25_bt_fill_kernel<<<static_cast<unsigned>((nq * sc.qs + 255) / 256), 256, 0, st>>>(nq * sc.qs, sc);
+    bm25_bt_fill_kernel<<<static_cast<unsigned>((nq * sc.qs + 255) / 256), 256, 0, st>>>(nq * sc.qs, sc, ix.n_planes);
     ARB_LAUNCH_OK();
     // ---- 1. member pass in rounds of growing size, a compaction after each.  The first round runs without a bound, so
     // every member with a positive score is a candidate: it covers ~64 tiles (16 K docs) whatever the corpus size, which
@@ -1147,18 +1155,21 @@ static int batch_chunk(const Bm25Dev& ix, const int32_t* d_terms, int64_t nq, in
     for (size_t r = 0; r < cuts.size(); ++r) {
       const int64_t hi = std::max(prev, cuts[r]);
       const bool last = r + 1 == cuts.size();
-      if (hi > prev) {
+      // a launch covers at most MJ_LAUNCH_TILES tiles: its queue of pairs for the exact kernel (MJ_DEF per CTA) then
+      // holds what a cfg3-sized round produces, whatever the corpus size
+      for (int64_t lo = prev; lo < hi; lo += MJ_LAUNCH_TILES) {
+        const int64_t lhi = std::min<int64_t>(hi, lo + MJ_LAUNCH_TILES);
         int sub = 1;
-        while (sub < 8 && (hi - prev) * sub < sms) sub <<= 1;
-        const unsigned grid = static_cast<unsigned>(std::min<int64_t>((hi - prev) * sub, sms));
+        while (sub < 8 && (lhi - lo) * sub < sms) sub <<= 1;
+        const unsigned grid = static_cast<unsigned>(std::min<int64_t>((lhi - lo) * sub, sms));
         switch (sc.qs) {
-#define ARB_MJ(QS_) case QS_: bm25_member_kernel<QS_><<<grid, MJ_THREADS, mj_smem, st>>>(ix, sc, prev, hi, sub, mj_ch, dbg); break;
+#define ARB_MJ(QS_) case QS_: bm25_member_kernel<QS_><<<grid, MJ_THREADS, mj_smem, st>>>(ix, sc, lo, lhi, sub, mj_ch, dbg); break;
           ARB_MJ(4) ARB_MJ(8) ARB_MJ(12) ARB_MJ(16) ARB_MJ(20) ARB_MJ(24) ARB_MJ(28) ARB_MJ(32)
 #undef ARB_MJ
           default: set_error("bm25 batch: more than 32 tokens per query"); return ARB_ELIMIT;
         }
         ARB_LAUNCH_OK();
-        bm25_member_exact_kernel<<<dim3(32, grid), 256, 0, st>>>(ix, sc, 1 + sc.qs / 4);
+        bm25_member_exact_kernel<<<dim3(32, grid), 256, 0, st>>>(ix, sc);
         ARB_LAUNCH_OK();
       }
       if (hi > prev || last) {
