@@ -283,7 +283,7 @@ struct ExactArgs {
   const uint32_t* drow_off; const uint32_t* drow_term; const double* drow_val; const int32_t* qinfo;
   unsigned long long* c_key; uint32_t* c_doc; int* c_cnt; int* n_nonpos; int qs, n_planes; int* tp_count;
 };
-template <class PlaneFn>
+template <int QS, class PlaneFn>
 __device__ __forceinline__ void exact_pair(const ExactArgs& ea, PlaneFn plane, int64_t d, double myval, const int4* __restrict__ rec,
                                            uint32_t hits) {
   const int4 hd = __ldg(rec);
@@ -291,43 +291,62 @@ __device__ __forceinline__ void exact_pair(const ExactArgs& ea, PlaneFn plane, i
   const int pos = hd.x & 31;
   const uint32_t r0 = __ldg(ea.drow_off + d);
   const int row_n = static_cast<int>(__ldg(ea.drow_off + d + 1) - r0);
+  // a match at an earlier position: the pair belongs to that position's record -- settled before any plane is read
+  for (uint32_t early = hits & ((1u << pos) - 1u); early != 0u; early &= early - 1u) {
+    const int pp = __ffs(early) - 1;
+    if (row_find(ea.drow_term + r0, row_n, static_cast<uint32_t>(__ldg(ea.qinfo + q * QS + pp))) >= 0) {
+      if (ea.tp_count) atomicAdd(ea.tp_count, 1);              // diagnostics
+      return;
+    }
+  }
+  hits &= ~((2u << pos) - 1u);                                 // earlier positions did not match: they add +0.0
+  // every plane value of the pair is requested before the first one is used (independent addresses: the loads overlap)
+  double pv[QS];
+#pragma unroll
+  for (int p2 = 0; p2 < QS / 2; ++p2) {
+    const int4 c4 = __ldg(rec + 2 + p2);
+    const uint32_t s0 = (static_cast<uint32_t>(c4.x) >> 23) & 127u, s1 = (static_cast<uint32_t>(c4.z) >> 23) & 127u;
+    pv[2 * p2] = s0 == SLOT_NONE ? 0.0 : plane(s0);
+    pv[2 * p2 + 1] = s1 == SLOT_NONE ? 0.0 : plane(s1);
+  }
   double acc = 0.0;
-  bool dup = false, matched = false;
-  for (int pp = 0; pp < ea.qs; ++pp) {
-    const uint32_t slot = (static_cast<uint32_t>(__ldg(reinterpret_cast<const int*>(rec + 2) + 2 * pp)) >> 23) & 127u;
-    double v = slot == SLOT_NONE ? 0.0 : plane(slot);
+  bool matched = false;
+#pragma unroll
+  for (int pp = 0; pp < QS; ++pp) {
+    double v = pv[pp];
     if (pp == pos) v = myval;
     if ((hits >> pp) & 1u) {
-      const int idx = row_find(ea.drow_term + r0, row_n, static_cast<uint32_t>(__ldg(ea.qinfo + q * ea.qs + pp)));
-      if (idx >= 0) { matched = true; if (pp < pos) dup = true; else v = __ldg(ea.drow_val + r0 + idx); }
+      const int idx = row_find(ea.drow_term + r0, row_n, static_cast<uint32_t>(__ldg(ea.qinfo + q * QS + pp)));
+      if (idx >= 0) { matched = true; v = __ldg(ea.drow_val + r0 + idx); }
     }
     acc = __dadd_rn(acc, v);
   }
   if (ea.tp_count && matched) atomicAdd(ea.tp_count, 1);       // diagnostics
-  if (!dup) member_emit(ea, q, acc, (static_cast<unsigned long long>(static_cast<uint32_t>(hd.w)) << 32) | static_cast<uint32_t>(hd.z), d);
+  member_emit(ea, q, acc, (static_cast<unsigned long long>(static_cast<uint32_t>(hd.w)) << 32) | static_cast<uint32_t>(hd.z), d);
 }
 // in place (a full queue): fp64 planes from global memory, pt = the doc's entry in plane 0 of its tile
+template <int QS>
 __device__ __noinline__ void member_exact(const ExactArgs ea, const double* __restrict__ pt, int64_t d, double myval,
                                           const int4* __restrict__ rec, uint32_t hits) {
-  exact_pair(ea, [&](uint32_t slot) { return __ldg(pt + slot * PLANE_TILE); }, d, myval, rec, hits);
+  exact_pair<QS>(ea, [&](uint32_t slot) { return __ldg(pt + slot * PLANE_TILE); }, d, myval, rec, hits);
 }
 
 // The set-aside pairs of a member-pass launch, one per thread, thousands in flight per SM: chains of dependent loads
 // that would idle a persistent CTA.  grid (x, member-pass CTAs); planes are read from global memory.
-struct MjDefer { uint32_t posting, rec, hits, tile; };
+struct __align__(8) MjDefer { uint32_t doc, rec, hits, pad; double myval; };   // the pair's doc and own contribution travel with it
+template <int QS>
 __global__ void __launch_bounds__(256)
 bm25_member_exact_kernel(const Bm25Dev ix, const BatchScratch sc) {
-  const int rs4 = rec_int4s(sc.qs);
+  constexpr int rs4 = 2 + QS / 2;
   const MjDefer* defer = sc.defer + static_cast<size_t>(blockIdx.y) * MJ_DEF;
   const int n = min(sc.def_cnt[blockIdx.y], MJ_DEF);
   const ExactArgs ea{ix.drow_off, ix.drow_term, ix.drow_val, sc.qinfo, sc.c_key, sc.c_doc, sc.c_cnt, sc.n_nonpos, sc.qs, ix.n_planes,
                      sc.stats_on ? sc.counters + 4 : nullptr};
   for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
     const MjDefer de = defer[k];
-    const int dl = __ldg(ix.tt_doc + de.posting);
-    const double* pt = ix.planes + static_cast<int64_t>(de.tile) * ix.n_planes * PLANE_TILE + plane_pos(static_cast<uint32_t>(dl));
-    exact_pair(ea, [&](uint32_t slot) { return __ldg(pt + slot * PLANE_TILE); }, static_cast<int64_t>(de.tile) * PLANE_TILE + dl,
-               __ldg(ix.tt_val + de.posting), sc.bt_rec + static_cast<size_t>(de.rec) * rs4, de.hits);
+    const double* pt = ix.planes + static_cast<int64_t>(de.doc >> PLANE_TILE_LOG2) * ix.n_planes * PLANE_TILE + plane_pos(de.doc & (PLANE_TILE - 1));
+    exact_pair<QS>(ea, [&](uint32_t slot) { return __ldg(pt + slot * PLANE_TILE); }, static_cast<int64_t>(de.doc), de.myval,
+               sc.bt_rec + static_cast<size_t>(de.rec) * rs4, de.hits);
   }
 }
 
@@ -518,8 +537,8 @@ bm25_member_kernel(const Bm25Dev ix, const BatchScratch sc, int64_t tile_lo, int
           const bool maybe = hits != 0u || static_cast<double>(ub) > bound_d;
           if (maybe && !(dbg & 1)) {
             const int at = atomicAdd(&n_def_s, 1);
-            if (at < MJ_DEF) *reinterpret_cast<uint4*>(defer + at) = make_uint4(c0 + i, r, hits, static_cast<uint32_t>(tile));
-            else member_exact(ea, ix.planes + tile * P * PLANE_TILE + plane_pos(static_cast<uint32_t>(dl)), doc_base + dl, myval,
+            if (at < MJ_DEF) { defer[at] = MjDefer{static_cast<uint32_t>(doc_base + dl), r, hits, 0u, myval}; }
+            else member_exact<QS>(ea, ix.planes + tile * P * PLANE_TILE + plane_pos(static_cast<uint32_t>(dl)), doc_base + dl, myval,
                               sc.bt_rec + static_cast<size_t>(r) * RS4, hits);
           } else if (!maybe && !(ub > 0.0f)) {
             atomicAdd(sc.n_nonpos + q, 1);
@@ -1159,17 +1178,23 @@ static int batch_chunk(const Bm25Dev& ix, const int32_t* d_terms, int64_t nq, in
       // holds what a cfg3-sized round produces, whatever the corpus size
       for (int64_t lo = prev; lo < hi; lo += MJ_LAUNCH_TILES) {
         const int64_t lhi = std::min<int64_t>(hi, lo + MJ_LAUNCH_TILES);
+        // a tile is split into `sub` units so that the units fill whole waves of the persistent grid (a unit re-stages
+        // its tile, ~2 us; a half-empty last wave costs a whole wave)
         int sub = 1;
-        while (sub < 8 && (lhi - lo) * sub < sms) sub <<= 1;
+        double best = 0.0;
+        for (int c = 1; c <= 8; ++c) {
+          const int64_t units = (lhi - lo) * c;
+          const double util = static_cast<double>(units) / static_cast<double>((units + sms - 1) / sms * sms);
+          if (util > best + 0.02) { best = util; sub = c; }
+        }
         const unsigned grid = static_cast<unsigned>(std::min<int64_t>((lhi - lo) * sub, sms));
         switch (sc.qs) {
-#define ARB_MJ(QS_) case QS_: bm25_member_kernel<QS_><<<grid, MJ_THREADS, mj_smem, st>>>(ix, sc, lo, lhi, sub, mj_ch, dbg); break;
+#define ARB_MJ(QS_) case QS_: bm25_member_kernel<QS_><<<grid, MJ_THREADS, mj_smem, st>>>(ix, sc, lo, lhi, sub, mj_ch, dbg); \
+                             bm25_member_exact_kernel<QS_><<<dim3(32, grid), 256, 0, st>>>(ix, sc); break;
           ARB_MJ(4) ARB_MJ(8) ARB_MJ(12) ARB_MJ(16) ARB_MJ(20) ARB_MJ(24) ARB_MJ(28) ARB_MJ(32)
 #undef ARB_MJ
           default: set_error("bm25 batch: more than 32 tokens per query"); return ARB_ELIMIT;
         }
-        ARB_LAUNCH_OK();
-        bm25_member_exact_kernel<<<dim3(32, grid), 256, 0, st>>>(ix, sc);
         ARB_LAUNCH_OK();
       }
       if (hi > prev || last) {
