@@ -1178,15 +1178,9 @@ static int batch_chunk(const Bm25Dev& ix, const int32_t* d_terms, int64_t nq, in
       // holds what a cfg3-sized round produces, whatever the corpus size
       for (int64_t lo = prev; lo < hi; lo += MJ_LAUNCH_TILES) {
         const int64_t lhi = std::min<int64_t>(hi, lo + MJ_LAUNCH_TILES);
-        // a tile is split into `sub` units so that the units fill whole waves of the persistent grid (a unit re-stages
-        // its tile, ~2 us; a half-empty last wave costs a whole wave)
         int sub = 1;
-        double best = 0.0;
-        for (int c = 1; c <= 8; ++c) {
-          const int64_t units = (lhi - lo) * c;
-          const double util = static_cast<double>(units) / static_cast<double>((units + sms - 1) / sms * sms);
-          if (util > best + 0.02) { best = util; sub = c; }
-        }
+        while (sub < 8 && (lhi - lo) * sub < sms) sub <<= 1;   // (splitting tiles further to fill whole waves measured slower:
+                                                                // every unit re-stages its tile)
         const unsigned grid = static_cast<unsigned>(std::min<int64_t>((lhi - lo) * sub, sms));
         switch (sc.qs) {
 #define ARB_MJ(QS_) case QS_: bm25_member_kernel<QS_><<<grid, MJ_THREADS, mj_smem, st>>>(ix, sc, lo, lhi, sub, mj_ch, dbg); \
