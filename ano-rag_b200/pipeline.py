@@ -92,6 +92,8 @@ class HybridPipeline:
         self.exchange = os.environ.get("ARB_EXCHANGE", "peer" if self.world <= 16 else "nccl")
         self._peer: Optional[PeerLists] = None
         self._copy_stream = None
+        self._bm25_stream = None
+        self.overlap_max_queries = int(os.environ.get("ARB_OVERLAP_MAX_QUERIES", str(1 << 30)))
         self._host_out, self._host_turn = {}, {}
 
     # ------------------------------------------------------------------ device-resident inputs
@@ -147,10 +149,26 @@ class HybridPipeline:
             peer.flip()
             return self.searcher.fuse_tensors(dense=(d_id, d_sc), bm25=(b_id, b_sc) if with_bm25 else None,
                                               pool=self.pool)
-        d_sc, d_id = self._dense(q_emb, None, emb_ready)
         b_sc = b_id = None
-        if with_bm25:
-            b_sc, b_id = self.bm25.search(q_terms, self.k_bm25, id_base=self.id_base)
+        if with_bm25 and nq <= self.overlap_max_queries:
+            # the two sources are independent until the fusion, so they run on two streams: small batches leave most of the
+            # GPU idle in either stage (the dense scan streams the corpus, the BM25 stage waits on dependent loads) --
+            # 0.70 -> 0.54 ms for one query, 1.71 -> 1.35 ms for 128; large batches gain the kernels' tails (~2 %)
+            main = torch.cuda.current_stream(q_emb.device)
+            if self._bm25_stream is None:
+                self._bm25_stream = torch.cuda.Stream(device=q_emb.device)
+            side = self._bm25_stream
+            side.wait_stream(main)
+            with torch.cuda.stream(side):
+                b_sc, b_id = self.bm25.search(q_terms, self.k_bm25, id_base=self.id_base)
+            d_sc, d_id = self._dense(q_emb, None, emb_ready)
+            main.wait_stream(side)
+            b_sc.record_stream(main)
+            b_id.record_stream(main)
+        else:
+            d_sc, d_id = self._dense(q_emb, None, emb_ready)
+            if with_bm25:
+                b_sc, b_id = self.bm25.search(q_terms, self.k_bm25, id_base=self.id_base)
         if self.world > 1:
             lo, hi = self.query_slice(q_emb.shape[0])
             d_sc, d_id = engine.merge_topk(self._exchange(d_sc, float("-inf")), self._exchange(d_id, -1))

@@ -609,6 +609,18 @@ def run_b200(a):
         vi.index = None
     barrier()
 
+    # ---- the same GPUs as N independent replicas (weak scaling): the 1.7 GB corpus fits every GPU, so a deployment that only
+    # wants queries/s shards the query STREAM -- every rank serves its own full 4096-query batch, nothing is exchanged
+    replicas_weak = None
+    if world > 1 and n_shards == 1:
+        qt_full = torch.from_numpy(np.ascontiguousarray(q_terms_all)).to(dev)
+        ms_w = timed(lambda: pipe.search_device(q_emb_all, qt_full), a.steps, warm=3)
+        replicas_weak = {"scaling": "weak", "global_batch": world * a.queries, "queries_per_gpu": a.queries, "ms_per_step": ms_w,
+                         "value": world * a.queries / (ms_w * 1e-3), "unit": UNIT,
+                         "note": "every rank scores its own full batch against its replica of the corpus; max over ranks, device-timed"}
+        del qt_full
+    barrier()
+
     # ---- per-source lists of the CPU sample's queries, for the parity check below (outside any timed region)
     n_cpu = min(a.cpu_sample, a.queries)
     gpu_parts = None
@@ -686,22 +698,27 @@ def run_b200(a):
                       "algorithmic_bytes": bm25_bytes, "postings_per_query": local_postings / max(1, q_local),
                       "dram_bytes": traffic.get("bm25_topk"),
                       "kernels": {
-                          "member_pass (bm25_member_kernel + bm25_member_exact_kernel + compaction, 5 rounds)":
-                              dict(hbm_stage(per_launch("bm25_sparse"), "bm25_member"), bound="issue + shared-memory bank conflicts + L2 latency"),
+                          "member_pass (bm25_member_kernel fp32 screening + bm25_member_exact_kernel fp64 + compaction, 5 rounds)":
+                              dict(hbm_stage(per_launch("bm25_sparse"), "bm25_member"), bound="issue (42 %) + L2 latency of the exact kernel's dependent loads"),
                           "screening_pass (bm25_screen_kernel + bm25_recheck_kernel)":
-                              dict(hbm_stage(per_launch("bm25_planes"), "bm25_screen"), bound="issue (fp32 adds on shared-memory tiles)"),
+                              dict(hbm_stage(per_launch("bm25_planes"), "bm25_screen"), bound="issue (fp32 adds on shared-memory tiles) + per-tile barrier"),
                           "final_merge_and_fallback":
                               dict(hbm_stage(per_launch("bm25_final"), "bm25_final"), bound="latency (16 queries take the per-query kernel)")}},
         "fuse": {"ms": per_launch("fuse"), "bound": "latency"},
         "dense_merge": {"ms": per_launch("dense_merge"), "bound": "latency"},
     }
-    dom = "bm25_topk" if b_ms >= d_ms else "dense_topk"
+    # the dominant KERNEL: the dense scan is one kernel (two launches per step); the BM25 stage is several kernels, the largest
+    # being the member pass (ncu launch list of the same step: profiles/r2_ncu_summary.md)
+    dom = "bm25_topk" if per_launch("bm25_sparse") >= d_ms else "dense_topk"
     if dom == "dense_topk":
         roofline = {"kernel": "dense_topk_kernel (tcgen05 GEMM + fused top-k select)", "bound": "tensor", "achieved": dense_tflops,
                     "peak": peaks["tflops_burst"], "unit": "TFLOP/s", "frac": dense_tflops / peaks["tflops_burst"],
                     "frac_of_sustained": dense_tflops / peaks["tflops_sustained"],
                     "traffic": traffic.get("dense_topk") if world == 1 else None,
-                    "peak_source": peaks["source"] + "; burst bf16 figure (the GEMM runs at ~40 % duty inside a step)", "launch_ms": d_ms}
+                    "peak_source": peaks["source"] + "; burst bf16 figure (the GEMM runs at ~50 % duty inside a step)", "launch_ms": d_ms,
+                    "share_of_step": d_ms / ms_step if ms_step > 0 else None,
+                    "note": "algorithmic flops 2 * queries * rows * dim over the kernel's live CUDA-event time (both chunk launches of a step); "
+                            "ncu: tensor pipe active 76.8 % (profiles/r2_ncu_summary.md)"}
     else:
         roofline = {"kernel": "bm25 stage (member + screening passes)", "bound": "hbm", "achieved": bm25_gbs, "peak": peaks["hbm_gbs"],
                     "unit": "GB/s", "frac": bm25_gbs / peaks["hbm_gbs"], "frac_of_nominal_8tbs": bm25_gbs / HBM_NOMINAL_GBS,
@@ -767,7 +784,7 @@ def run_b200(a):
                 "dtype": "bf16", "data": "synthetic", "config": workload_config(a, n_gpus, n_shards), "e2e": e2e,
                 "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "stages": stages,
                 "cpu_baseline": cpu_baseline, "parity": parity, "result_hash": headline_hash, "latency_ms": latency, "reference_shaped_api": api_shaped,
-                "row_sharded": row_sharded, "replicated": replicated, "cfg4": cfg4, "impl": "b200",
+                "row_sharded": row_sharded, "replicated": replicated, "replicas_weak": replicas_weak, "cfg4": cfg4, "impl": "b200",
                 "layout": "single GPU" if world == 1 else ("row-sharded (north-star layout)" if n_shards == world else "replicated corpus, split batch"),
                 "collective": "none in the timed data path (replicated layout); row_sharded: NVLink peer loads by the merge kernel, NCCL for setup / timing only",
                 "dtype_note": "dense: bf16 operands, fp32 accumulate on tcgen05; BM25 and fusion: fp64"}

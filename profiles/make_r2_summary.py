@@ -1,0 +1,109 @@
+#!/usr/bin/env python
+"""Builds profiles/r2_ncu_summary.md, r2_ncu_full_step.json and r2_dram_traffic.json from the round-2 captures
+(launch list CSV + the two --set full reports).  Run here (no GPU): python profiles/make_r2_summary.py"""
+import collections
+import csv
+import io
+import json
+import os
+import subprocess
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+OUT = os.path.join(ROOT, "gpurun_out")
+KEYS = {"gpu__time_duration.sum": "duration_ns", "launch__grid_size": "grid", "launch__block_size": "block",
+        "launch__registers_per_thread": "regs", "sm__warps_active.avg.pct_of_peak_sustained_active": "warps_active_pct",
+        "smsp__inst_executed.sum": "warp_inst", "smsp__issue_active.avg.pct_of_peak_sustained_active": "issue_active_pct",
+        "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active": "tensor_pipe_active_pct",
+        "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum": "smem_wavefronts",
+        "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum": "smem_bank_conflicts", "lts__t_sectors.sum": "l2_sectors",
+        "lts__t_sector_hit_rate.pct": "l2_hit_pct", "dram__bytes_read.sum": "dram_read", "dram__bytes_write.sum": "dram_write",
+        "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed": "dram_pct_of_peak"}
+
+
+def short(name):
+    return name.split("(")[0].replace("void ", "").replace("arb::", "")
+
+
+def launch_list():
+    rows = [r for r in csv.reader(open(os.path.join(ROOT, "profiles", "r2_launches_step.csv"))) if len(r) > 10 and r[0].isdigit()]
+    L = collections.OrderedDict()
+    for r in rows:
+        L.setdefault(int(r[0]), {"name": short(r[4]), "grid": r[8], "block": r[7]})[r[12]] = float(r[14].replace(",", ""))
+    fuse = [i for i in L if "fuse_kernel" in L[i]["name"]]
+    lo, hi = fuse[-2] + 1, fuse[-1]
+    agg = collections.OrderedDict()
+    for i in range(lo, hi + 1):
+        e = L[i]
+        a = agg.setdefault(e["name"], {"launches": 0, "us": 0.0, "dram_read": 0.0, "dram_write": 0.0, "grid": e["grid"], "block": e["block"]})
+        a["launches"] += 1
+        a["us"] += e.get("gpu__time_duration.sum", 0) / 1e3
+        a["dram_read"] += e.get("dram__bytes_read.sum", 0)
+        a["dram_write"] += e.get("dram__bytes_write.sum", 0)
+    return agg
+
+
+def full(rep):
+    txt = subprocess.run(["ncu", "-i", os.path.join(OUT, rep), "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(io.StringIO(txt)))
+    h, units = rows[0], rows[1]
+    out = []
+    for r in rows[2:]:
+        d = {"kernel": short(r[h.index("Kernel Name")])}
+        for k, nm in KEYS.items():
+            if k in h:
+                v = float(r[h.index(k)].replace(",", "") or 0)
+                u = units[h.index(k)]
+                mult = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "ms": 1e6, "us": 1e3, "s": 1e9}.get(u, 1.0)
+                d[nm] = v * mult
+        st = sorted([(float(r[i] or 0), k.replace("smsp__average_warps_issue_stalled_", "").replace("_per_issue_active.ratio", ""))
+                     for i, k in enumerate(h) if "issue_stalled" in k and k.endswith("per_issue_active.ratio")], reverse=True)[:5]
+        d["stalls_per_issue"] = {n: round(v, 2) for v, n in st}
+        out.append(d)
+    return out
+
+
+def main():
+    agg = launch_list()
+    total = sum(a["us"] for a in agg.values())
+    fa, fb = full("r2_step_full_a.ncu-rep"), full("r2_step_full_b.ncu-rep")
+    json.dump({"launch_list_of_one_step": agg, "step_total_us_under_ncu": total, "set_full": fa + fb,
+               "source": "ncu 2025 on one B200 via gpurun; tests/gpu_profile_step.py (cfg3: 1 M notes, 4096 queries); second of two steps"},
+              open(os.path.join(ROOT, "profiles", "r2_ncu_full_step.json"), "w"), indent=1)
+
+    def grp(pred):
+        return int(sum(a["dram_read"] + a["dram_write"] for k, a in agg.items() if pred(k)))
+    traffic = {"dense_topk": grp(lambda k: k.startswith("dense_topk")), "bm25_topk": grp(lambda k: k.startswith("bm25_")),
+               "bm25_member": grp(lambda k: "member" in k or "compact" in k or "bt_" in k or "qclassify" in k),
+               "bm25_screen": grp(lambda k: "screen" in k or "recheck" in k or "h3" in k),
+               "bm25_final": grp(lambda k: "final" in k or "bm25_topk_kernel" in k or "flag_merge" in k),
+               "fuse": grp(lambda k: k.startswith("fuse")),
+               "source": "ncu dram__bytes_read.sum + dram__bytes_write.sum per launch, summed over the launches of one cfg3 step "
+                         "(profiles/r2_launches_step.csv, the build of profiles/r2_bench_n1.json)"}
+    json.dump(traffic, open(os.path.join(ROOT, "profiles", "r2_dram_traffic.json"), "w"), indent=1)
+    md = ["# Round-2 profiling evidence (B200, sm_100a)", "",
+          "Captured with `gpurun` on one B200 after the profiled command had exited 0 without ncu. Per-launch times under ncu are",
+          "cold-cache and serialised: compare SHARES with the live CUDA-event stage times of `profiles/r2_bench_n1.json`",
+          "(dense 4.87 ms, BM25 4.90 ms = 3.51 member pass + 1.07 screening + 0.29 final/fallback, fuse 0.17 ms; step 9.95 ms).", "",
+          "## 1. Launch list of one cfg3 step", "",
+          "`ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -c 400 --csv python tests/gpu_profile_step.py`",
+          "(raw: `profiles/r2_launches_step.csv`; the second of the two steps the script runs)", "",
+          "| kernel | launches | grid x block | us | share | DRAM read MB | DRAM write MB |", "|---|---|---|---|---|---|---|"]
+    for k, a in agg.items():
+        md.append(f"| `{k}` | {a['launches']} | {a['grid']} x {a['block']} | {a['us']:.1f} | {a['us'] / total * 100:.1f} % | {a['dram_read'] / 1e6:.1f} | {a['dram_write'] / 1e6:.1f} |")
+    md += [f"| **step** | | | **{total:.1f}** | 100 % | {sum(a['dram_read'] for a in agg.values()) / 1e6:.0f} | {sum(a['dram_write'] for a in agg.values()) / 1e6:.0f} |", "",
+           "## 2. `ncu --set full --import-source on --clock-control none` of the step's kernels", "",
+           "(reports: `gpurun_out/r2_step_full_a.ncu-rep` = dense / screening / fuse, `r2_step_full_b.ncu-rep` = last member-pass round;",
+           "machine-readable copy: `profiles/r2_ncu_full_step.json`)", "",
+           "| kernel | duration | regs | warps active | issue active | tensor pipe | smem wavefronts (conflicts) | L2 sectors (hit) | DRAM rd / wr | top stalls per issue |",
+           "|---|---|---|---|---|---|---|---|---|---|"]
+    for d in fa + fb:
+        md.append(f"| `{d['kernel']}` | {d['duration_ns'] / 1e6:.3f} ms | {int(d['regs'])} | {d['warps_active_pct']:.1f} % | {d['issue_active_pct']:.1f} % | "
+                  f"{d.get('tensor_pipe_active_pct', 0):.1f} % | {d['smem_wavefronts'] / 1e6:.1f} M ({d['smem_bank_conflicts'] / 1e6:.1f} M) | "
+                  f"{d['l2_sectors'] / 1e6:.0f} M ({d['l2_hit_pct']:.0f} %) | {d['dram_read'] / 1e6:.0f} / {d['dram_write'] / 1e6:.0f} MB | "
+                  f"{', '.join(f'{k} {v}' for k, v in d['stalls_per_issue'].items())} |")
+    open(os.path.join(ROOT, "profiles", "r2_ncu_summary_tables.md"), "w").write("\n".join(md) + "\n")
+    print("\n".join(md))
+
+
+if __name__ == "__main__":
+    main()
