@@ -53,6 +53,7 @@ constexpr int E_CAP = 1024;                          // screening-pass emissions
 constexpr int RQ_CAP = 1 << 20;                      // queued fp64 rechecks per batch chunk (more: done in place)
 constexpr unsigned long long THR_SKIP = ~0ull;
 constexpr int H3_MAX = 1024;                         // queries per batch chunk that may take the histogram path
+constexpr int H3_DIRECT = 64;                        // up to this many listed queries read their plane rows straight from global memory
 constexpr int H3_BINS = 4096;                        // 128 bins per octave from 2^-12 up
 constexpr unsigned long long H3_BASE = (1ull << 18) | (static_cast<unsigned long long>(1023 - 12) << 7);
 // bin of a positive score: sign | exponent | 7 mantissa bits of its order-preserving key, clamped
@@ -871,8 +872,9 @@ bm25_recheck_kernel(const Bm25Dev ix, const BatchScratch sc) {
   }
 }
 
-// The histogram path costs two extra fp64 sweeps over all plane tiles; the per-query fallback costs ~13 us per query
-// and 16K-doc block.  With fewer than H3_MIN listed queries the fallback is cheaper: hand them over.  One block.
+// The per-query fallback has a fixed latency of ~0.2 ms per batch however few queries take it.  A large batch that lists
+// only a few queries for the histogram path already pays that latency for its overflowed queries: hand the listed ones
+// over as well (their low thresholds would add more screening work than the fallback costs).  One block.
 constexpr int H3_MIN = 64;
 __global__ void __launch_bounds__(256)
 bm25_h3_decide_kernel(const BatchScratch sc) {
@@ -888,21 +890,52 @@ bm25_h3_decide_kernel(const BatchScratch sc) {
 }
 
 // ----------------------------------------------------------------------------
-// 2b. histogram path: queries whose list A holds fewer than k docs although they have plane tokens (frequent on
-// small shards and tiny vocabularies).  EMIT = false: histogram of the plane-only scores of ALL docs (a member's
-// plane-only score is counted too: the threshold kernel asks for correspondingly more docs).  EMIT = true: docs at
-// or above the threshold derived from it that are not members go to list E.  Returns at once when the list is empty.
+// 2a. histogram path: queries whose list A holds fewer than k docs although they have plane tokens (frequent on
+// small shards and tiny vocabularies).  EMIT = false: histogram of the plane-only scores of the docs of every
+// tile_step-th tile (a member's plane-only score is counted too: the threshold kernel asks for correspondingly more
+// docs); the threshold derived from it is what the screening pass then uses for the query.  (EMIT = true, a second
+// sweep that emits the docs at or above the threshold itself, is no longer launched.)  Returns at once when the list is empty.
 // ----------------------------------------------------------------------------
 template <bool EMIT>
 __global__ void __launch_bounds__(PL_WARPS * 32, 1)
-bm25_plane_h3_kernel(const Bm25Dev ix, const BatchScratch sc) {
+bm25_plane_h3_kernel(const Bm25Dev ix, const BatchScratch sc, int tile_step) {
   extern __shared__ __align__(16) double pll_smem[];           // [n_planes][256]
   const int n3 = min(sc.counters[2], H3_MAX);
   if (n3 == 0) return;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int P = ix.n_planes;
   const uint32_t lt = (1u << lane) - 1u;
-  for (int64_t tile = blockIdx.x; tile < ix.n_tiles; tile += gridDim.x) {
+  if (!EMIT && n3 <= H3_DIRECT) {
+    // a handful of queries: staging whole tiles (96 planes) for them costs more than it saves -- one warp per
+    // (query, sampled tile) reads just the query's plane rows from global memory (2 KB each, coalesced)
+    const int64_t n_samp = (ix.n_tiles + tile_step - 1) / tile_step;
+    const int64_t tasks = n_samp * n3;
+    for (int64_t t = static_cast<int64_t>(blockIdx.x) * PL_WARPS + warp; t < tasks; t += static_cast<int64_t>(gridDim.x) * PL_WARPS) {
+      const int idx = static_cast<int>(t % n3);
+      const int64_t tile = (t / n3) * tile_step;
+      const int64_t q = sc.h3_list[idx];
+      double acc[8];
+#pragma unroll
+      for (int r = 0; r < 8; ++r) acc[r] = 0.0;
+      for (int i = 0; i < sc.qd_stride; ++i) {
+        const uint32_t ps = sc.qd[q * sc.qd_stride + i];
+        if (ps == 0xFFu) break;
+        const double2* row = reinterpret_cast<const double2*>(ix.planes + (tile * P + ps) * PLANE_TILE) + lane;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const double2 v = __ldg(row + j * 32);
+          acc[2 * j] = __dadd_rn(acc[2 * j], v.x);
+          acc[2 * j + 1] = __dadd_rn(acc[2 * j + 1], v.y);
+        }
+      }
+      uint32_t* H = sc.hist + static_cast<size_t>(idx) * H3_BINS;
+#pragma unroll
+      for (int r = 0; r < 8; ++r)
+        if (acc[r] > 0.0) atomicAdd(&H[h3_bin(acc[r])], 1u);
+    }
+    return;
+  }
+  for (int64_t tile = static_cast<int64_t>(blockIdx.x) * tile_step; tile < ix.n_tiles; tile += static_cast<int64_t>(gridDim.x) * tile_step) {
     __syncthreads();
     {
       const double2* src = reinterpret_cast<const double2*>(ix.planes + tile * P * PLANE_TILE);
@@ -1201,8 +1234,24 @@ static int batch_chunk(const Bm25Dev& ix, const int32_t* d_terms, int64_t nq, in
   if (planes) {
     ProfileScope ps(PROF_BM25_PLANES, st);
     ARB_CUDA(cudaMemsetAsync(sc.hist, 0, static_cast<size_t>(H3_MAX) * H3_BINS * 4, st));
-    bm25_h3_decide_kernel<<<1, 256, 0, st>>>(sc);
-    ARB_LAUNCH_OK();
+    // ---- 2a. queries whose list A holds fewer than k docs although they have plane tokens have no bound for the screening
+    // pass.  A histogram of the plane-only scores over a SAMPLE of the tiles (every 4th) gives one: the edge at which the
+    // count from the top reaches k + the query's members is met by at least k non-member docs, whose complete score is
+    // their plane-only score -- a valid lower bound of the final k-th score.  The query then takes the ordinary screening
+    // pass with that threshold (about 4k emissions; an overflowing list E sends it to the per-query kernel).
+    {
+      if (nq > 2048) {
+        bm25_h3_decide_kernel<<<1, 256, 0, st>>>(sc);
+        ARB_LAUNCH_OK();
+      }
+      const int step = ix.n_tiles > 256 ? 4 : 1;
+      const size_t plane_smem = static_cast<size_t>(ix.n_planes) * PLANE_TILE * 8;
+      const unsigned h3_grid = static_cast<unsigned>(std::min<int64_t>((ix.n_tiles + step - 1) / step, sms));
+      bm25_plane_h3_kernel<false><<<h3_grid, PL_WARPS * 32, plane_smem, st>>>(ix, sc, step);
+      ARB_LAUNCH_OK();
+      bm25_h3_threshold_kernel<<<H3_MAX / 4, 128, 0, st>>>(k, sc);
+      ARB_LAUNCH_OK();
+    }
     // ---- 2. screening pass: one CTA per SM; query groups sized by what is left of shared memory beside two tiles
     const size_t tiles_smem = 2 * static_cast<size_t>(ix.n_planes) * PLANE_TILE * 4 + 2 * static_cast<size_t>((ix.n_planes + 1) & ~1) * 8;
     const int64_t max_qpg = static_cast<int64_t>((SMEM_MAX - tiles_smem) / 20);     // {thr, slots} record + query index per query
@@ -1216,15 +1265,6 @@ static int batch_chunk(const Bm25Dev& ix, const int32_t* d_terms, int64_t nq, in
     bm25_screen_kernel<<<grid, SC_WARPS * 32, tiles_smem + static_cast<size_t>(qpg) * 20, st>>>(ix, nq, qpg, sc);
     ARB_LAUNCH_OK();
     bm25_recheck_kernel<<<static_cast<unsigned>(8 * sms), 256, 0, st>>>(ix, sc);
-    ARB_LAUNCH_OK();
-    // ---- 2b. histogram path (returns at once unless at least H3_MIN queries lack a bound from list A)
-    const size_t plane_smem = static_cast<size_t>(ix.n_planes) * PLANE_TILE * 8;
-    const unsigned h3_grid = static_cast<unsigned>(std::min<int64_t>(ix.n_tiles, sms));
-    bm25_plane_h3_kernel<false><<<h3_grid, PL_WARPS * 32, plane_smem, st>>>(ix, sc);
-    ARB_LAUNCH_OK();
-    bm25_h3_threshold_kernel<<<H3_MAX / 4, 128, 0, st>>>(k, sc);
-    ARB_LAUNCH_OK();
-    bm25_plane_h3_kernel<true><<<h3_grid, PL_WARPS * 32, plane_smem, st>>>(ix, sc);
     ARB_LAUNCH_OK();
   }
   {
