@@ -233,7 +233,8 @@ bm25_bt_fill_kernel(int64_t n, const BatchScratch sc, int n_planes) {
 // 1. member pass
 // ----------------------------------------------------------------------------
 constexpr int MJ_THREADS = 640;
-constexpr int MJ_CH_MAX = 2560;                      // postings joined per chunk (4 per thread)
+constexpr int MJ_PPT = 4;                            // postings a thread owns in the join's preparation
+constexpr int MJ_CH_MAX = MJ_THREADS * MJ_PPT;       // postings joined per chunk
 constexpr int MJ_LAUNCH_TILES = 2048;                 // tiles per member-pass launch
 constexpr int MJ_DEF = 65536;                        // set-aside pairs per CTA and launch, in global scratch (more: finished in place)
 constexpr int MJ_PSTRIDE = MJ_ROW_BYTES / 4;
@@ -413,14 +414,14 @@ bm25_member_kernel(const Bm25Dev ix, const BatchScratch sc, int64_t tile_lo, int
     const int64_t doc_base = tile * PLANE_TILE;
     for (uint32_t c0 = o_lo; c0 < o_hi; c0 += ch) {
       const int n_ch = static_cast<int>(min(static_cast<uint32_t>(ch), o_hi - c0));
-      // ---- runs (thread t owns postings 4t .. 4t+3): head flags, record ranges
-      uint32_t rcnt[4];
+      // ---- runs (thread t owns postings MJ_PPT * t ..): head flags, record ranges
+      uint32_t rcnt[MJ_PPT];
       {
         uint32_t prev = 0xFFFFFFFFu;
-        if (tid * 4 < n_ch && tid > 0) prev = __ldg(ix.tt_term + c0 + tid * 4 - 1);
+        if (tid * MJ_PPT < n_ch && tid > 0) prev = __ldg(ix.tt_term + c0 + tid * MJ_PPT - 1);
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const int i = tid * 4 + e;
+        for (int e = 0; e < MJ_PPT; ++e) {
+          const int i = tid * MJ_PPT + e;
           rcnt[e] = 0u;
           if (i < n_ch) {
             const uint32_t t = __ldg(ix.tt_term + c0 + i);
@@ -438,11 +439,11 @@ bm25_member_kernel(const Bm25Dev ix, const BatchScratch sc, int64_t tile_lo, int
       }
       __syncthreads();
       // ---- run lengths, pairs per run = records x docs, exclusive scan
-      uint32_t cnt[4];
+      uint32_t cnt[MJ_PPT];
       uint32_t tsum = 0u;
 #pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const int i = tid * 4 + e;
+      for (int e = 0; e < MJ_PPT; ++e) {
+        const int i = tid * MJ_PPT + e;
         cnt[e] = 0u;
         if (i < n_ch && (pinfo[i] >> 31)) {
           int len = 1;
@@ -469,8 +470,8 @@ bm25_member_kernel(const Bm25Dev ix, const BatchScratch sc, int64_t tile_lo, int
       {
         uint32_t run = wsum[warp] + incl - tsum;
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const int i = tid * 4 + e;
+        for (int e = 0; e < MJ_PPT; ++e) {
+          const int i = tid * MJ_PPT + e;
           if (i < n_ch) pscan[i] = run;
           run += cnt[e];
         }
