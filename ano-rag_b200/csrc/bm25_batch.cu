@@ -45,6 +45,8 @@
 
 namespace arb {
 
+constexpr int SC_GRAB = 8;                           // active queries a warp takes at a time: small grabs keep the 32 warps of a CTA
+                                                     // busy until the tile's barrier (32 per grab left a third of the last wave idle)
 constexpr int SC_WARPS = 32;                         // screening pass: warps per CTA (two fp32 plane tiles in flight)
 constexpr int PL_WARPS = 16;                         // fp64 plane kernels of the histogram path
 constexpr int SMEM_MAX = 227 * 1024 - 256;           // dynamic shared memory per CTA (256 B left for static barriers / scan scratch)
@@ -731,7 +733,7 @@ __device__ __noinline__ void screen_recheck(const RecheckArgs ra, int64_t q, int
 }
 
 __global__ void __launch_bounds__(SC_WARPS * 32, 1)
-bm25_screen_kernel(const Bm25Dev ix, int64_t nq, int64_t q_per_group, const BatchScratch sc) {
+bm25_screen_kernel(const Bm25Dev ix, int64_t nq, int64_t q_per_group, const BatchScratch sc, int grab) {
   extern __shared__ __align__(16) uint8_t sn_smem[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int P = ix.n_planes, Pp = (P + 1) & ~1;
@@ -791,17 +793,17 @@ bm25_screen_kernel(const Bm25Dev ix, int64_t nq, int64_t q_per_group, const Batc
     __syncthreads();
     const float* T = reinterpret_cast<const float*>(sn_smem + static_cast<size_t>(b) * tile_bytes);
     const double* tm = tmax_s + b * Pp;
-    while (true) {                                             // warps take 32 active queries at a time
+    while (true) {                                             // warps take SC_GRAB active queries at a time
       int a0 = 0;
-      if (lane == 0) a0 = atomicAdd(&next_a[b], 32);
+      if (lane == 0) a0 = atomicAdd(&next_a[b], grab);
       a0 = __shfl_sync(0xffffffffu, a0, 0);
       if (a0 >= na) break;
-      // this tile's bound for 32 queries at once, one query per lane (same token order as the scores)
+      // this tile's bound for SC_GRAB queries at once, one query per lane (same token order as the scores)
       const int a = a0 + lane;
       ulonglong2 rec = make_ulonglong2(0ull, ~0ull);
       int q_mine = 0;
       bool alive = false;
-      if (a < na) {
+      if (lane < grab && a < na) {
         rec = qrec[a];                                         // {k-th score of A as fp64 bits, packed plane slots}
         q_mine = qidx[a];
         double ub = tm[static_cast<uint32_t>(rec.y) & 0xFFu];
@@ -1263,7 +1265,8 @@ static int batch_chunk(const Bm25Dev& ix, const int32_t* d_terms, int64_t nq, in
     groups = (nq + qpg - 1) / qpg;
     const int64_t sets = std::max<int64_t>(1, std::min<int64_t>(ix.n_tiles, sms / groups));
     dim3 grid(static_cast<unsigned>(sets), static_cast<unsigned>(groups));
-    bm25_screen_kernel<<<grid, SC_WARPS * 32, tiles_smem + static_cast<size_t>(qpg) * 20, st>>>(ix, nq, qpg, sc);
+    static const int grab = std::getenv("ARB_BM25_GRAB") ? std::max(1, std::min(32, atoi(std::getenv("ARB_BM25_GRAB")))) : SC_GRAB;
+    bm25_screen_kernel<<<grid, SC_WARPS * 32, tiles_smem + static_cast<size_t>(qpg) * 20, st>>>(ix, nq, qpg, sc, grab);
     ARB_LAUNCH_OK();
     bm25_recheck_kernel<<<static_cast<unsigned>(8 * sms), 256, 0, st>>>(ix, sc);
     ARB_LAUNCH_OK();
