@@ -74,6 +74,7 @@ struct BatchScratch {
   // ---- query-term index of the batch
   int32_t* qinfo;              // [nq, qs] per query token: >= 0 sparse term id, -1 contributes nothing, <= -2 plane slot (-2 - slot)
   int qs;                      // tokens per query rounded up to a multiple of 4 (16-byte rows)
+  uint32_t* qdup;              // [nq] bit p: token p repeats a sparse term of an earlier position (it gets no record of its own)
   uint2* bt_ent;               // [n_terms] {first record, number of records} of a term in bt_rec (count 0: not in the batch)
   uint32_t* bt_cur;            // [n_terms] 0 = unclaimed, then 1 + records placed so far
   int4* bt_rec;                // [sparse tokens of the batch] records of 1 + qs/4 int4, grouped by term (bm25_bt_fill_kernel)
@@ -161,16 +162,25 @@ bm25_qclassify_kernel(const Bm25Dev ix, const int32_t* __restrict__ q_terms, int
   const int64_t q = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
   if (q >= nq) return;
   int np = 0;
+  uint32_t dup = 0u;
   for (int p = 0; p < sc.qs; ++p) {
     int code = -1;
     const int t = p < mq ? q_terms[q * mq + p] : -1;
     if (t >= 0 && t < ix.n_terms && __ldg(ix.idf + t) != 0.0) {        // (idf.get(q) or 0) == 0 adds +0.0: a no-op
       const int ps = ix.n_planes > 0 ? __ldg(ix.plane_slot + t) : -1;
       if (ps >= 0) { code = -2 - ps; sc.qd[q * sc.qd_stride + np++] = static_cast<uint8_t>(ps); }
-      else { code = t; atomicAdd(&sc.bt_ent[t].y, 1u); }
+      else {
+        // a term that occurs twice in a query adds its contribution twice (the reference sums per token); the first
+        // occurrence's record carries the repeats, so that a doc holding the term is joined once, not once per repeat
+        code = t;
+        bool rep = false;
+        for (int e = 0; e < p; ++e) rep |= sc.qinfo[q * sc.qs + e] == t;
+        if (rep) dup |= 1u << p; else atomicAdd(&sc.bt_ent[t].y, 1u);
+      }
     }
     sc.qinfo[q * sc.qs + p] = code;
   }
+  sc.qdup[q] = dup;
   for (int i = np; i < sc.qd_stride; ++i) sc.qd[q * sc.qd_stride + i] = 0xFF;
   sc.gthr[q] = f64_key(0.0);                                            // only positive scores are candidates
 }
@@ -182,7 +192,7 @@ bm25_bt_alloc_kernel(int64_t n, const BatchScratch sc) {
   const int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
   if (i >= n) return;
   const int code = sc.qinfo[i];
-  if (code < 0) return;
+  if (code < 0 || ((sc.qdup[i / sc.qs] >> (i % sc.qs)) & 1u)) return;
   if (atomicExch(sc.bt_cur + code, 1u) == 0u)
     sc.bt_ent[code].x = static_cast<uint32_t>(atomicAdd(&sc.counters[5], static_cast<int>(sc.bt_ent[code].y)));
 }
@@ -199,14 +209,14 @@ bm25_bt_fill_kernel(int64_t n, const BatchScratch sc, int n_planes) {
   const int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
   if (i >= n) return;
   const int code = sc.qinfo[i];
-  if (code < 0) { sc.rec_of[i] = 0xFFFFFFFFu; return; }
   const int64_t q = i / sc.qs;
   const int own = static_cast<int>(i - q * sc.qs);
+  if (code < 0 || ((sc.qdup[q] >> own) & 1u)) { sc.rec_of[i] = 0xFFFFFFFFu; return; }
   const uint32_t at = sc.bt_ent[code].x + atomicAdd(sc.bt_cur + code, 1u) - 1u;
   sc.rec_of[i] = at;
   int4* rec = sc.bt_rec + static_cast<size_t>(at) * rec_int4s(sc.qs);
   const int* src = sc.qinfo + q * sc.qs;
-  uint32_t plane_bits = 0u, sparse_bits = 0u;
+  uint32_t plane_bits = 0u, sparse_bits = 0u, own_bits = 1u << own;
   for (int j = 0; j < (sc.qs >> 1); ++j) {
     uint32_t f[4];
 #pragma unroll
@@ -215,7 +225,8 @@ bm25_bt_fill_kernel(int64_t n, const BatchScratch sc, int n_planes) {
       const int c = src[p];
       uint32_t slot = SLOT_NONE, po = static_cast<uint32_t>(n_planes) * MJ_ROW_BYTES, bw = 0u, bm = 1u << 31;
       if (c <= -2) { slot = static_cast<uint32_t>(-2 - c); po = slot * MJ_ROW_BYTES; plane_bits |= 1u << p; }
-      else if (c >= 0 && p != own) {
+      else if (c == code) own_bits |= 1u << p;                                   // the own token and its repeats
+      else if (c >= 0) {
         bm = bloom_mask(static_cast<uint32_t>(c));                             // one to three distinct bits
         bw = bloom_word(static_cast<uint32_t>(c)) * 4u;
         sparse_bits |= 1u << p;
@@ -228,7 +239,7 @@ bm25_bt_fill_kernel(int64_t n, const BatchScratch sc, int n_planes) {
   const unsigned long long b0 = f64_key(0.0);
   rec[0] = make_int4(static_cast<int>(static_cast<uint32_t>(q << 5) | static_cast<uint32_t>(own)), static_cast<int>(plane_bits),
                      static_cast<int>(static_cast<uint32_t>(b0)), static_cast<int>(static_cast<uint32_t>(b0 >> 32)));
-  rec[1] = make_int4(static_cast<int>(sparse_bits), 0, 0, 0);
+  rec[1] = make_int4(static_cast<int>(sparse_bits), static_cast<int>(own_bits), 0, 0);
 }
 
 // ----------------------------------------------------------------------------
@@ -293,6 +304,7 @@ __device__ __forceinline__ void exact_pair(const ExactArgs& ea, PlaneFn plane, i
   const int4 hd = __ldg(rec);
   const int64_t q = static_cast<uint32_t>(hd.x) >> 5;
   const int pos = hd.x & 31;
+  const uint32_t own_bits = static_cast<uint32_t>(__ldg(reinterpret_cast<const int*>(rec + 1) + 1));
   const uint32_t r0 = __ldg(ea.drow_off + d);
   const int row_n = static_cast<int>(__ldg(ea.drow_off + d + 1) - r0);
   // a match at an earlier position: the pair belongs to that position's record -- settled before any plane is read
@@ -318,7 +330,7 @@ __device__ __forceinline__ void exact_pair(const ExactArgs& ea, PlaneFn plane, i
 #pragma unroll
   for (int pp = 0; pp < QS; ++pp) {
     double v = pv[pp];
-    if (pp == pos) v = myval;
+    if ((own_bits >> pp) & 1u) v = myval;
     if ((hits >> pp) & 1u) {
       const int idx = row_find(ea.drow_term + r0, row_n, static_cast<uint32_t>(__ldg(ea.qinfo + q * QS + pp)));
       if (idx >= 0) { matched = true; v = __ldg(ea.drow_val + r0 + idx); }
@@ -505,7 +517,9 @@ bm25_member_kernel(const Bm25Dev ix, const BatchScratch sc, int64_t tile_lo, int
             const int4 hd = __ldg(rec);
             ptx::prefetch_l1(rec + RS4);                       // the next record of the run (records of a term are contiguous)
             plane_bits = static_cast<uint32_t>(hd.y);
-            sparse_bits = static_cast<uint32_t>(__ldg(reinterpret_cast<const int*>(rec + 1)));
+            const int2 h1 = __ldg(reinterpret_cast<const int2*>(rec + 1));
+            sparse_bits = static_cast<uint32_t>(h1.x);
+            own_bit = static_cast<uint32_t>(h1.y);
 #pragma unroll
             for (int p2 = 0; p2 < QS / 2; ++p2) {
               const int4 c4 = __ldg(rec + 2 + p2);
@@ -516,7 +530,6 @@ bm25_member_kernel(const Bm25Dev ix, const BatchScratch sc, int64_t tile_lo, int
               bw[2 * p2 + 1] = (static_cast<uint32_t>(c4.z) >> 17) & 63u;
               bm[2 * p2 + 1] = static_cast<uint32_t>(c4.w);
             }
-            own_bit = 1u << (hd.x & 31);
             q = static_cast<uint32_t>(hd.x) >> 5;
             bound_d = key_f64((static_cast<unsigned long long>(static_cast<uint32_t>(hd.w)) << 32) | static_cast<uint32_t>(hd.z));
           }
@@ -1133,7 +1146,7 @@ static int batch_chunk(const Bm25Dev& ix, const int32_t* d_terms, int64_t nq, in
   ARB_CUDA(b_defer.alloc(static_cast<size_t>(sms) * MJ_DEF * sizeof(MjDefer) + static_cast<size_t>(sms) * 4, st));
   sc.defer = b_defer.as<MjDefer>();
   sc.def_cnt = reinterpret_cast<int*>(sc.defer + static_cast<size_t>(sms) * MJ_DEF);
-  AsyncBuf b_qinfo, b_bt, b_pair, b_ckey, b_cdoc, b_akey, b_adoc, b_i32, b_u64, b_u8, b_ekey, b_edoc, b_hist;
+  AsyncBuf b_qdup, b_qinfo, b_bt, b_pair, b_ckey, b_cdoc, b_akey, b_adoc, b_i32, b_u64, b_u8, b_ekey, b_edoc, b_hist;
   const size_t nt = static_cast<size_t>(std::max<int64_t>(ix.n_terms, 1));
   ARB_CUDA(b_qinfo.alloc(static_cast<size_t>(nq) * sc.qs * 4, st));
   ARB_CUDA(b_bt.alloc(3 * nt * 4, st));                                             // bt_ent | bt_cur
@@ -1145,6 +1158,8 @@ static int batch_chunk(const Bm25Dev& ix, const int32_t* d_terms, int64_t nq, in
   ARB_CUDA(b_i32.alloc((static_cast<size_t>(nq) * 5 + 8 + H3_MAX) * 4, st));        // c_cnt | n_nonpos | e_cnt | counters | a_cnt | flag_list | h3_list
   ARB_CUDA(b_u64.alloc(static_cast<size_t>(nq) * 2 * 8, st));                       // gthr | thr
   ARB_CUDA(b_u8.alloc(static_cast<size_t>(nq) * (sc.qd_stride + 2) + 16, st));      // qd | state | ovf
+  ARB_CUDA(b_qdup.alloc(static_cast<size_t>(nq) * 4, st));
+  sc.qdup = b_qdup.as<uint32_t>();
   sc.qinfo = b_qinfo.as<int32_t>();
   sc.bt_ent = b_bt.as<uint2>();
   sc.bt_cur = b_bt.as<uint32_t>() + 2 * nt;

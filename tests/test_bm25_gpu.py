@@ -164,6 +164,9 @@ def test_batched_pipeline_equals_per_query_kernel(n, v, nq, k, mean_len, planes,
     qt[4, 1:] = -1
     qt[5, :] = 0                              # the densest term only (no sparse members: fallback path)
     qt[6, :4] = np.arange(4)                  # mostly plane terms
+    qt[7, 2] = qt[7, 5] = qt[7, 4]            # a document's (mostly sparse) term three times, other terms in between
+    qt[7, 3] = qt[7, 6]                       # and a second repeated term, interleaved
+    qt[8, 4:] = qt[8, 4]                      # the same document term four times at the end
     gpu = GpuBM25.from_token_ids(ptr, tok, v, variant="okapi")
     monkeypatch.setenv("ARB_BM25_MODE", "query")
     s0, i0 = gpu.search_terms(qt, k)
@@ -174,7 +177,7 @@ def test_batched_pipeline_equals_per_query_kernel(n, v, nq, k, mean_len, planes,
     assert stats["queries"] == nq
     assert np.array_equal(i0, i1) and np.array_equal(s0, s1), stats
     ora = obm.ArrayBM25Oracle(ptr, tok, variant="okapi")
-    for r in (0, 3, 4, 5, 6, nq - 1):
+    for r in (0, 3, 4, 5, 6, 7, 8, nq - 1):
         ws, wi = obm.topk_positive(ora.get_scores([t for t in qt[r] if t >= 0]), k)
         assert np.array_equal(i1[r], wi) and np.array_equal(s1[r], ws), f"query {r}"
     gpu.close()
