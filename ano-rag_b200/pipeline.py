@@ -126,7 +126,7 @@ class HybridPipeline:
                                   out=(out[0][lo:hi], out[1][lo:hi]))
         return out
 
-    def search_device(self, q_emb: torch.Tensor, q_terms: Optional[torch.Tensor], emb_ready=None):
+    def search_device(self, q_emb: torch.Tensor, q_terms: Optional[torch.Tensor], emb_ready=None, terms_ready=None):
         """q_emb [nq, d] CUDA (fp32 or bf16), q_terms [nq, max_qt] CUDA int32 (or None: dense only).
         -> (ids [nq,pool] int64, final [nq,pool] fp64, src [nq,pool,4] fp64, count [nq] int32) on the device.
         With world > 1 every rank returns the rows of its own query slice
@@ -136,9 +136,20 @@ class HybridPipeline:
         if self.world > 1 and self.exchange == "peer":
             peer = self._peer_lists(nq)
             lo, hi = self.query_slice(nq)
-            self._dense(q_emb, peer.dense_out(nq), emb_ready)
-            if with_bm25:
-                self.bm25.search(q_terms, self.k_bm25, id_base=self.id_base, out=peer.bm25_out(nq))
+            if with_bm25 and nq <= self.overlap_max_queries:      # the two sources on two streams (see below)
+                main, side = torch.cuda.current_stream(q_emb.device), self._side()
+                if terms_ready is not None:
+                    side.wait_event(terms_ready)
+                else:
+                    side.wait_stream(main)
+                with torch.cuda.stream(side):
+                    self.bm25.search(q_terms, self.k_bm25, id_base=self.id_base, out=peer.bm25_out(nq))
+                self._dense(q_emb, peer.dense_out(nq), emb_ready)
+                main.wait_stream(side)
+            else:
+                self._dense(q_emb, peer.dense_out(nq), emb_ready)
+                if with_bm25:
+                    self.bm25.search(q_terms, self.k_bm25, id_base=self.id_base, out=peer.bm25_out(nq))
             peer.barrier()                       # every rank's lists are written and visible
             d_sc, d_id = engine.merge_topk_peers(peer.ptrs(0), peer.ptrs(1), torch.float32, lo, hi - lo,
                                                  self.k_dense, self.device)
@@ -154,11 +165,11 @@ class HybridPipeline:
             # the two sources are independent until the fusion, so they run on two streams: small batches leave most of the
             # GPU idle in either stage (the dense scan streams the corpus, the BM25 stage waits on dependent loads) --
             # 0.70 -> 0.54 ms for one query, 1.71 -> 1.35 ms for 128; large batches gain the kernels' tails (~2 %)
-            main = torch.cuda.current_stream(q_emb.device)
-            if self._bm25_stream is None:
-                self._bm25_stream = torch.cuda.Stream(device=q_emb.device)
-            side = self._bm25_stream
-            side.wait_stream(main)
+            main, side = torch.cuda.current_stream(q_emb.device), self._side()
+            if terms_ready is not None:
+                side.wait_event(terms_ready)             # search_host: q_terms is on the device; the embeddings may still travel
+            else:
+                side.wait_stream(main)
             with torch.cuda.stream(side):
                 b_sc, b_id = self.bm25.search(q_terms, self.k_bm25, id_base=self.id_base)
             d_sc, d_id = self._dense(q_emb, None, emb_ready)
@@ -178,6 +189,11 @@ class HybridPipeline:
                 b_sc, b_id = b_sc[: hi - lo], b_id[: hi - lo]
         return self.searcher.fuse_tensors(dense=(d_id, d_sc), bm25=(b_id, b_sc) if b_sc is not None else None,
                                           pool=self.pool)
+
+    def _side(self):
+        if self._bm25_stream is None:
+            self._bm25_stream = torch.cuda.Stream(device=self.device)
+        return self._bm25_stream
 
     def _peer_lists(self, nq: int) -> PeerLists:
         """(Re)allocate the symmetric buffers; collective, and every rank sees the same nq."""
@@ -205,6 +221,13 @@ class HybridPipeline:
         with torch.cuda.device(dev):
             main = torch.cuda.current_stream(dev)
             q_emb = torch.empty(h_emb.shape, dtype=h_emb.dtype, device=dev)
+            # the query terms (a few hundred KB) go first: the BM25 stream starts on them while the embeddings still travel
+            q_terms = None
+            terms_ready = None
+            if q_terms_host is not None:
+                q_terms = torch.as_tensor(q_terms_host).to(dev, non_blocking=True)
+                terms_ready = torch.cuda.Event()
+                terms_ready.record(main)
             half = ((nq // 2 + 127) // 128) * 128
             emb_ready = None
             if h_emb.is_pinned() and nq >= 1024 and 0 < half < nq:
@@ -220,10 +243,7 @@ class HybridPipeline:
                 emb_ready = [(0, half, None), (half, nq, ev)]
             else:
                 q_emb.copy_(h_emb, non_blocking=True)
-            q_terms = None
-            if q_terms_host is not None:
-                q_terms = torch.as_tensor(q_terms_host).to(dev, non_blocking=True)
-            res = self.search_device(q_emb, q_terms, emb_ready=emb_ready)
+            res = self.search_device(q_emb, q_terms, emb_ready=emb_ready, terms_ready=terms_ready)
             ids, fin, src, cnt = res
             outs = [ids, fin, cnt] + ([src] if return_src else [])
             key = tuple((tuple(t.shape), t.dtype) for t in outs)
