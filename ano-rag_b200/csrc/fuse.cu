@@ -143,7 +143,23 @@ fuse_kernel(const FuseParams p) {
       uint32_t h = hash_id<FUSE_HASH>(key);
       while (true) {
         const unsigned long long prev = atomicCAS(&s.hkey[h], HASH_EMPTY, key);
-        if (prev == HASH_EMPTY || prev == key) { s.hpos[h][src] = static_cast<short>(j); break; }
+        if (prev == HASH_EMPTY || prev == key) {
+          // an id that occurs twice in one source keeps its LAST position, like the reference's dict built from the list
+          // (retrieval/hybrid_search.py:46-49) -- a 16-bit atomic max through the enclosing 32-bit word, so the result
+          // does not depend on which thread gets here first
+          unsigned int* w = reinterpret_cast<unsigned int*>(&s.hpos[h][src & ~1]);
+          unsigned int seen = *w;
+          while (true) {
+            const short cur = static_cast<short>((src & 1) ? (seen >> 16) : (seen & 0xFFFFu));
+            if (cur >= static_cast<short>(j)) break;
+            const unsigned int want = (src & 1) ? ((seen & 0xFFFFu) | (static_cast<unsigned int>(j) << 16))
+                                                : ((seen & 0xFFFF0000u) | static_cast<unsigned int>(j));
+            const unsigned int got = atomicCAS(w, seen, want);
+            if (got == seen) break;
+            seen = got;
+          }
+          break;
+        }
         h = (h + 1) & (FUSE_HASH - 1);
       }
     }

@@ -129,3 +129,41 @@ def test_fuse_with_more_ids_than_the_kernel_holds_keeps_the_best_per_source():
     got = HybridSearcher(cfg).fuse(dense=dense, bm25=bm25)
     want = ofu.HybridSearcherOracle(cfg).fuse(dense=dense, bm25=bm25)
     assert [(e["note_id"], e["final_similarity"]) for e in got] == [(e["note_id"], e["final_similarity"]) for e in want]
+
+
+def test_coalesced_single_queries_equal_the_batched_call_and_share_launches():
+    """Single-query callers on several threads (the reference's per-entity / per-sub-question calls) through the request
+    coalescer: same fused lists as one batched call, fewer device batches than requests."""
+    import threading
+    import torch
+    import ano_rag_b200  # noqa: F401
+    from ano_rag_b200 import engine, bm25_build as bb, synth
+    from ano_rag_b200.pipeline import HybridPipeline
+    from ano_rag_b200.query.coalescer import coalesced_pipeline
+    from ano_rag_b200.retrieval.hybrid_search import HybridSearcher
+    dev = torch.device("cuda:0")
+    n, d, v, nq, k = 20_000, 64, 3000, 48, 10
+    ix = engine.DenseIndex(d, storage="bf16", normalize=False)
+    for _, rows in synth.dense_rows(0, n, d, dev):
+        ix.add(rows)
+    q = synth.dense_queries(nq, d, dev, n_rows=n).to(torch.float32).cpu().numpy()
+    ptr, tok = synth.bm25_corpus(n, v, 30)
+    qt = synth.bm25_queries(nq, ptr, tok, v)
+    arr = bb.build_arrays(ptr, tok, v)
+    bm = engine.BM25Index(n, arr.term_ptr, arr.post_doc, arr.post_gcode, arr.stats.idf, arr.gtab)
+    cfg = {"retrieval": {"candidate_pool": k, "hybrid": {"fusion_method": "rrf", "rrf_k": 60, "weights": {"dense": 1.0, "bm25": 1.0}}}}
+    pipe = HybridPipeline(ix, bm, HybridSearcher(cfg), k_dense=k, k_bm25=k, pool=k, query_planes=1, device=dev)
+    want = tuple(np.array(x, copy=True) for x in pipe.search_host(q, qt)[:3])
+    co = coalesced_pipeline(pipe, max_batch=16, max_wait_ms=20.0)
+    got = [None] * nq
+    th = [threading.Thread(target=lambda i=i: got.__setitem__(i, co((q[i], qt[i])))) for i in range(nq)]
+    for t in th:
+        t.start()
+    for t in th:
+        t.join()
+    co.close()
+    for i in range(nq):
+        ids, fin, cnt = got[i]
+        assert cnt == int(want[2][i]) and np.array_equal(ids[:cnt], want[0][i][:cnt]) and np.array_equal(fin[:cnt], want[1][i][:cnt])
+    assert co.requests == nq and co.batches < nq
+    bm.close(); ix.close()

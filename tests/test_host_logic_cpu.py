@@ -135,3 +135,54 @@ def test_bm25_scores_accepts_any_corpus_with_get_scores():
         def get_scores(self, tokens):
             return [0.0, 0.0]
     assert bm25_scores(ListCorpus(), [{}] * 2, "x") == [0.0, 0.0]
+
+
+def test_request_coalescer_batches_concurrent_calls():
+    """Concurrent single-query calls (query/query_processor.py:1478-1482, :2761-2764) share one batch call; results go back
+    to their callers, a failing batch fails each of its callers, close() drains."""
+    import threading
+    import time
+    import ano_rag_b200  # noqa: F401
+    from ano_rag_b200.query.coalescer import RequestCoalescer, coalesced_search
+
+    sizes = []
+
+    def batch_fn(reqs):
+        sizes.append(len(reqs))
+        time.sleep(0.01)
+        if any(r == "boom" for r in reqs):
+            raise ValueError("bad batch")
+        return [r * 2 for r in reqs]
+
+    c = RequestCoalescer(batch_fn, max_batch=8, max_wait_ms=50.0)
+    out = [None] * 20
+    th = [threading.Thread(target=lambda i=i: out.__setitem__(i, c(i))) for i in range(20)]
+    for t in th:
+        t.start()
+    for t in th:
+        t.join()
+    assert out == [2 * i for i in range(20)]
+    assert sum(sizes) == 20 and max(sizes) <= 8 and len(sizes) < 20 and c.requests == 20 and c.batches == len(sizes)
+    f1, f2 = c.submit("boom"), c.submit(5)
+    import pytest
+    with pytest.raises(ValueError):
+        f1.result(timeout=5)
+    with pytest.raises(ValueError):
+        f2.result(timeout=5)                                               # same batch, same failure
+    assert c(7) == 14                                                      # the worker survives a failing batch
+    c.close()
+    with pytest.raises(RuntimeError):
+        c.submit(1)
+
+    class FakeRetriever:
+        calls = 0
+
+        def search(self, queries, top_k=None, similarity_threshold=None, include_metadata=True):
+            FakeRetriever.calls += 1
+            return [[{"note_id": q, "k": top_k}] for q in queries]
+
+    cs = coalesced_search(FakeRetriever(), top_k=5, max_wait_ms=20.0)
+    futs = [cs.submit(f"entity {i}") for i in range(6)]
+    assert [f.result(timeout=5)[0]["note_id"] for f in futs] == [f"entity {i}" for i in range(6)]
+    assert FakeRetriever.calls < 6
+    cs.close()
