@@ -74,6 +74,111 @@ __global__ void tfidf_emit_kernel(const unsigned long long* __restrict__ keys, c
   out_ids[i] = id;
 }
 
+
+// ----------------------------------------------------------------------------
+// top-k of one query's N similarities without sorting them: an MSD radix select over the order-preserving keys finds the
+// k-th largest positive key T in eight 8-bit passes (256-bin shared-memory histograms), the entries above T plus the
+// first ones equal to T in position order (np.argsort(...)[::-1] semantics: the larger doc id first among equals; the
+// keys are stored in reverse doc order) are collected and only those <= 1024 entries are sorted.  One CTA per query.
+// ----------------------------------------------------------------------------
+constexpr int SEL_THREADS = 1024;
+constexpr int SEL_MAX_K = 1024;
+__global__ void __launch_bounds__(SEL_THREADS)
+tfidf_select_kernel(const unsigned long long* __restrict__ keys, int64_t n_docs, int k, double* __restrict__ out_scores,
+                    int64_t* __restrict__ out_ids) {
+  __shared__ unsigned int hist[256];
+  __shared__ unsigned long long ckey[SEL_MAX_K];
+  __shared__ unsigned int cpos[SEL_MAX_K];
+  __shared__ unsigned long long s_prefix;
+  __shared__ unsigned int s_need, s_ngt, s_base, s_wsum[SEL_THREADS / 32];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int64_t q = blockIdx.x;
+  const unsigned long long* K = keys + q * n_docs;
+  const unsigned long long K0 = f64_key(0.0);                  // only similarities > 0 are results (retriever.py:985)
+  unsigned long long prefix = 0ull;
+  unsigned int need = static_cast<unsigned int>(k);
+  bool take_all = false;
+  for (int pass = 0; pass < 8 && !take_all; ++pass) {
+    const int shift = 56 - 8 * pass;
+    if (tid < 256) hist[tid] = 0u;
+    __syncthreads();
+    for (int64_t i = tid; i < n_docs; i += SEL_THREADS) {
+      const unsigned long long key = K[i];
+      if (key > K0 && (pass == 0 || (key >> (shift + 8)) == (prefix >> (shift + 8))))
+        atomicAdd(&hist[static_cast<unsigned int>(key >> shift) & 255u], 1u);
+    }
+    __syncthreads();
+    if (tid == 0) {
+      unsigned int above = 0u;
+      int d = 255;
+      for (; d >= 0; --d) {
+        if (above + hist[d] >= need) break;
+        above += hist[d];
+      }
+      if (d < 0) { s_need = 0xFFFFFFFFu; }                    // fewer positive entries than k (only possible in pass 0): all of them
+      else { s_need = need - above; s_prefix = prefix | (static_cast<unsigned long long>(d) << shift); }
+    }
+    __syncthreads();
+    if (s_need == 0xFFFFFFFFu) take_all = true;
+    else { need = s_need; prefix = s_prefix; }
+    __syncthreads();
+  }
+  // T = k-th largest positive key; `need` entries equal to T are wanted (the first in position order)
+  const unsigned long long T = take_all ? K0 : prefix;
+  if (take_all) need = 0u;
+  if (tid == 0) { s_ngt = 0u; s_base = 0u; }
+  __syncthreads();
+  const unsigned int n_gt_expected = take_all ? 0xFFFFFFFFu : static_cast<unsigned int>(k) - need;
+  for (int64_t c0 = 0; c0 < n_docs; c0 += SEL_THREADS) {
+    const int64_t i = c0 + tid;
+    const unsigned long long key = i < n_docs ? K[i] : 0ull;
+    const bool gt = i < n_docs && key > T;
+    const bool eq = !take_all && i < n_docs && key == T;
+    if (gt) {
+      const unsigned int at = atomicAdd(&s_ngt, 1u);
+      if (at < static_cast<unsigned int>(SEL_MAX_K)) { ckey[at] = key; cpos[at] = static_cast<unsigned int>(i); }
+    }
+    // ordered ranks of the entries equal to T
+    const unsigned int bal = __ballot_sync(0xffffffffu, eq);
+    if (lane == 0) s_wsum[warp] = __popc(bal);
+    __syncthreads();
+    unsigned int before = s_base;
+    for (int w = 0; w < warp; ++w) before += s_wsum[w];
+    if (eq) {
+      const unsigned int r = before + __popc(bal & ((1u << lane) - 1u));
+      if (r < need) { ckey[n_gt_expected + r] = key; cpos[n_gt_expected + r] = static_cast<unsigned int>(i); }
+    }
+    __syncthreads();
+    if (tid == 0) { unsigned int t = 0u; for (int w = 0; w < SEL_THREADS / 32; ++w) t += s_wsum[w]; s_base += t; }
+    __syncthreads();
+  }
+  const int cnt = take_all ? static_cast<int>(min(s_ngt, static_cast<unsigned int>(SEL_MAX_K))) : k;
+  int n2 = 2;
+  while (n2 < cnt) n2 <<= 1;
+  for (int i = cnt + tid; i < n2; i += SEL_THREADS) { ckey[i] = 0ull; cpos[i] = 0xFFFFFFFFu; }
+  __syncthreads();
+  // bitonic sort by (key desc, position asc)
+  for (int size = 2; size <= n2; size <<= 1) {
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+      for (int i = tid; i < n2 / 2; i += SEL_THREADS) {
+        const int lo = 2 * i - (i & (stride - 1));
+        const int hi = lo + stride;
+        const bool best_first = ((lo & size) == 0);
+        const unsigned long long ka = ckey[lo], kb = ckey[hi];
+        const unsigned int pa = cpos[lo], pb = cpos[hi];
+        const bool a_before_b = (ka > kb) || (ka == kb && pa < pb);
+        if (a_before_b != best_first) { ckey[lo] = kb; ckey[hi] = ka; cpos[lo] = pb; cpos[hi] = pa; }
+      }
+      __syncthreads();
+    }
+  }
+  for (int j = tid; j < k; j += SEL_THREADS) {
+    const bool ok = j < cnt;
+    out_scores[q * k + j] = ok ? key_f64(ckey[j]) : 0.0;
+    out_ids[q * k + j] = ok ? n_docs - 1 - static_cast<int64_t>(cpos[j]) : -1;
+  }
+}
+
 }  // namespace arb
 
 using namespace arb;
@@ -179,8 +284,15 @@ extern "C" int arb_tfidf_search(const arb_tfidf* ix, int64_t nq, const int64_t* 
     tfidf_scores_kernel<<<grid, TF_THREADS, 0, st>>>(n, ix->nb, ix->blk_off, ix->post_doc, ix->post_val, d_ptr.as<int64_t>() + q0,
                                                     d_term.as<int32_t>(), d_val.as<double>(), dk.Current(), dv.Current());
     ARB_LAUNCH_OK();
-    // np.argsort(similarities)[::-1] (retriever.py:980): descending similarity, the LARGER index first among equal
-    // ones -- the keys were written in reverse doc order and the radix sort is stable
+    if (k <= SEL_MAX_K) {
+      // np.argsort(similarities)[::-1] (retriever.py:980): descending similarity, the LARGER index first among equal
+      // ones -- the keys are stored in reverse doc order, ties are taken in position order
+      tfidf_select_kernel<<<static_cast<unsigned>(m), SEL_THREADS, 0, st>>>(dk.Current(), n, k, o_s.as<double>() + q0 * k,
+                                                                          o_i.as<int64_t>() + q0 * k);
+      ARB_LAUNCH_OK();
+      continue;
+    }
+    // k beyond the select kernel's list: a stable segmented radix sort of all scores (library sort; same order)
     ARB_CUDA(cub::DeviceSegmentedRadixSort::SortPairsDescending(tmp.p, tmp_bytes, dk, dv, m * n, static_cast<int>(m),
                                                                 seg.as<int64_t>(), seg.as<int64_t>() + 1, 0, 64, st));
     count_launch();

@@ -4,6 +4,8 @@ import json
 import os
 import random
 
+import numpy as np
+
 import pytest
 
 pytestmark = pytest.mark.gpu
@@ -60,3 +62,36 @@ def test_bm25_fallback_matches_reference_golden(golden_dir, tmp_path):
         same(res[0], c["results"][0])
         vr.cleanup()
     config.reset()
+
+
+@pytest.mark.parametrize("n,k", [(50_000, 1), (50_000, 100), (200_000, 1024), (3000, 1500), (700, 100)])
+def test_select_kernel_equals_a_stable_sort_of_all_scores(n, k):
+    """The top-k is SELECTED (radix select + a sort of the k survivors), not read off a sort of all N scores: same lists
+    as ``np.argsort(similarities)[::-1]`` with a stable sort (larger doc id first among equal similarities, only
+    similarities > 0, -1 beyond), including thousands of exact ties at the k-th score and k beyond the select kernel's
+    list (k > 1024 takes the segmented sort)."""
+    import scipy.sparse as sp
+    import ano_rag_b200  # noqa: F401
+    from ano_rag_b200 import engine
+    rng = np.random.default_rng(n + k)
+    n_terms = 40
+    # few distinct values per term -> mass ties; ~30 % of the docs hold a term
+    rows, cols, vals = [], [], []
+    for t in range(n_terms):
+        docs = np.flatnonzero(rng.random(n) < 0.3)
+        rows.append(docs); cols.append(np.full(len(docs), t)); vals.append(rng.integers(1, 6, len(docs)) / 8.0)
+    m = sp.csr_matrix((np.concatenate(vals), (np.concatenate(rows), np.concatenate(cols))), shape=(n, n_terms))
+    ix = engine.TfidfIndex(m)
+    # single-term queries: the similarity is one exactly rounded product, so numpy reproduces it bit for bit
+    qs = sp.csr_matrix((np.array([0.5, 1.0, 0.25, 2.0]), (np.arange(4), np.array([3, 7, 11, 39]))), shape=(4, n_terms))
+    s, i = ix.search(qs, k)
+    dense = m.toarray()
+    for r in range(4):
+        t = qs[r].indices[0]
+        sims = qs[r].data[0] * dense[:, t]
+        order = np.argsort(sims, kind="stable")[::-1]
+        order = order[sims[order] > 0][:k]
+        want_i = np.full(k, -1, np.int64); want_i[:len(order)] = order
+        want_s = np.zeros(k); want_s[:len(order)] = sims[order]
+        assert np.array_equal(i[r], want_i) and np.array_equal(s[r], want_s), (r, n, k)
+    ix.close()
