@@ -245,7 +245,7 @@ bm25_bt_fill_kernel(int64_t n, const BatchScratch sc, int n_planes) {
 // ----------------------------------------------------------------------------
 // 1. member pass
 // ----------------------------------------------------------------------------
-constexpr int MJ_THREADS = 640;
+constexpr int MJ_THREADS = 768;
 constexpr int MJ_PPT = 4;                            // postings a thread owns in the join's preparation
 constexpr int MJ_CH_MAX = MJ_THREADS * MJ_PPT;       // postings joined per chunk
 constexpr int MJ_LAUNCH_TILES = 2048;                 // tiles per member-pass launch
