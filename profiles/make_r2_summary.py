@@ -83,7 +83,8 @@ def main():
     md = ["# Round-2 profiling evidence (B200, sm_100a)", "",
           "Captured with `gpurun` on one B200 after the profiled command had exited 0 without ncu. Per-launch times under ncu are",
           "cold-cache and serialised: compare SHARES with the live CUDA-event stage times of `profiles/r2_bench_n1.json`",
-          "(dense 4.87 ms, BM25 4.90 ms = 3.51 member pass + 1.07 screening + 0.29 final/fallback, fuse 0.17 ms; step 9.95 ms).", "",
+          "(one-stream pass: dense 4.73 ms, BM25 4.32 ms = 3.09 member pass + 0.91 screening + 0.29 final/fallback, fuse 0.17 ms = 9.24 ms;",
+          "headline with the two sources on two streams: 8.93 ms).", "",
           "## 1. Launch list of one cfg3 step", "",
           "`ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -c 400 --csv python tests/gpu_profile_step.py`",
           "(raw: `profiles/r2_launches_step.csv`; the second of the two steps the script runs)", "",
@@ -111,11 +112,19 @@ def main():
            "| member pass screens pairs in fp32 (rounded-up plane tiles, upward-rounded in-order sums); exact fp64 only above the bound | 5.41 | | |",
            "| query-term records stored decoded (decode ran with a third of the lanes) | 5.05 | | |",
            "| exact kernel templated on the query width (plane loads overlap), early duplicate exit | 4.92 | 4.87 | 9.95 |",
-           "| dense and BM25 on two streams | | | 9.69 (probe) |", "",
+           "| dense and BM25 on two streams | | | 9.16 |",
+           "| screening pass: warps take 8 active queries at a time instead of 32 | 4.79 | | |",
+           "| one record for a sparse term repeated inside a query (13.1 M -> 8.8 M exact evaluations per batch) | 4.56 | | |",
+           "| member pass at 768 threads per CTA (80 registers) | 4.32 | 4.73 | 8.93 (9.24 on one stream) |", "",
            "Negative results: tiles split into more units to fill whole waves (3.52 -> 3.77 ms member pass: every unit re-stages its tile);",
            "queue entries carrying doc / contribution instead of a posting index (no change: the exact kernel is bound by the plane and row sectors).",
            "cfg5 (10 M docs): BM25 stage 158 -> 69.6 ms by sizing the rounds in tiles (the 64ths plan overflowed the candidate lists in round 1,",
-           "90 ms of per-query fallback), then -> ~60 ms with the fp32-screened member pass.", "",
+           "90 ms of per-query fallback), then -> 35.7 ms with launches bounded to 2048 tiles (the exact kernel's queues overflowed) and the",
+           "fp32-screened member pass, -> 29.8 ms with the later member-pass changes; cfg5 step 162 -> 33.0 ms.", "",
+           "Also measured slower: 6 / 8 postings per thread in the join's preparation (3.56 / 4.31 ms member pass vs 3.09), 832 / 1024 threads per",
+           "member-pass CTA (3.25 / 4.24 ms; register spills), screening grabs of 2 / 4 / 16 queries (1.18 / 0.98 / 0.96 ms vs 0.91 at 8); a sampled-",
+           "histogram bound for every bound-less query at 4096 queries (+0.09 ms: their low thresholds add screening work while the per-query",
+           "kernel still runs for the overflowed ones) -- kept for batches <= 2048 queries where it removes the per-query kernel (-0.2 ms).", "",
            "Kernel-only timing experiments (ARB_BM25_DEBUG, wrong results, timing only): member pass with pairs skipped 0.60 ms (4096 queries) /",
            "0.56 ms (512) = the fixed cost; with the queue disabled 2.30 / 0.97 ms; complete 3.66 / 1.26 ms."]
     open(os.path.join(ROOT, "profiles", "r2_ncu_summary.md"), "w").write("\n".join(md) + "\n")
