@@ -22,6 +22,24 @@ def shard_range(n: int, world: int, rank: int) -> Tuple[int, int]:
     return min(n, rank * per), min(n, (rank + 1) * per)
 
 
+def grid_layout(world: int, rank: int, n_shards: int, n_rows: int, n_queries: int):
+    """``world`` GPUs as ``n_shards`` row shards x ``world / n_shards`` query groups (``bench.py --row-shards``).
+
+    Rank r holds row shard ``r % n_shards`` and serves the query slice of group ``r // n_shards``; the ranks
+    ``[g * n_shards, (g + 1) * n_shards)`` of one group exchange and merge their candidates, each finishing 1 / n_shards of
+    the group's queries.  -> dict(shard, group, rows=(lo, hi), queries=(lo, hi), peers=[ranks of the group],
+    out_queries=(lo, hi): the GLOBAL query range whose fused results this rank returns)."""
+    if n_shards < 1 or world % n_shards:
+        raise ValueError(f"{n_shards} row shards do not divide {world} GPUs")
+    n_groups = world // n_shards
+    shard, grp = rank % n_shards, rank // n_shards
+    r_lo, r_hi = shard_range(n_rows, n_shards, shard)
+    q_lo, q_hi = shard_range(n_queries, n_groups, grp)
+    o_lo, o_hi = shard_range(q_hi - q_lo, n_shards, shard) if n_shards > 1 else (0, q_hi - q_lo)
+    return {"shard": shard, "group": grp, "n_groups": n_groups, "rows": (r_lo, r_hi), "queries": (q_lo, q_hi),
+            "peers": list(range(grp * n_shards, (grp + 1) * n_shards)), "out_queries": (q_lo + o_lo, q_lo + o_hi)}
+
+
 def global_bm25_stats(doc_ptr: np.ndarray, doc_tok: np.ndarray, n_terms: int, token_base: int,
                       variant: str = "okapi", k1: float = bb.K1_DEFAULT, b: float = bb.B_DEFAULT,
                       epsilon: float = bb.EPS_DEFAULT, group=None, device: Optional[torch.device] = None) -> bb.BM25Stats:

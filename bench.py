@@ -423,12 +423,10 @@ def run_b200(a):
     def build_layout(n_shards):
         """world = n_shards row shards x n_groups query groups: rank r holds row shard r % n_shards and serves the
         query slice of group r // n_shards; the ranks of one group exchange and merge their candidates."""
-        n_groups = world // n_shards
-        shard, grp = rank % n_shards, rank // n_shards
-        per = (a.notes + n_shards - 1) // n_shards
-        row0, row1 = min(a.notes, shard * per), min(a.notes, (shard + 1) * per)
-        qper = (a.queries + n_groups - 1) // n_groups
-        q0, q1 = min(a.queries, grp * qper), min(a.queries, (grp + 1) * qper)
+        from ano_rag_b200.sharded import grid_layout
+        g_ = grid_layout(world, rank, n_shards, a.notes, a.queries)
+        n_groups, grp = g_["n_groups"], g_["group"]
+        (row0, row1), (q0, q1) = g_["rows"], g_["queries"]
         dense = engine.DenseIndex(a.dim, storage="bf16", normalize=False)
         for _, rows in synth.dense_rows(row0, row1 - row0, a.dim, dev, host_rng=True):
             dense.add(rows)

@@ -96,3 +96,25 @@ def test_query_slice_exchange_world2(tmp_path, nq):
             want = np.arange(nq * k).reshape(nq, k)[lo:hi] + 1_000_000 * src
             assert np.array_equal(got[src, : hi - lo], want)
             assert (got[src, hi - lo:] == -1).all()
+
+
+def test_grid_layout_covers_every_row_and_query_exactly_once():
+    """N GPUs = R row shards x N/R query groups (bench.py layouts): inside a group the shards tile the corpus, across groups the
+    query slices tile the batch, and the ranks' output slices tile the batch too (every query is finished by exactly one rank)."""
+    for world in (1, 2, 4, 8):
+        for r_shards in [r for r in (1, 2, 4, 8) if world % r == 0 and r <= world]:
+            for n_rows, n_q in ((1_000_000, 4096), (1001, 37), (5, 3)):
+                rows = np.zeros((world // r_shards, n_rows), dtype=np.int32)
+                served = np.zeros(n_q, dtype=np.int32)
+                out = np.zeros(n_q, dtype=np.int32)
+                for rank in range(world):
+                    g = sharded.grid_layout(world, rank, r_shards, n_rows, n_q)
+                    assert g["peers"] == list(range(g["group"] * r_shards, (g["group"] + 1) * r_shards)) and rank in g["peers"]
+                    rows[g["group"], g["rows"][0]:g["rows"][1]] += 1
+                    if g["shard"] == 0:
+                        served[g["queries"][0]:g["queries"][1]] += 1
+                    out[g["out_queries"][0]:g["out_queries"][1]] += 1
+                    assert g["queries"][0] <= g["out_queries"][0] <= g["out_queries"][1] <= g["queries"][1]
+                assert np.all(rows == 1) and np.all(served == 1) and np.all(out == 1), (world, r_shards, n_rows, n_q)
+    with pytest.raises(ValueError):
+        sharded.grid_layout(8, 0, 3, 10, 10)
