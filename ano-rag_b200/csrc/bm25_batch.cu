@@ -1207,13 +1207,14 @@ static int batch_chunk(const Bm25Dev& ix, const int32_t* d_terms, int64_t nq, in
     ARB_LAUNCH_OK();
     // ---- 1. member pass in rounds of growing size, a compaction after each.  The first round runs without a bound, so
     // every member with a positive score is a candidate: it covers ~64 tiles (16 K docs) whatever the corpus size, which
-    // keeps even heavy queries below C_CAP; each later round covers 4x (the last two 2x) the docs before it, so with the
-    // bound of the rounds before it a query collects ~3k (~k) new candidates per round, independent of the corpus size.
+    // keeps even heavy queries below C_CAP; each later round covers 4x the docs before it, so with the bound of the rounds
+    // before it a query collects ~3k new candidates per round, independent of the corpus size (an extra round at half the
+    // corpus measured slower: its launches and compaction cost more than the ~100 candidates per query it saves).
     std::vector<int64_t> cuts;                                   // ascending round ends, in tiles
     if (ix.n_tiles <= 8) cuts = {ix.n_tiles};
     else if (ix.n_tiles < 1024) cuts = {(ix.n_tiles * 4 + 63) / 64, (ix.n_tiles * 16 + 63) / 64, ix.n_tiles};   // shards of up to 256 K docs: a round costs more than it prunes
     else {
-      cuts = {ix.n_tiles, (ix.n_tiles + 1) / 2};
+      cuts = {ix.n_tiles};
       for (int64_t c = (ix.n_tiles + 3) / 4; ; c = (c + 3) / 4) { cuts.push_back(c); if (c <= 64) break; }
       std::reverse(cuts.begin(), cuts.end());
     }
