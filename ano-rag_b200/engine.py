@@ -120,6 +120,15 @@ class DenseIndex:
         nat.check(nat.lib.arb_index_reconstruct(self._h, row0, n, out.ctypes.data, 0, _stream_ptr()))
         return out
 
+    def reconstruct_device(self, row0: int = 0, n: Optional[int] = None):
+        """The stored rows as an fp32 CUDA tensor [n, dim] (no host round trip)."""
+        n = self.ntotal - row0 if n is None else n
+        dev = torch.device("cuda", torch.cuda.current_device())
+        out = torch.empty((n, self.dim), dtype=torch.float32, device=dev)
+        if n:
+            nat.check(nat.lib.arb_index_reconstruct(self._h, row0, n, out.data_ptr(), 1, _stream_ptr(dev)))
+        return out
+
     def search(self, queries, k: int, query_planes: Optional[int] = None, id_base: int = 0, out=None):
         """-> (scores fp32 [nq,k], ids int64 [nq,k]); numpy in -> numpy out, CUDA tensor in -> CUDA tensors out.
         out = (scores, ids): contiguous CUDA tensors to write into (device queries only)."""

@@ -339,10 +339,13 @@ class VectorIndex:
             else:
                 keep = np.setdiff1d(np.arange(n, dtype=np.int64), ids)
             removed = n - len(keep)
-            rows = self.index.reconstruct(0, n)[keep] if n else np.zeros((0, self.embedding_dim), np.float32)
+            # the surviving rows never leave the device: reconstruct -> gather -> re-add as they are (already normalised)
+            rows = None
+            if n and len(keep):
+                rows = self.index.reconstruct_device(0, n).index_select(0, torch.from_numpy(keep).to(f"cuda:{torch.cuda.current_device()}"))
             self.index.reset()
-            if len(rows):
-                self.index.add_prepared(rows)                                               # stored rows are already normalised
+            if rows is not None and len(rows):
+                self.index.add_prepared(rows.contiguous())
             self.total_vectors -= len(ids)                                                  # :404 (reference subtracts len(ids))
             logger.info(f"Removed {removed} vectors from index")
             return True

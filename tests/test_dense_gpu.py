@@ -159,7 +159,12 @@ def test_vector_index_dropin_matches_oracle_shaping(tmp_path):
     assert vi3.nlist == 25
     stats = vi.get_index_stats()
     assert stats["ntotal"] == 2000 and stats["index_type"] == "IVFFlat" and stats["nprobe"] == 10
-    assert vi.remove_vectors(np.array([0, 1])) and vi.index.ntotal == 1998
+    before = vi.index.reconstruct(0, 2000)
+    assert vi.remove_vectors(np.array([0, 1, 777])) and vi.index.ntotal == 1997
+    keep = np.setdiff1d(np.arange(2000), [0, 1, 777])
+    assert np.array_equal(vi.index.reconstruct(0, 1997), before[keep])       # survivors stay bit for bit (no second normalisation)
+    res = vi.search(x[[5, 778]], top_k=1)
+    assert res[0][0]["index"] == 3 and res[1][0]["index"] == 775              # faiss remove_ids semantics: later rows shift down
     vi.reset_index()
     assert vi.total_vectors == 0 and vi.search(q) == []
     config.reset()
