@@ -104,9 +104,15 @@ def choose_row_shards(a, world):
 
 
 def workload_config(a, n_gpus, row_shards=None):
-    row_shards = row_shards or n_gpus
-    groups = n_gpus // row_shards
-    layout = "none" if n_gpus == 1 else f"{row_shards} row shard(s) x {groups} query group(s)"
+    # the same string in the b200 and the reference arm: with --row-shards auto the layout is chosen by measurement and
+    # reported under the line's own "layout" / "layouts" keys, not here
+    if n_gpus == 1:
+        layout = "none"
+    elif getattr(a, "row_shards", "auto") == "auto" and a.workload == "cfg3":
+        layout = f"auto: fastest of the R row shards x {n_gpus}/R query groups layouts, R in divisors of {n_gpus}"
+    else:
+        row_shards = row_shards or n_gpus
+        layout = f"{row_shards} row shard(s) x {n_gpus // row_shards} query group(s)"
     if a.workload == "cfg4":
         return {"workload": f"cfg4 dense: {a.notes} notes x {a.dim}-d bf16 row-sharded over {n_gpus} GPU(s) "
                             f"({a.notes // n_gpus} rows each), exact IP local top-{a.topk} + peer merge, {a.queries}-query batch",

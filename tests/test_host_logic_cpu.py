@@ -109,8 +109,11 @@ def test_bench_layout_choice():
     a.row_shards = "3"
     with pytest.raises(SystemExit):
         bench.choose_row_shards(a, 8)
-    cfg = bench.workload_config(types.SimpleNamespace(workload="cfg3", notes=10, dim=4, queries=2, topk=1, vocab=5), 8, 2)
+    cfg = bench.workload_config(types.SimpleNamespace(workload="cfg3", notes=10, dim=4, queries=2, topk=1, vocab=5, row_shards="2"), 8, 2)
     assert cfg["sharding"] == "2 row shard(s) x 4 query group(s)"
+    ns = types.SimpleNamespace(workload="cfg3", notes=10, dim=4, queries=2, topk=1, vocab=5, row_shards="auto")
+    assert bench.workload_config(ns, 8, 1) == bench.workload_config(ns, 8, 4)            # both arms print the same config at N > 1
+    assert bench.workload_config(ns, 1, 1)["sharding"] == "none"
 
 
 def test_bm25_scores_accepts_any_corpus_with_get_scores():
