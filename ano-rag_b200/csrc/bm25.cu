@@ -162,6 +162,19 @@ __global__ void bm25_tt_fill_kernel(const uint32_t* __restrict__ sorted_val, int
   tt_val[i] = __dmul_rn(idf[t], gtab[gcode[p]]);
   atomicOr(tt_bloom + static_cast<int64_t>(doc[p]) * BLOOM_W + bloom_word(static_cast<uint32_t>(t)), bloom_mask(static_cast<uint32_t>(t)));
 }
+// run structure of the tile rows, static per index: the member pass joins whole runs (the postings of one term inside a
+// tile) with the batch's records and no longer rediscovers heads and lengths for every batch.  One block per tile.
+__global__ void bm25_tt_info_kernel(const uint32_t* __restrict__ tt_off, const uint32_t* __restrict__ tt_term,
+                                    const uint8_t* __restrict__ tt_doc, uint32_t* __restrict__ tt_info) {
+  const uint32_t lo = tt_off[blockIdx.x], hi = tt_off[blockIdx.x + 1];
+  for (uint32_t i = lo + threadIdx.x; i < hi; i += blockDim.x) {
+    const uint32_t t = tt_term[i];
+    const uint32_t head = (i == lo || tt_term[i - 1] != t) ? 1u : 0u;
+    uint32_t rem = 1u;                                          // a term occurs once per doc: a run holds at most 256 postings
+    while (i + rem < hi && tt_term[i + rem] == t) ++rem;
+    tt_info[i] = static_cast<uint32_t>(tt_doc[i]) | ((rem - 1u) << 8) | (head << 31);
+  }
+}
 // step 3: term id and finished contribution idf * g of every row entry
 __global__ void bm25_drow_fill_kernel(const uint32_t* __restrict__ sorted_val, int64_t n_sp, const int64_t* __restrict__ term_ptr,
                                       int64_t n_terms, const int32_t* __restrict__ gcode, const double* __restrict__ idf,
@@ -793,6 +806,7 @@ extern "C" int arb_bm25_create(arb_bm25** out, int64_t n_docs, int64_t n_terms, 
           if (cudaMalloc(&bm->tt_off, static_cast<size_t>(n_tiles + 1) * 4) != cudaSuccess ||
               cudaMalloc(&bm->tt_term, std::max<size_t>(n_sp, 1) * 4) != cudaSuccess ||
               cudaMalloc(&bm->tt_doc, std::max<size_t>(n_sp, 1) + 16) != cudaSuccess ||
+              cudaMalloc(&bm->tt_info, std::max<size_t>(n_sp, 1) * 4) != cudaSuccess ||
               cudaMalloc(&bm->tt_val, std::max<size_t>(n_sp, 1) * 8) != cudaSuccess) {
             cudaGetLastError(); set_error("arb_bm25_create: out of device memory (tile rows)"); return fail(ARB_ENOMEM);
           }
@@ -826,6 +840,8 @@ extern "C" int arb_bm25_create(arb_bm25** out, int64_t n_docs, int64_t n_terms, 
                 v_out.as<uint32_t>(), n_sp, d_ptr.as<int64_t>(), n_terms, d_doc.as<int32_t>(), d_code.as<int32_t>(), bm->idf, bm->gtab,
                 bm->tt_term, bm->tt_doc, bm->tt_val, bm->tt_bloom);
             count_launch();
+            bm25_tt_info_kernel<<<static_cast<unsigned>(n_tiles), 256, 0, st>>>(bm->tt_off, bm->tt_term, bm->tt_doc, bm->tt_info);
+            count_launch();
           }
         }
         e = cudaStreamSynchronize(st);
@@ -855,7 +871,7 @@ extern "C" int arb_bm25_create(arb_bm25** out, int64_t n_docs, int64_t n_terms, 
   bm->dev.plane_gmax = bm->plane_tmax ? bm->plane_tmax + static_cast<size_t>(bm->dev.n_tiles) * bm->dev.n_planes : nullptr;
   bm->dev.planes32 = bm->planes32;
   bm->dev.drow_off = bm->drow_off; bm->dev.drow_term = bm->drow_term; bm->dev.drow_val = bm->drow_val;
-  bm->dev.tt_off = bm->tt_off; bm->dev.tt_term = bm->tt_term; bm->dev.tt_doc = bm->tt_doc; bm->dev.tt_val = bm->tt_val;
+  bm->dev.tt_off = bm->tt_off; bm->dev.tt_term = bm->tt_term; bm->dev.tt_doc = bm->tt_doc; bm->dev.tt_info = bm->tt_info; bm->dev.tt_val = bm->tt_val;
   bm->dev.tt_bloom = bm->tt_bloom;
   *out = bm;
   return ARB_OK;
@@ -879,6 +895,7 @@ extern "C" int arb_bm25_destroy(arb_bm25* bm) {
   if (bm->tt_off) cudaFree(bm->tt_off);
   if (bm->tt_term) cudaFree(bm->tt_term);
   if (bm->tt_doc) cudaFree(bm->tt_doc);
+  if (bm->tt_info) cudaFree(bm->tt_info);
   if (bm->tt_val) cudaFree(bm->tt_val);
   if (bm->tt_bloom) cudaFree(bm->tt_bloom);
   delete bm;

@@ -63,6 +63,7 @@ struct Bm25Dev {
   const uint32_t* tt_off;       // [n_tiles + 1]
   const uint32_t* tt_term;      // [n_sp]
   const uint8_t* tt_doc;        // [n_sp] doc inside the tile
+  const uint32_t* tt_info;      // [n_sp] doc inside the tile | (postings from here to the end of the term's run - 1) << 8 | first of its run << 31
   const double* tt_val;         // [n_sp]
   const uint32_t* tt_bloom;     // [n_tiles * 256 * BLOOM_W] per-doc filter of the doc's sparse terms (bloom_word / bloom_mask)
 };
@@ -116,6 +117,7 @@ struct arb_bm25 {
   uint32_t* tt_off = nullptr;
   uint32_t* tt_term = nullptr;
   uint8_t* tt_doc = nullptr;
+  uint32_t* tt_info = nullptr;
   double* tt_val = nullptr;
   uint32_t* tt_bloom = nullptr;
   std::vector<int64_t> df;      // host copy of per-term df (roofline accounting)

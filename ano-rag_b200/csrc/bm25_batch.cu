@@ -428,42 +428,26 @@ bm25_member_kernel(const Bm25Dev ix, const BatchScratch sc, int64_t tile_lo, int
     const int64_t doc_base = tile * PLANE_TILE;
     for (uint32_t c0 = o_lo; c0 < o_hi; c0 += ch) {
       const int n_ch = static_cast<int>(min(static_cast<uint32_t>(ch), o_hi - c0));
-      // ---- runs (thread t owns postings MJ_PPT * t ..): head flags, record ranges
-      uint32_t rcnt[MJ_PPT];
-      {
-        uint32_t prev = 0xFFFFFFFFu;
-        if (tid * MJ_PPT < n_ch && tid > 0) prev = __ldg(ix.tt_term + c0 + tid * MJ_PPT - 1);
-#pragma unroll
-        for (int e = 0; e < MJ_PPT; ++e) {
-          const int i = tid * MJ_PPT + e;
-          rcnt[e] = 0u;
-          if (i < n_ch) {
-            const uint32_t t = __ldg(ix.tt_term + c0 + i);
-            uint32_t info = __ldg(ix.tt_doc + c0 + i);
-            if (t != prev) {                                   // first posting of a run (a chunk boundary starts one too)
-              const uint2 be = __ldg(sc.bt_ent + t);
-              rcnt[e] = be.y;
-              cbase[i] = be.x;
-              info |= 0x80000000u;
-            }
-            pinfo[i] = info;
-            prev = t;
-          }
-        }
-      }
-      __syncthreads();
-      // ---- run lengths, pairs per run = records x docs, exclusive scan
+      // ---- runs (thread t owns postings MJ_PPT * t ..): the index knows where a term's run starts and how far it goes
+      // (tt_info); a run head -- and the first posting of the chunk, which may sit inside a run -- looks up the term's
+      // records in the batch: pairs of the run = records x docs
       uint32_t cnt[MJ_PPT];
       uint32_t tsum = 0u;
 #pragma unroll
       for (int e = 0; e < MJ_PPT; ++e) {
         const int i = tid * MJ_PPT + e;
         cnt[e] = 0u;
-        if (i < n_ch && (pinfo[i] >> 31)) {
-          int len = 1;
-          while (i + len < n_ch && !(pinfo[i + len] >> 31)) ++len;
-          pinfo[i] |= static_cast<uint32_t>(len) << 8;
-          cnt[e] = rcnt[e] * static_cast<uint32_t>(len);
+        if (i < n_ch) {
+          const uint32_t info = __ldg(ix.tt_info + c0 + i);
+          uint32_t out = info & 0xFFu;
+          if ((info >> 31) || i == 0) {
+            const uint2 be = __ldg(sc.bt_ent + __ldg(ix.tt_term + c0 + i));
+            const uint32_t len = min(((info >> 8) & 0xFFu) + 1u, static_cast<uint32_t>(n_ch - i));
+            cbase[i] = be.x;
+            out |= (len << 8) | 0x80000000u;
+            cnt[e] = be.y * len;
+          }
+          pinfo[i] = out;
         }
         tsum += cnt[e];
       }
