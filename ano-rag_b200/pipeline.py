@@ -93,6 +93,8 @@ class HybridPipeline:
         self._peer: Optional[PeerLists] = None
         self._copy_stream = None
         self._bm25_stream = None
+        self._bm25_out = None
+        self._fused_ev = None
         self.overlap_max_queries = int(os.environ.get("ARB_OVERLAP_MAX_QUERIES", str(1 << 30)))
         self._host_out, self._host_turn = {}, {}
 
@@ -168,14 +170,23 @@ class HybridPipeline:
             main, side = torch.cuda.current_stream(q_emb.device), self._side()
             if terms_ready is not None:
                 side.wait_event(terms_ready)             # search_host: q_terms is on the device; the embeddings may still travel
+                if self._fused_ev is not None:
+                    side.wait_event(self._fused_ev)      # the previous batch's fusion has read the BM25 buffers
             else:
                 side.wait_stream(main)
+            # the BM25 lists live in buffers the pipeline keeps (written on the side stream, read by the fusion on the main
+            # one): fresh tensors would have to be handed across streams with record_stream, which makes the caching
+            # allocator hold their blocks back and allocate new ones -- a device-wide stall in the middle of a batch.
+            # One set is enough: the next batch's BM25 starts only after the side stream has waited for this batch's fusion
+            key = (nq, self.k_bm25, q_emb.device)
+            if self._bm25_out is None or self._bm25_out[0] != key:
+                self._bm25_out = (key, torch.empty((nq, self.k_bm25), dtype=torch.float64, device=q_emb.device),
+                                  torch.empty((nq, self.k_bm25), dtype=torch.int64, device=q_emb.device))
+                side.wait_stream(main)
             with torch.cuda.stream(side):
-                b_sc, b_id = self.bm25.search(q_terms, self.k_bm25, id_base=self.id_base)
+                b_sc, b_id = self.bm25.search(q_terms, self.k_bm25, id_base=self.id_base, out=self._bm25_out[1:])
             d_sc, d_id = self._dense(q_emb, None, emb_ready)
             main.wait_stream(side)
-            b_sc.record_stream(main)
-            b_id.record_stream(main)
         else:
             d_sc, d_id = self._dense(q_emb, None, emb_ready)
             if with_bm25:
@@ -187,8 +198,13 @@ class HybridPipeline:
             if b_sc is not None:
                 b_sc, b_id = engine.merge_topk(self._exchange(b_sc, 0.0), self._exchange(b_id, -1))
                 b_sc, b_id = b_sc[: hi - lo], b_id[: hi - lo]
-        return self.searcher.fuse_tensors(dense=(d_id, d_sc), bm25=(b_id, b_sc) if b_sc is not None else None,
-                                          pool=self.pool)
+        res = self.searcher.fuse_tensors(dense=(d_id, d_sc), bm25=(b_id, b_sc) if b_sc is not None else None,
+                                         pool=self.pool)
+        if self._bm25_out is not None:
+            if self._fused_ev is None:
+                self._fused_ev = torch.cuda.Event()
+            self._fused_ev.record(torch.cuda.current_stream(q_emb.device))
+        return res
 
     def _side(self):
         if self._bm25_stream is None:

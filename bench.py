@@ -538,7 +538,7 @@ def run_b200(a):
         prof = nat.profile_collect()
         nat.profile(False)
         ms_one_stream = max_over_ranks(e0.elapsed_time(e1)) / a.steps
-        pipe.overlap_max_queries = saved_overlap
+        pipe.overlap_max_queries = saved_overlap if ms_step <= ms_one_stream else 0        # e2e runs the faster mode
         # ---- end to end: pinned host inputs, host outputs
         q_emb_h = q_emb.to(torch.float32).cpu().pin_memory()                          # encoder output is fp32 on the host
         q_terms_p = torch.from_numpy(np.ascontiguousarray(lay["q_terms_h"])).pin_memory()
@@ -554,7 +554,12 @@ def run_b200(a):
         h2d = q_emb_h.numel() * 4 + q_terms_p.numel() * 4
         d2h = sum(int(r.nbytes) for r in res)
         res = tuple(np.array(r, copy=True) for r in res)
-        return {"ms_step": ms_step, "ms_one_stream": ms_one_stream, "value": a.queries / (ms_step * 1e-3), "warmup": n_warm, "launches": int(launches),
+        # the headline is the faster of the two stream modes of the same public call (both timed over exactly a.steps steps)
+        ms_two_streams = ms_step
+        if ms_one_stream < ms_step:
+            ms_step = ms_one_stream
+        return {"ms_step": ms_step, "ms_one_stream": ms_one_stream, "ms_two_streams": ms_two_streams,
+                "value": a.queries / (ms_step * 1e-3), "warmup": n_warm, "launches": int(launches),
                 "prof": prof, "clocks": clocks, "res": res,
                 "e2e": {"value": a.queries / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
                         "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms}}
@@ -568,7 +573,7 @@ def run_b200(a):
     m = measure(lay, sampler if rank == 0 else None)
     pipe, prof, res, e2e, clocks = lay["pipe"], m["prof"], m["res"], m["e2e"], m["clocks"]
     ms_step, value, n_warm, launches = m["ms_step"], m["value"], m["warmup"], m["launches"]
-    ms_one_stream = m["ms_one_stream"]
+    ms_one_stream, ms_two_streams = m["ms_one_stream"], m["ms_two_streams"]
     row0, row1 = lay["rows"]
     q_local = lay["queries"][1] - lay["queries"][0]
     local_postings = lay["local_postings"]
@@ -657,7 +662,7 @@ def run_b200(a):
     if world > 1 and a.row_shards == "auto":
         def describe(lay_x, m_x, h_x):
             return {"row_shards": lay_x["n_shards"], "query_groups": lay_x["n_groups"], "value": m_x["value"], "unit": UNIT,
-                    "ms_per_step": m_x["ms_step"], "ms_per_step_one_stream": m_x["ms_one_stream"], "e2e": m_x["e2e"], "gpu_launches": m_x["launches"],
+                    "ms_per_step": m_x["ms_step"], "ms_per_step_one_stream": m_x["ms_one_stream"], "ms_per_step_two_streams": m_x["ms_two_streams"], "e2e": m_x["e2e"], "gpu_launches": m_x["launches"],
                     "exchange": lay_x["pipe"].exchange if lay_x["n_shards"] > 1 else "none", "result_hash": h_x,
                     "parity": bool(h_x == headline_hash) if rank == 0 else None,
                     "stages_ms": {k: v[0] / max(1, v[1]) for k, v in m_x["prof"].items() if v[1]}}
@@ -686,7 +691,7 @@ def run_b200(a):
             lay, m2 = best[1], best[2]
             n_shards = lay["n_shards"]
             prof, e2e, ms_step, value, launches = m2["prof"], m2["e2e"], m2["ms_step"], m2["value"], m2["launches"]
-            ms_one_stream = m2["ms_one_stream"]
+            ms_one_stream, ms_two_streams = m2["ms_one_stream"], m2["ms_two_streams"]
             row0, row1 = lay["rows"]
             q_local = lay["queries"][1] - lay["queries"][0]
             local_postings = lay["local_postings"]
@@ -811,9 +816,9 @@ def run_b200(a):
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": n_gpus, "steps": a.steps, "warmup": n_warm,
                 "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
                 "dtype": "bf16", "data": "synthetic", "config": workload_config(a, n_gpus, n_shards), "e2e": e2e,
-                "ms_per_step_one_stream": ms_one_stream,
-                "stages_note": "stage and kernel durations (stages, roofline) come from a second pass of the same step with the dense and "
-                               "the BM25 source on one stream; the headline runs them on two streams",
+                "ms_per_step_one_stream": ms_one_stream, "ms_per_step_two_streams": ms_two_streams,
+                "stages_note": "stage and kernel durations (stages, roofline) come from a pass of the same step with the dense and the BM25 "
+                               "source on one stream; ms_per_step is the faster of the two stream modes, each timed over exactly `steps` steps",
                 "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "stages": stages,
                 "cpu_baseline": cpu_baseline, "parity": parity, "result_hash": headline_hash, "latency_ms": latency, "reference_shaped_api": api_shaped,
                 "row_sharded": row_sharded, "replicated": replicated, "layouts": layouts, "replicas_weak": replicas_weak, "cfg4": cfg4, "impl": "b200",
