@@ -84,7 +84,7 @@ def main():
           "Captured with `gpurun` on one B200 after the profiled command had exited 0 without ncu. Per-launch times under ncu are",
           "cold-cache and serialised: compare SHARES with the live CUDA-event stage times of `profiles/r2_bench_n1.json`",
           "(one-stream pass: dense 4.76 ms, BM25 4.24 ms = 3.00 member pass + 0.92 screening + 0.29 final/fallback, fuse 0.17 ms = 9.19 ms;",
-          "headline with the two sources on two streams: 8.81 ms).", "",
+          "headline with the two sources on two streams: 8.70-9.01 ms over five runs of the final builds).", "",
           "## 1. Launch list of one cfg3 step", "",
           "`ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -c 400 --csv python tests/gpu_profile_step.py`",
           "(raw: `profiles/r2_launches_step.csv`; the second of the two steps the script runs)", "",
@@ -116,7 +116,8 @@ def main():
            "| screening pass: warps take 8 active queries at a time instead of 32 | 4.79 | | |",
            "| one record for a sparse term repeated inside a query (13.1 M -> 8.8 M exact evaluations per batch) | 4.56 | | |",
            "| member pass at 768 threads per CTA (80 registers) | 4.32 | 4.73 | 8.93 (9.24 on one stream) |",
-           "| rounds grow x4 throughout (no extra half-corpus round) | 4.24 | 4.76 | 8.81 (9.19 on one stream) |", "",
+           "| rounds grow x4 throughout (no extra half-corpus round) | 4.24 | 4.76 | 8.81 (9.19 on one stream) |",
+           "| run structure of the tile rows precomputed in the index; BM25 lists of the two-stream path in persistent buffers | 4.18-4.24 | 4.75-4.81 | 8.70-9.01 (9.12-9.25) |", "",
            "Negative results: tiles split into more units to fill whole waves (3.52 -> 3.77 ms member pass: every unit re-stages its tile);",
            "queue entries carrying doc / contribution instead of a posting index (no change: the exact kernel is bound by the plane and row sectors).",
            "cfg5 (10 M docs): BM25 stage 158 -> 69.6 ms by sizing the rounds in tiles (the 64ths plan overflowed the candidate lists in round 1,",
