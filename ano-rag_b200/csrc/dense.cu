@@ -587,6 +587,14 @@ dense_topk_pair_kernel(const __grid_constant__ CUtensorMap tmap_a,
 }
 
 
+// warp_select for the merge kernel's shared-memory buffers as a real function: the merge kernel calls it from inside
+// loops that are unrolled EPL times, and inlining it there (up to 32 copies per instantiation, nine instantiations)
+// cost minutes of compile time for a path that runs once per overflowing list.
+template <int EPL>
+__device__ __noinline__ uint32_t warp_select_shared(uint2* list, int cnt, int k, int lane) {
+  return warp_select<EPL, false>(list, cnt, k, lane);
+}
+
 // ----------------------------------------------------------------------------
 // Merge the per-item candidate lists of each query into its final top-k.
 // One CTA of MERGE_WARPS warps per query: the lists are dealt round-robin to the warps, every list is fetched
@@ -655,7 +663,7 @@ dense_merge_kernel(const DenseParams p, int64_t id_base, float* __restrict__ out
           if (pass) buf[cnt + __popc(m & lt)] = e[i];
           cnt += __popc(m);
           if (cnt > C - 32) {
-            const uint32_t T = warp_select<EPL, false>(buf, cnt, p.k, lane);
+            const uint32_t T = warp_select_shared<EPL>(buf, cnt, p.k, lane);
             cnt = p.k;
             thr_key = max(thr_key, T);
             if (lane == 0) atomicMax(&s_thr, T);
@@ -666,7 +674,7 @@ dense_merge_kernel(const DenseParams p, int64_t id_base, float* __restrict__ out
     cur = nxt; n_cur = n_nxt;
   }
   __syncwarp();
-  if (cnt > p.k) { warp_select<EPL, false>(buf, cnt, p.k, lane); cnt = p.k; }
+  if (cnt > p.k) { warp_select_shared<EPL>(buf, cnt, p.k, lane); cnt = p.k; }
   if (lane == 0) s_cnt[warp] = cnt;
   __syncthreads();
   if (warp != 0) return;
@@ -683,14 +691,14 @@ dense_merge_kernel(const DenseParams p, int64_t id_base, float* __restrict__ out
       if (pass) buf[cnt + __popc(m & lt)] = e;
       cnt += __popc(m);
       if (cnt > C - 32) {
-        const uint32_t T = warp_select<EPL, false>(buf, cnt, p.k, lane);
+        const uint32_t T = warp_select_shared<EPL>(buf, cnt, p.k, lane);
         cnt = p.k;
         thr_key = max(thr_key, T);
       }
     }
   }
   __syncwarp();
-  if (cnt > p.k) { warp_select<EPL, false>(buf, cnt, p.k, lane); cnt = p.k; }
+  if (cnt > p.k) { warp_select_shared<EPL>(buf, cnt, p.k, lane); cnt = p.k; }
   __syncwarp();
   // rank by (score desc, id asc): cnt <= k <= 256, O(cnt^2 / 32) per lane
   for (int j = lane; j < cnt; j += 32) {
