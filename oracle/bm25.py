@@ -5,8 +5,12 @@
 * ``BM25OkapiOracle`` restates ``rank_bm25.BM25Okapi`` (rank_bm25 0.2.x; the
   reference does not pin it and it is not in requirements.txt -- optional import
   at ``utils/bm25_search.py:7-13``, constructed with library defaults k1=1.5,
-  b=0.75, epsilon=0.25 at ``:273``).  PARITY UNPINNED: the library is not
-  installed here; the restatement follows its published algorithm.
+  b=0.75, epsilon=0.25 at ``:273``).  The library is not installed here; the
+  restatement follows its published algorithm and is PINNED ONLY to the one
+  library-held vector available offline, the known answer of rank_bm25's README
+  (corpus of three sentences, query "windy London" -> [0., 0.93729472, 0.];
+  tests/test_oracle_golden.py::test_okapi_oracle_reproduces_rank_bm25_readme_vector).
+  Beyond that vector: PARITY UNPINNED.
 * ``bm25_scores`` restates the wrapper ``utils/bm25_search.py:286-340``.
 
 All arithmetic is IEEE float64 in the reference's operation order; that order is
